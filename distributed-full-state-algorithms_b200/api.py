@@ -1,0 +1,252 @@
+"""ctypes binding of the drop-in host API (libdfsa_host.so -> host/*.hpp -> libdfsa_b200.so -> CUDA).
+
+`DeviceState` mirrors the reference's StateVector / DensityMatrix plus one method per public API function,
+named like the op tuples the tests use (sv_oneTargGate, dm_damping, ...). Nothing here computes: every call
+goes to the native libraries, and a missing library or GPU raises DfsaError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_dev = None
+_host = None
+
+
+class DfsaError(RuntimeError):
+    pass
+
+
+def device_lib():
+    """libdfsa_b200.so (thin C-ABI over the CUDA kernels and transports)."""
+    global _dev
+    if _dev is None:
+        path = os.path.join(_PKG, "libdfsa_b200.so")
+        if not os.path.exists(path):
+            raise DfsaError("libdfsa_b200.so is not built (run __graft_entry__.build()); there is no CPU fallback")
+        _dev = C.CDLL(path, mode=C.RTLD_GLOBAL)
+        _dev.dfsa_last_error.restype = C.c_char_p
+        _dev.dfsa_version.restype = C.c_char_p
+        _dev.dfsa_comm_transport.restype = C.c_char_p
+        _dev.dfsa_stream_compute.restype = C.c_void_p
+        _dev.dfsa_state_ptr.restype = C.c_void_p
+        _dev.dfsa_state_ptr.argtypes = [C.c_void_p, C.c_int]
+        _dev.dfsa_state_num_amps_per_node.restype = C.c_uint64
+        _dev.dfsa_state_num_amps_per_node.argtypes = [C.c_void_p]
+    return _dev
+
+
+def host_lib():
+    """libdfsa_host.so (extern "C" face of the C++ drop-in headers)."""
+    global _host
+    if _host is None:
+        device_lib()
+        path = os.path.join(_PKG, "libdfsa_host.so")
+        if not os.path.exists(path):
+            raise DfsaError("libdfsa_host.so is not built (run __graft_entry__.build())")
+        h = C.CDLL(path)
+        for name in ("dfsa_host_StateVector_new", "dfsa_host_DensityMatrix_new", "dfsa_host_dm_partialTrace", "dfsa_host_state_handle"):
+            getattr(h, name).restype = C.c_void_p
+        h.dfsa_host_state_numAmpsPerNode.restype = C.c_uint64
+        h.dfsa_host_state_getNorm2.restype = C.c_double
+        h.dfsa_host_comm_getRank.restype = C.c_uint
+        h.dfsa_host_comm_getNumNodes.restype = C.c_uint
+        _host = h
+    return _host
+
+
+def check(rc):
+    if rc != 0:
+        raise DfsaError("libdfsa_b200 call failed (%d): %s" % (rc, device_lib().dfsa_last_error().decode()))
+
+
+def comm_init():
+    """comm_init(): joins the job described by RANK/WORLD_SIZE (torchrun-style) or runs single-rank.
+    Uses the non-aborting C-ABI entry so that 'no GPU' surfaces as an exception."""
+    check(device_lib().dfsa_comm_init())
+
+
+def comm_init_with_id(rank, size, unique_id, device=-1):
+    buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+    check(device_lib().dfsa_comm_init_with_id(int(rank), int(size), buf, int(device)))
+
+
+def comm_unique_id():
+    buf = (C.c_char * 128)()
+    check(device_lib().dfsa_comm_get_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_end():
+    check(device_lib().dfsa_comm_finalize())
+
+
+def comm_rank():
+    return int(device_lib().dfsa_comm_rank())
+
+
+def comm_size():
+    return int(device_lib().dfsa_comm_size())
+
+
+def comm_synch():
+    check(device_lib().dfsa_comm_barrier())
+
+
+def _u32(xs):
+    xs = [int(x) for x in np.asarray(xs).reshape(-1)]
+    return (C.c_uint * max(len(xs), 1))(*xs), len(xs)
+
+
+def _cplx(a):
+    a = np.ascontiguousarray(a, dtype=np.complex128)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class DeviceState:
+    """StateVector ("sv") or DensityMatrix ("dm") of the host API, amplitudes resident in HBM."""
+
+    def __init__(self, kind, num_qubits, _ptr=None):
+        h = host_lib()
+        # fail with an exception (not the C++ layer's abort) when there is no device
+        check(device_lib().dfsa_device_sync())
+        self.kind = kind
+        self.num_qubits = int(num_qubits)
+        if _ptr is not None:
+            self.p = C.c_void_p(_ptr)
+        elif kind == "dm":
+            self.p = C.c_void_p(h.dfsa_host_DensityMatrix_new(self.num_qubits))
+        else:
+            self.p = C.c_void_p(h.dfsa_host_StateVector_new(self.num_qubits))
+        self.total_bits = (2 if kind == "dm" else 1) * self.num_qubits
+        self.num_amps_per_node = int(h.dfsa_host_state_numAmpsPerNode(self.p))
+        self.log_num_amps_per_node = int(h.dfsa_host_state_logNumAmpsPerNode(self.p))
+        self.values = []
+
+    def close(self):
+        if getattr(self, "p", None):
+            host_lib().dfsa_host_state_delete(self.p)
+            self.p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return C.c_void_p(host_lib().dfsa_host_state_handle(self.p))
+
+    # ---- state I/O
+    def set_amps(self, amps):
+        a, ptr = _cplx(amps)
+        assert a.size == 1 << self.total_bits
+        host_lib().dfsa_host_state_setAllVecAmps(self.p, ptr)
+
+    def get_amps(self):
+        out = np.empty(1 << self.total_bits, dtype=np.complex128)
+        host_lib().dfsa_host_state_getAllVecAmps(self.p, out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def get_local_amps(self):
+        out = np.empty(self.num_amps_per_node, dtype=np.complex128)
+        check(device_lib().dfsa_state_download(self.handle, 0, C.c_uint64(0), C.c_uint64(self.num_amps_per_node), out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def init_hash(self, seed):
+        host_lib().dfsa_host_state_setHashAmps(self.p, C.c_ulonglong(seed))
+
+    def norm2(self):
+        return float(host_lib().dfsa_host_state_getNorm2(self.p))
+
+    # ---- state-vector API
+    def sv_oneTargGate(self, target, gate):
+        g, p = _cplx(gate)
+        host_lib().dfsa_host_sv_oneTargGate(self.p, int(target), p)
+
+    def sv_manyCtrlOneTargGate(self, ctrls, target, gate):
+        g, p = _cplx(gate)
+        c, n = _u32(ctrls)
+        host_lib().dfsa_host_sv_manyCtrlOneTargGate(self.p, c, n, int(target), p)
+
+    def sv_swapGate(self, q1, q2):
+        host_lib().dfsa_host_sv_swapGate(self.p, int(q1), int(q2))
+
+    def sv_manyTargGate(self, targets, gate):
+        g, p = _cplx(gate)
+        t, n = _u32(targets)
+        host_lib().dfsa_host_sv_manyTargGate(self.p, t, n, p)
+
+    def sv_pauliTensor(self, targets, paulis):
+        t, n = _u32(targets)
+        q, _ = _u32(paulis)
+        host_lib().dfsa_host_sv_pauliTensor(self.p, t, q, n)
+
+    def sv_pauliGadget(self, targets, paulis, theta):
+        t, n = _u32(targets)
+        q, _ = _u32(paulis)
+        host_lib().dfsa_host_sv_pauliGadget(self.p, t, q, n, C.c_double(theta))
+
+    def sv_phaseGadget(self, targets, theta):
+        t, n = _u32(targets)
+        host_lib().dfsa_host_sv_phaseGadget(self.p, t, n, C.c_double(theta))
+
+    # ---- density-matrix API
+    def dm_manyTargGate(self, targets, gate):
+        g, p = _cplx(gate)
+        t, n = _u32(targets)
+        host_lib().dfsa_host_dm_manyTargGate(self.p, t, n, p)
+
+    def dm_swapGate(self, q1, q2):
+        host_lib().dfsa_host_dm_swapGate(self.p, int(q1), int(q2))
+
+    def dm_pauliTensor(self, targets, paulis):
+        t, n = _u32(targets)
+        q, _ = _u32(paulis)
+        host_lib().dfsa_host_dm_pauliTensor(self.p, t, q, n)
+
+    def dm_pauliGadget(self, targets, paulis, theta):
+        t, n = _u32(targets)
+        q, _ = _u32(paulis)
+        host_lib().dfsa_host_dm_pauliGadget(self.p, t, q, n, C.c_double(theta))
+
+    def dm_phaseGadget(self, targets, theta):
+        t, n = _u32(targets)
+        host_lib().dfsa_host_dm_phaseGadget(self.p, t, n, C.c_double(theta))
+
+    def dm_krausMap(self, targets, kraus_ops):
+        k, p = _cplx(np.stack([np.asarray(m, dtype=np.complex128) for m in kraus_ops]))
+        t, n = _u32(targets)
+        host_lib().dfsa_host_dm_krausMap(self.p, p, len(kraus_ops), t, n)
+
+    def dm_oneQubitDephasing(self, q, prob):
+        host_lib().dfsa_host_dm_oneQubitDephasing(self.p, int(q), C.c_double(prob))
+
+    def dm_twoQubitDephasing(self, q1, q2, prob):
+        host_lib().dfsa_host_dm_twoQubitDephasing(self.p, int(q1), int(q2), C.c_double(prob))
+
+    def dm_oneQubitDepolarising(self, q, prob):
+        host_lib().dfsa_host_dm_oneQubitDepolarising(self.p, int(q), C.c_double(prob))
+
+    def dm_twoQubitDepolarising(self, q1, q2, prob, corrected=False):
+        host_lib().dfsa_host_dm_twoQubitDepolarising(self.p, int(q1), int(q2), C.c_double(prob), int(bool(corrected)))
+
+    def dm_damping(self, q, prob):
+        host_lib().dfsa_host_dm_damping(self.p, int(q), C.c_double(prob))
+
+    def dm_expecPauliString(self, coeffs, paulis):
+        coeffs = np.ascontiguousarray(coeffs, dtype=np.float64)
+        p, n = _u32(paulis)
+        assert n == coeffs.size * self.num_qubits
+        out = (C.c_double * 2)()
+        host_lib().dfsa_host_dm_expecPauliString(self.p, coeffs.ctypes.data_as(C.POINTER(C.c_double)), coeffs.size, p, out)
+        v = complex(out[0], out[1])
+        self.values.append(v)
+        return v
+
+    def dm_partialTrace(self, targets):
+        t, n = _u32(targets)
+        ptr = host_lib().dfsa_host_dm_partialTrace(self.p, t, n)
+        return DeviceState("dm", self.num_qubits - n, _ptr=ptr)

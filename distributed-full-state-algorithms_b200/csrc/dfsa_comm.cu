@@ -1,0 +1,474 @@
+// dfsa_comm.cu -- process bootstrap and the pairwise amplitude exchange of libdfsa_b200.so.
+//
+// Replaces src/communication.hpp of the reference (MPI_Init/Barrier/Isend/Irecv/Waitall/Allreduce). One process
+// per GPU. Two transports behind the same dfsa_x_* calls:
+//   "nccl": ncclSend + ncclRecv in one group on the comm stream (NVLink 5 / NVSwitch between the GPUs of one box);
+//           stream-ordered against the compute stream with events -- no host synchronisation on the data path.
+//   "ipc" : cudaIpc-mapped peer shards + cudaMemcpyAsync puts, host-mediated pair barriers in shared memory.
+//           Works for several ranks on ONE device (NCCL refuses that), which is what lets the multi-rank parity
+//           tests run on a single-GPU box; it is also the groundwork for the fused remote-load kernels.
+// Host side channel: one POSIX shared-memory page set (barrier, NCCL id, IPC handle registry, reduce slots).
+#include <errno.h>
+#include <fcntl.h>
+#include <map>
+#include <nccl.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <sys/wait.h>
+#include <time.h>
+#include <unistd.h>
+#include <vector>
+
+#include "dfsa_internal.cuh"
+
+namespace {
+
+constexpr int      MAXP = 16;
+constexpr int      MAXALLOC = 128;
+constexpr uint32_t SHM_MAGIC = 0xDF5AB200u;
+
+struct AllocSlot {
+    cudaIpcMemHandle_t handle;
+    uint64_t           bytes;
+    volatile int       valid;
+};
+
+struct Shm {
+    volatile uint32_t magic;
+    int               size;
+    volatile int      barrierCount, barrierSense;
+    volatile int      idReady;
+    char              ncclId[128];
+    double            reduce[MAXP][2];
+    volatile uint64_t pairSeq[MAXP][MAXP];
+    AllocSlot         alloc[MAXP][MAXALLOC];
+};
+
+struct CommState {
+    Shm*        shm = nullptr;
+    bool        shmOwner = false;
+    std::string shmName;
+    int         localSense = 0;
+    ncclComm_t  nccl = nullptr;
+    bool        forked = false;
+    std::vector<pid_t> children;
+    bool        slotUsed[MAXALLOC] = {};
+    void*       localPtr[MAXALLOC] = {};
+    std::map<std::pair<int, int>, void*> peerMap;   // (rank, slot) -> mapped device pointer
+    uint64_t    pairCount[MAXP] = {};
+};
+
+CommState g_comm;
+
+#define DFSA_NCCL(call)                                                                              \
+    do {                                                                                             \
+        ncclResult_t r_ = (call);                                                                    \
+        if (r_ != ncclSuccess) {                                                                     \
+            dfsaSetError("%s:%d: %s -> %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_));      \
+            return DFSA_ERR_NCCL;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+void napBriefly() {
+    struct timespec ts = {0, 50000};
+    nanosleep(&ts, nullptr);
+}
+
+int shmBarrier() {
+    Shm* m = g_comm.shm;
+    if (!m || m->size == 1) return DFSA_OK;
+    g_comm.localSense = !g_comm.localSense;
+    if (__sync_add_and_fetch(&m->barrierCount, 1) == m->size) {
+        m->barrierCount = 0;
+        __sync_synchronize();
+        m->barrierSense = g_comm.localSense;
+    } else {
+        uint64_t spins = 0;
+        while (m->barrierSense != g_comm.localSense) {
+            if (++spins > 2000) napBriefly();
+            if (spins > 40000000ULL) { dfsaSetError("host barrier timed out (a rank died?)"); return DFSA_ERR_COMM; }
+        }
+    }
+    __sync_synchronize();
+    return DFSA_OK;
+}
+
+// both partners call this the same number of times; returns once the partner has arrived too
+int pairBarrier(int pair) {
+    Shm* m = g_comm.shm;
+    DfsaContext& c = dfsaCtx();
+    uint64_t mine = ++g_comm.pairCount[pair];
+    __sync_synchronize();
+    m->pairSeq[c.rank][pair] = mine;
+    uint64_t spins = 0;
+    while (m->pairSeq[pair][c.rank] < mine) {
+        if (++spins > 2000) napBriefly();
+        if (spins > 40000000ULL) { dfsaSetError("pair barrier with rank %d timed out", pair); return DFSA_ERR_COMM; }
+    }
+    __sync_synchronize();
+    return DFSA_OK;
+}
+
+int mapShm(const char* name, bool create, int size) {
+    size_t bytes = sizeof(Shm);
+    int fd = -1;
+    if (create) {
+        shm_unlink(name);
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        if (fd < 0 || ftruncate(fd, (off_t)bytes) != 0) { dfsaSetError("shm_open/ftruncate(%s) failed: %s", name, strerror(errno)); return DFSA_ERR_COMM; }
+    } else {
+        for (int tries = 0; tries < 600000; tries++) {       // up to ~60 s
+            fd = shm_open(name, O_RDWR, 0600);
+            if (fd >= 0) {
+                struct stat st;
+                if (fstat(fd, &st) == 0 && (size_t)st.st_size >= bytes) break;
+                close(fd); fd = -1;
+            }
+            struct timespec ts = {0, 100000};
+            nanosleep(&ts, nullptr);
+        }
+        if (fd < 0) { dfsaSetError("rank 0 never created the shared segment %s", name); return DFSA_ERR_COMM; }
+    }
+    void* mem = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (mem == MAP_FAILED) { dfsaSetError("mmap of %s failed: %s", name, strerror(errno)); return DFSA_ERR_COMM; }
+    g_comm.shm = (Shm*)mem;
+    if (create) {
+        memset(mem, 0, bytes);
+        g_comm.shm->size = size;
+        __sync_synchronize();
+        g_comm.shm->magic = SHM_MAGIC;
+    } else {
+        for (uint64_t spins = 0; g_comm.shm->magic != SHM_MAGIC; spins++) {
+            napBriefly();
+            if (spins > 1200000) { dfsaSetError("shared segment %s never became ready", name); return DFSA_ERR_COMM; }
+        }
+    }
+    return DFSA_OK;
+}
+
+int finishInit() {
+    DfsaContext& c = dfsaCtx();
+    c.initialised = true;
+    if (c.size == 1) { c.transport = Transport::Single; return dfsaEnsureDevice(); }
+
+    int devCount = 0;
+    cudaError_t e = cudaGetDeviceCount(&devCount);
+    if (e != cudaSuccess || devCount == 0) { dfsaSetError("no CUDA device available; libdfsa_b200 has no CPU fallback"); return DFSA_ERR_CUDA; }
+    const char* lr = getenv("LOCAL_RANK");
+    int local = lr ? atoi(lr) : c.rank;
+    c.device = local % devCount;
+    DFSA_TRY(dfsaEnsureDevice());
+
+    const char* want = getenv("DFSA_TRANSPORT");
+    bool distinctDevices = devCount >= c.size;
+    bool useNccl = want ? (strcmp(want, "nccl") == 0) : distinctDevices;
+    if (useNccl && !distinctDevices) { dfsaSetError("DFSA_TRANSPORT=nccl needs one GPU per rank (%d ranks, %d devices)", c.size, devCount); return DFSA_ERR_COMM; }
+
+    if (useNccl) {
+        ncclUniqueId id;
+        static_assert(sizeof(ncclUniqueId) == 128, "unique id size");
+        Shm* m = g_comm.shm;
+        if (c.rank == 0) {
+            DFSA_NCCL(ncclGetUniqueId(&id));
+            memcpy(m->ncclId, &id, sizeof(id));
+            __sync_synchronize();
+            m->idReady = 1;
+        } else {
+            for (uint64_t spins = 0; !m->idReady; spins++) {
+                napBriefly();
+                if (spins > 1200000) { dfsaSetError("NCCL id never published"); return DFSA_ERR_COMM; }
+            }
+            __sync_synchronize();
+            memcpy(&id, m->ncclId, sizeof(id));
+        }
+        DFSA_NCCL(ncclCommInitRank(&g_comm.nccl, c.size, id, c.rank));
+        c.transport = Transport::Nccl;
+    } else {
+        c.transport = Transport::Ipc;
+    }
+    return shmBarrier();
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ bootstrap
+
+extern "C" int dfsa_comm_init(void) {
+    DfsaContext& c = dfsaCtx();
+    if (c.initialised) return DFSA_OK;                        // idempotent like comm_init (communication.hpp:16-21)
+    const char* ws = getenv("WORLD_SIZE");
+    const char* rk = getenv("RANK");
+    const char* np = getenv("DFSA_NP");
+    if (ws && rk && atoi(ws) > 1) {
+        c.size = atoi(ws);
+        c.rank = atoi(rk);
+        if (c.size > MAXP) { dfsaSetError("at most %d ranks", MAXP); return DFSA_ERR_ARG; }
+        const char* job = getenv("DFSA_JOB_ID");
+        const char* port = getenv("MASTER_PORT");
+        char name[128];
+        if (job) snprintf(name, sizeof(name), "/dfsa_%s", job);
+        else snprintf(name, sizeof(name), "/dfsa_%d_%s", (int)getppid(), port ? port : "0");
+        g_comm.shmName = name;
+        g_comm.shmOwner = (c.rank == 0);
+        DFSA_TRY(mapShm(name, c.rank == 0, c.size));
+    } else if (np && atoi(np) > 1) {
+        // fork model: must happen before this process touches CUDA (children cannot inherit a CUDA context)
+        if (c.compute) { dfsaSetError("dfsa_comm_init with DFSA_NP must be the first CUDA-touching call"); return DFSA_ERR_COMM; }
+        c.size = atoi(np);
+        if (c.size > MAXP) { dfsaSetError("at most %d ranks", MAXP); return DFSA_ERR_ARG; }
+        void* mem = mmap(nullptr, sizeof(Shm), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        if (mem == MAP_FAILED) { dfsaSetError("mmap failed: %s", strerror(errno)); return DFSA_ERR_COMM; }
+        memset(mem, 0, sizeof(Shm));
+        g_comm.shm = (Shm*)mem;
+        g_comm.shm->size = c.size;
+        g_comm.shm->magic = SHM_MAGIC;
+        g_comm.forked = true;
+        fflush(stdout); fflush(stderr);
+        for (int r = 1; r < c.size; r++) {
+            pid_t pid = fork();
+            if (pid < 0) { dfsaSetError("fork failed: %s", strerror(errno)); return DFSA_ERR_COMM; }
+            if (pid == 0) {
+                c.rank = r;
+                g_comm.children.clear();
+                if (!getenv("DFSA_KEEP_STDOUT")) { if (!freopen("/dev/null", "w", stdout)) {} }
+                break;
+            }
+            g_comm.children.push_back(pid);
+        }
+    } else {
+        c.size = 1;
+        c.rank = 0;
+    }
+    return finishInit();
+}
+
+extern "C" int dfsa_comm_get_unique_id(void* out128) {
+    DFSA_REQUIRE(out128, "null id buffer");
+    ncclUniqueId id;
+    DFSA_NCCL(ncclGetUniqueId(&id));
+    memcpy(out128, &id, sizeof(id));
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_comm_init_with_id(int rank, int numRanks, const void* uniqueId128, int device) {
+    DfsaContext& c = dfsaCtx();
+    if (c.initialised) return DFSA_OK;
+    DFSA_REQUIRE(numRanks >= 1 && rank >= 0 && rank < numRanks && numRanks <= MAXP, "bad rank / size");
+    c.rank = rank;
+    c.size = numRanks;
+    c.initialised = true;
+    int devCount = 0;
+    cudaError_t e = cudaGetDeviceCount(&devCount);
+    if (e != cudaSuccess || devCount == 0) { dfsaSetError("no CUDA device available; libdfsa_b200 has no CPU fallback"); return DFSA_ERR_CUDA; }
+    c.device = (device >= 0 ? device : rank) % devCount;
+    DFSA_TRY(dfsaEnsureDevice());
+    if (numRanks == 1) { c.transport = Transport::Single; return DFSA_OK; }
+    DFSA_REQUIRE(uniqueId128, "null unique id");
+    ncclUniqueId id;
+    memcpy(&id, uniqueId128, sizeof(id));
+    DFSA_NCCL(ncclCommInitRank(&g_comm.nccl, numRanks, id, rank));
+    c.transport = Transport::Nccl;
+    return DFSA_OK;
+}
+
+int dfsaHostBarrier() {
+    DfsaContext& c = dfsaCtx();
+    if (c.size == 1) return DFSA_OK;
+    if (g_comm.shm) return shmBarrier();
+    // NCCL-only bootstrap (no shared segment): a 1-element all-reduce is the barrier
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(64, &scratch));
+    DFSA_NCCL(ncclAllReduce(scratch, scratch, 1, ncclDouble, ncclSum, g_comm.nccl, c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_comm_barrier(void) {
+    DFSA_TRY(dfsa_device_sync());
+    return dfsaHostBarrier();
+}
+
+extern "C" int dfsa_comm_finalize(void) {
+    DfsaContext& c = dfsaCtx();
+    if (!c.initialised) return DFSA_OK;
+    DFSA_TRY(dfsa_comm_barrier());                            // comm_end: Barrier then Finalize (communication.hpp:24-27)
+    for (auto& kv : g_comm.peerMap) cudaIpcCloseMemHandle(kv.second);
+    g_comm.peerMap.clear();
+    if (g_comm.nccl) { ncclCommDestroy(g_comm.nccl); g_comm.nccl = nullptr; }
+    if (g_comm.forked) {
+        fflush(stdout);
+        if (c.rank != 0) _exit(0);                            // children never run the caller's epilogue
+        for (pid_t pid : g_comm.children) { int st; waitpid(pid, &st, 0); }
+    }
+    if (g_comm.shm && g_comm.shmOwner) shm_unlink(g_comm.shmName.c_str());
+    c.initialised = false;
+    c.size = 1; c.rank = 0; c.transport = Transport::Single;
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_comm_rank(void) { return dfsaCtx().rank; }
+extern "C" int dfsa_comm_size(void) { return dfsaCtx().size; }
+extern "C" const char* dfsa_comm_transport(void) {
+    switch (dfsaCtx().transport) { case Transport::Nccl: return "nccl"; case Transport::Ipc: return "ipc"; default: return "single"; }
+}
+
+// ------------------------------------------------------------------------------------------------ IPC registry
+
+int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut) {
+    DfsaContext& c = dfsaCtx();
+    int slot = -1;
+    for (int i = 0; i < MAXALLOC; i++) if (!g_comm.slotUsed[i]) { slot = i; break; }   // same sequence on every rank (SPMD)
+    if (slot < 0) { dfsaSetError("too many live states (%d allocation slots)", MAXALLOC); return DFSA_ERR_UNSUPPORTED; }
+    g_comm.slotUsed[slot] = true;
+    g_comm.localPtr[slot] = ptr;
+    *idOut = slot;
+    if (c.transport != Transport::Ipc) return DFSA_OK;
+    AllocSlot& a = g_comm.shm->alloc[c.rank][slot];
+    DFSA_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)&a.handle, ptr));
+    a.bytes = bytes;
+    __sync_synchronize();
+    a.valid = 1;
+    return shmBarrier();                                       // every rank's handle is published
+}
+
+int dfsaUnregisterAllocation(int id) {
+    DfsaContext& c = dfsaCtx();
+    if (c.transport == Transport::Ipc) {
+        DFSA_TRY(shmBarrier());                                // nobody is still using the mappings
+        for (auto it = g_comm.peerMap.begin(); it != g_comm.peerMap.end();) {
+            if (it->first.second == id) { cudaIpcCloseMemHandle(it->second); it = g_comm.peerMap.erase(it); }
+            else ++it;
+        }
+        g_comm.shm->alloc[c.rank][id].valid = 0;
+        DFSA_TRY(shmBarrier());                                // all mappings closed before the owner frees
+    }
+    g_comm.slotUsed[id] = false;
+    g_comm.localPtr[id] = nullptr;
+    return DFSA_OK;
+}
+
+static int peerPointer(int pair, int slot, double2** out) {
+    auto key = std::make_pair(pair, slot);
+    auto it = g_comm.peerMap.find(key);
+    if (it == g_comm.peerMap.end()) {
+        AllocSlot& a = g_comm.shm->alloc[pair][slot];
+        if (!a.valid) { dfsaSetError("rank %d has not published allocation %d", pair, slot); return DFSA_ERR_COMM; }
+        void* p = nullptr;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const void*)&a.handle, sizeof(h));
+        DFSA_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        it = g_comm.peerMap.emplace(key, p).first;
+    }
+    *out = (double2*)it->second;
+    return DFSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ exchange
+
+static int checkXArgs(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
+    DfsaContext& c = dfsaCtx();
+    DFSA_REQUIRE(s && c.size > 1, "exchange needs more than one rank");
+    DFSA_REQUIRE(pairRank >= 0 && pairRank < c.size && pairRank != c.rank, "bad pair rank");
+    DFSA_REQUIRE((sendWhich | 1) == 1 && (recvWhich | 1) == 1, "array selector must be DFSA_AMPS or DFSA_BUFFER");
+    DFSA_REQUIRE(sendStart + num <= s->numAmps && recvStart + num <= s->numAmps, "exchange range exceeds the shard");
+    DFSA_REQUIRE(sendWhich != recvWhich || sendStart + num <= recvStart || recvStart + num <= sendStart, "send and receive regions overlap");
+    return DFSA_OK;
+}
+
+// direction flags: doSend / doRecv
+static int transfer(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank, bool doSend, bool doRecv) {
+    DfsaContext& c = dfsaCtx();
+    if (c.transport == Transport::Nccl) {
+        // comm stream waits for every kernel enqueued so far; compute stream then waits for the transfer
+        DFSA_CUDA(cudaEventRecord(c.evCompute, c.compute));
+        DFSA_CUDA(cudaStreamWaitEvent(c.comm, c.evCompute, 0));
+        DFSA_NCCL(ncclGroupStart());
+        if (doSend) DFSA_NCCL(ncclSend(s->arr[sendWhich] + sendStart, 2 * num, ncclDouble, pairRank, g_comm.nccl, c.comm));
+        if (doRecv) DFSA_NCCL(ncclRecv(s->arr[recvWhich] + recvStart, 2 * num, ncclDouble, pairRank, g_comm.nccl, c.comm));
+        DFSA_NCCL(ncclGroupEnd());
+        DFSA_CUDA(cudaEventRecord(c.evComm, c.comm));
+        DFSA_CUDA(cudaStreamWaitEvent(c.compute, c.evComm, 0));
+        return DFSA_OK;
+    }
+    // IPC: put into the partner's receive region
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));               // my data is final, my receive region is free
+    DFSA_TRY(pairBarrier(pairRank));                           // ... and so is the partner's
+    if (doSend) {
+        double2* remote;
+        DFSA_TRY(peerPointer(pairRank, s->allocId[recvWhich], &remote));
+        DFSA_CUDA(cudaMemcpyAsync(remote + recvStart, s->arr[sendWhich] + sendStart, num * sizeof(double2), cudaMemcpyDeviceToDevice, c.comm));
+        DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    }
+    return pairBarrier(pairRank);                              // the partner's put has landed in my region
+}
+
+extern "C" int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_TRY(checkXArgs(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank));
+    return transfer(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank, true, true);
+}
+
+extern "C" int dfsa_x_send(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_TRY(checkXArgs(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank));
+    return transfer(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank, true, false);
+}
+
+extern "C" int dfsa_x_recv(dfsa_state* s, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_TRY(checkXArgs(s, recvWhich ^ 1, 0, recvWhich, recvStart, num, pairRank));
+    return transfer(s, recvWhich, recvStart, recvWhich, recvStart, num, pairRank, false, true);
+}
+
+extern "C" int dfsa_x_allreduce_amp(double reim[2]) {
+    DfsaContext& c = dfsaCtx();
+    DFSA_REQUIRE(reim, "null argument");
+    if (c.size == 1) return DFSA_OK;
+    if (g_comm.shm) {
+        // rank-ordered sum through the shared page: deterministic, identical on every rank
+        g_comm.shm->reduce[c.rank][0] = reim[0];
+        g_comm.shm->reduce[c.rank][1] = reim[1];
+        DFSA_TRY(shmBarrier());
+        double re = 0.0, im = 0.0;
+        for (int r = 0; r < c.size; r++) { re += g_comm.shm->reduce[r][0]; im += g_comm.shm->reduce[r][1]; }
+        DFSA_TRY(shmBarrier());
+        reim[0] = re; reim[1] = im;
+        return DFSA_OK;
+    }
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(64, &scratch));
+    DFSA_CUDA(cudaMemcpyAsync(scratch, reim, 16, cudaMemcpyHostToDevice, c.comm));
+    DFSA_NCCL(ncclAllReduce(scratch, scratch, 2, ncclDouble, ncclSum, g_comm.nccl, c.comm));
+    DFSA_CUDA(cudaMemcpyAsync(reim, scratch, 16, cudaMemcpyDeviceToHost, c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    return DFSA_OK;
+}
+
+// getAllVecAmps (tests/test_utilities.hpp:419-435): every rank ends up with the whole state in host memory
+extern "C" int dfsa_state_download_all(dfsa_state* s, double* hostAll) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && hostAll, "null argument");
+    DfsaContext& c = dfsaCtx();
+    DFSA_TRY(dfsa_comm_barrier());
+    if (c.size == 1) return dfsa_state_download(s, DFSA_AMPS, 0, s->numAmps, hostAll);
+    size_t shardBytes = s->numAmps * sizeof(double2);
+    if (c.transport == Transport::Nccl) {
+        double2* all = nullptr;
+        DFSA_CUDA(cudaMalloc((void**)&all, shardBytes * c.size));
+        DFSA_NCCL(ncclAllGather(s->arr[DFSA_AMPS], all, 2 * s->numAmps, ncclDouble, g_comm.nccl, c.comm));
+        DFSA_CUDA(cudaMemcpyAsync(hostAll, all, shardBytes * c.size, cudaMemcpyDeviceToHost, c.comm));
+        DFSA_CUDA(cudaStreamSynchronize(c.comm));
+        DFSA_CUDA(cudaFree(all));
+    } else {
+        for (int r = 0; r < c.size; r++) {
+            double2* src = s->arr[DFSA_AMPS];
+            if (r != c.rank) DFSA_TRY(peerPointer(r, s->allocId[DFSA_AMPS], &src));
+            DFSA_CUDA(cudaMemcpyAsync((char*)hostAll + shardBytes * r, src, shardBytes, cudaMemcpyDeviceToHost, c.comm));
+        }
+        DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    }
+    return dfsaHostBarrier();
+}

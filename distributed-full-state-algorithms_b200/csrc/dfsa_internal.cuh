@@ -1,0 +1,132 @@
+// dfsa_internal.cuh -- shared by the translation units of libdfsa_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "dfsa_b200.h"
+
+// ------------------------------------------------------------------------------------------------ state
+
+struct dfsa_state {
+    int      isDensity;
+    unsigned numQubits;        // n (sv) or N (dm)
+    int      rank, numNodes;
+    unsigned logNumNodes;
+    unsigned logNumAmps;       // per rank
+    uint64_t numAmps;          // per rank
+    double2* arr[2];           // DFSA_AMPS, DFSA_BUFFER (buffer == nullptr when numNodes == 1)
+    int      allocId[2];       // slot in the IPC allocation registry (-1 if none)
+};
+
+// ------------------------------------------------------------------------------------------------ context
+
+enum class Transport { Single, Nccl, Ipc };
+
+struct DfsaContext {
+    bool         initialised = false;
+    int          rank = 0, size = 1, device = 0;
+    int          numSMs = 148;
+    Transport    transport = Transport::Single;
+    cudaStream_t compute = nullptr;   // every kernel
+    cudaStream_t comm = nullptr;      // every transfer
+    cudaEvent_t  evCompute = nullptr, evComm = nullptr;
+    double2*     devScratch = nullptr;    // gate matrices, reduction partials
+    size_t       devScratchBytes = 0;
+    double*      hostPinned = nullptr;    // small pinned staging (reduction results)
+};
+
+DfsaContext& dfsaCtx();
+void dfsaSetError(const char* fmt, ...);
+int  dfsaEnsureDevice();                         // lazily create streams etc.; DFSA_ERR_CUDA if no device
+int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
+
+#define DFSA_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            dfsaSetError("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));      \
+            return DFSA_ERR_CUDA;                                                                    \
+        }                                                                                            \
+    } while (0)
+
+#define DFSA_REQUIRE(cond, msg)                                                                      \
+    do {                                                                                             \
+        if (!(cond)) {                                                                               \
+            dfsaSetError("%s:%d: precondition failed: %s (%s)", __FILE__, __LINE__, #cond, msg);     \
+            return DFSA_ERR_ARG;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define DFSA_TRY(call)                                                                               \
+    do {                                                                                             \
+        int r_ = (call);                                                                             \
+        if (r_ != DFSA_OK) return r_;                                                                \
+    } while (0)
+
+#define DFSA_LAUNCH_CHECK() DFSA_CUDA(cudaGetLastError())
+
+// transport hooks implemented in dfsa_comm.cu
+int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc
+int dfsaUnregisterAllocation(int id);
+int dfsaHostBarrier();                                             // inter-rank barrier without touching streams
+
+// ------------------------------------------------------------------------------------------------ device helpers
+
+// Sorted bit positions at which bits are inserted into a running index (bit_maths.hpp:37-58 restated for
+// the device, 64-bit throughout -- the reference's Nat shifts truncate above 32 index bits).
+struct BitSpec {
+    uint32_t n;
+    uint8_t  pos[DFSA_MAX_QUBITS];
+};
+
+__host__ __device__ __forceinline__ uint64_t insertZeroBit(uint64_t v, unsigned p) {
+    uint64_t lowMask = (1ULL << p) - 1ULL;
+    return ((v & ~lowMask) << 1) | (v & lowMask);
+}
+
+__host__ __device__ __forceinline__ uint64_t insertZeroBits(uint64_t v, const BitSpec& s) {
+    for (uint32_t q = 0; q < s.n; q++) v = insertZeroBit(v, s.pos[q]);
+    return v;
+}
+
+template <int N>
+__device__ __forceinline__ uint64_t insertZeroBitsN(uint64_t v, const BitSpec& s) {
+#pragma unroll
+    for (int q = 0; q < N; q++) v = insertZeroBit(v, s.pos[q]);
+    return v;
+}
+
+__device__ __forceinline__ unsigned parity64(uint64_t m) { return (unsigned)__popcll(m) & 1u; }
+
+// complex arithmetic on double2 (x = re, y = im)
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cfma(double2 a, double2 b, double2 c) {   // a*b + c
+    return make_double2(fma(a.x, b.x, fma(-a.y, b.y, c.x)), fma(a.x, b.y, fma(a.y, b.x, c.y)));
+}
+__device__ __forceinline__ double2 cscale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+// multiply by i^k without arithmetic: exact (bit-preserving up to the sign of zero)
+__device__ __forceinline__ double2 mulPowI(double2 a, unsigned k) {
+    switch (k & 3u) {
+        case 0:  return a;
+        case 1:  return make_double2(-a.y, a.x);
+        case 2:  return make_double2(-a.x, -a.y);
+        default: return make_double2(a.y, -a.x);
+    }
+}
+
+struct Gate2 { double2 m00, m01, m10, m11; };
+
+static inline double2 hostAmp(const double* p) { return make_double2(p[0], p[1]); }
+
+// launch geometry: a grid that is a multiple of the SM count (persistent-style grid-stride kernels)
+static inline unsigned dfsaGrid(uint64_t workItems, unsigned threads, unsigned itemsPerThread, unsigned blocksPerSM) {
+    uint64_t perBlock = (uint64_t)threads * itemsPerThread;
+    uint64_t needed = (workItems + perBlock - 1) / perBlock;
+    uint64_t cap = (uint64_t)dfsaCtx().numSMs * blocksPerSM;
+    if (needed < 1) needed = 1;
+    return (unsigned)(needed < cap ? needed : cap);
+}

@@ -1,0 +1,418 @@
+// dfsa_kernels_dm.cu -- density-matrix kernels K12-K17, K19-K23 for sm_100a.
+// The density matrix is a Choi vector of 2N index bits: bit q (< N) is the ket/row bit of qubit q, bit q+N its
+// bra/column bit; flat = 2^N*col + row (tests/test_utilities.hpp:498-500). Ranks own column blocks, so the
+// "prefix" qubits are the bra bits q+N >= logNumAmps, i.e. q >= N - log2(P).
+#include <algorithm>
+#include <vector>
+
+#include "dfsa_stream_kernels.cuh"
+
+namespace {
+inline unsigned prefixThreshold(const dfsa_state* s) { return s->numQubits - s->logNumNodes; }
+inline int rankBit(const dfsa_state* s, unsigned qb) { return (s->rank >> (qb - prefixThreshold(s))) & 1; }
+}  // namespace
+
+#define DFSA_DM_ENTRY(s)                              \
+    DFSA_TRY(dfsaEnsureDevice());                     \
+    DFSA_REQUIRE((s) && (s)->isDensity, "needs a density-matrix state")
+
+// ---------------------------------------------------------------------------------------------------------
+// K12: local_densitymatrix.hpp:12-42. Scale the amplitudes whose ket bit != bra bit by 1-2p. 16*A bytes.
+extern "C" int dfsa_k_oneQubitDephasing(dfsa_state* s, unsigned qb, double prob) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb < s->numQubits, "qubit out of range");
+    const double fac = 1 - 2 * prob;
+    double2* amps = s->arr[DFSA_AMPS];
+    if (qb >= prefixThreshold(s)) {
+        // bra bit lives in the rank index: scale the half whose ket bit differs from it
+        const uint64_t fixed = (uint64_t)(!rankBit(s, qb)) << qb;
+        auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | fixed]}; };
+        auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = cscale(fac, v.a); };
+        return launchStream<4, Amp1>(s->numAmps >> 1, ld, st);
+    }
+    const unsigned alt = qb + s->numQubits;
+    const uint64_t bKet = 1ULL << qb, bBra = 1ULL << alt;
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        return Amp2{amps[j00 | bKet], amps[j00 | bBra]};
+    };
+    auto st = [=] __device__(uint64_t k, const Amp2& v) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        amps[j00 | bKet] = cscale(fac, v.a0);
+        amps[j00 | bBra] = cscale(fac, v.a1);
+    };
+    return launchStream<2, Amp2>(s->numAmps >> 2, ld, st);
+}
+
+// K13: local_densitymatrix.hpp:45-60. amps[j] *= 1 - 4p/3 where either qubit's ket/bra bits differ (global index).
+extern "C" int dfsa_k_twoQubitDephasing(dfsa_state* s, unsigned qb1, unsigned qb2, double prob) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb1 < s->numQubits && qb2 < s->numQubits && qb1 != qb2, "needs two distinct qubits");
+    const unsigned N = s->numQubits;
+    const double fac = -4 * prob / 3 + 1.;
+    const uint64_t rs = (uint64_t)s->rank << s->logNumAmps;
+    double2* amps = s->arr[DFSA_AMPS];
+    auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) {
+        uint64_t i = rs | j;
+        unsigned differ = (unsigned)(((i >> qb1) ^ (i >> (qb1 + N))) | ((i >> qb2) ^ (i >> (qb2 + N)))) & 1u;
+        if (differ) amps[j] = cscale(fac, v.a);            // untouched amplitudes are not written back
+    };
+    return launchStream<4, Amp1>(s->numAmps, ld, st);
+}
+
+// K14: local_densitymatrix.hpp:63-81 (suffix qubit). c1 = 2p/3, c2 = 1-2p/3, c3 = 1-4p/3
+// (distributed_densitymatrix.hpp:106-108). 32*A bytes.
+extern "C" int dfsa_k_oneQubitDepolarising(dfsa_state* s, unsigned qb, double prob) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb < prefixThreshold(s), "local kernel needs a suffix qubit");
+    const double c1 = 2 * prob / 3, c2 = 1 - 2 * prob / 3, c3 = 1 - 4 * prob / 3;
+    const unsigned alt = qb + s->numQubits;
+    const uint64_t bKet = 1ULL << qb, bBra = 1ULL << alt;
+    double2* amps = s->arr[DFSA_AMPS];
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        return Amp4{amps[j00], amps[j00 | bKet], amps[j00 | bBra], amps[j00 | bKet | bBra]};
+    };
+    auto st = [=] __device__(uint64_t k, const Amp4& v) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        amps[j00]               = make_double2(fma(c1, v.a11.x, c2 * v.a00.x), fma(c1, v.a11.y, c2 * v.a00.y));
+        amps[j00 | bKet]        = cscale(c3, v.a01);
+        amps[j00 | bBra]        = cscale(c3, v.a10);
+        amps[j00 | bKet | bBra] = make_double2(fma(c2, v.a11.x, c1 * v.a00.x), fma(c2, v.a11.y, c1 * v.a00.y));
+    };
+    return launchStream<1, Amp4>(s->numAmps >> 2, ld, st);
+}
+
+// K16: local_densitymatrix.hpp:111-131 (suffix qubit). a00 += p*a11; a01,a10 *= sqrt(1-p); a11 *= 1-p.
+extern "C" int dfsa_k_damping(dfsa_state* s, unsigned qb, double prob) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb < prefixThreshold(s), "local kernel needs a suffix qubit");
+    const double c1 = sqrt(1 - prob), c2 = 1 - prob;
+    const unsigned alt = qb + s->numQubits;
+    const uint64_t bKet = 1ULL << qb, bBra = 1ULL << alt;
+    double2* amps = s->arr[DFSA_AMPS];
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        return Amp4{amps[j00], amps[j00 | bKet], amps[j00 | bBra], amps[j00 | bKet | bBra]};
+    };
+    auto st = [=] __device__(uint64_t k, const Amp4& v) {
+        uint64_t j00 = insertZeroBit(insertZeroBit(k, qb), alt);
+        amps[j00]               = make_double2(fma(prob, v.a11.x, v.a00.x), fma(prob, v.a11.y, v.a00.y));
+        amps[j00 | bKet]        = cscale(c1, v.a01);
+        amps[j00 | bBra]        = cscale(c1, v.a10);
+        amps[j00 | bKet | bBra] = cscale(c2, v.a11);
+    };
+    return launchStream<1, Amp4>(s->numAmps >> 2, ld, st);
+}
+
+// K15: local_densitymatrix.hpp:83-108 (both qubits suffix). Pass 1 scales every amplitude whose (ket,bra) bits
+// of either qubit differ by 1+c3; pass 2 mixes the four "diagonal" amplitudes of each 16-group:
+//   a' = c1*a + c2*(a0000 + a0101 + a1010 + a1111)   (sum in that order).
+// Reference constants (distributed_densitymatrix.hpp:247-249): c1 = 1-4p/5, c2 = 4p/15, c3 = -16p/15 -- with
+// these the map is NOT the depolarising channel but it is what the reference computes; `corrected`
+// uses c1 = 1-16p/15, which is the channel (1-16p/15) rho + (4p/15) I (x) Tr_2 rho.
+extern "C" int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned qb2, double prob, int corrected) {
+    DFSA_DM_ENTRY(s);
+    if (qb1 > qb2) std::swap(qb1, qb2);
+    DFSA_REQUIRE(qb1 != qb2 && qb2 < prefixThreshold(s), "local kernel needs two distinct suffix qubits");
+    const unsigned N = s->numQubits, q0 = qb1, q1 = qb2, q2 = qb1 + N, q3 = qb2 + N;
+    const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
+    const double offFac = 1. + c3;
+    double2* amps = s->arr[DFSA_AMPS];
+    {
+        auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
+        auto st = [=] __device__(uint64_t j, const Amp1& v) {
+            unsigned differ = (unsigned)(((j >> q0) ^ (j >> q2)) | ((j >> q1) ^ (j >> q3))) & 1u;
+            if (differ) amps[j] = cscale(offFac, v.a);
+        };
+        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+    }
+    const uint64_t b02 = (1ULL << q0) | (1ULL << q2), b13 = (1ULL << q1) | (1ULL << q3);
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j = insertZeroBit(insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2), q3);
+        return Amp4{amps[j], amps[j | b02], amps[j | b13], amps[j | b02 | b13]};
+    };
+    auto st = [=] __device__(uint64_t k, const Amp4& v) {
+        uint64_t j = insertZeroBit(insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2), q3);
+        double tx = ((v.a00.x + v.a01.x) + v.a10.x) + v.a11.x, ty = ((v.a00.y + v.a01.y) + v.a10.y) + v.a11.y;
+        amps[j]             = make_double2(fma(c2, tx, c1 * v.a00.x), fma(c2, ty, c1 * v.a00.y));
+        amps[j | b02]       = make_double2(fma(c2, tx, c1 * v.a01.x), fma(c2, ty, c1 * v.a01.y));
+        amps[j | b13]       = make_double2(fma(c2, tx, c1 * v.a10.x), fma(c2, ty, c1 * v.a10.y));
+        amps[j | b02 | b13] = make_double2(fma(c2, tx, c1 * v.a11.x), fma(c2, ty, c1 * v.a11.y));
+    };
+    return launchStream<1, Amp4>(s->numAmps >> 4, ld, st);
+}
+
+// K19: distributed_densitymatrix.hpp:130-141. After the half exchange (received half at buffer[A/2..)):
+//   other half (ket bit != rank bit) *= c3;   this half: a = c2*a + c1*recv.
+extern "C" int dfsa_k_depol1Combine(dfsa_state* s, unsigned qb, unsigned bit, double prob) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb >= prefixThreshold(s) && qb < s->numQubits && s->arr[DFSA_BUFFER], "needs a prefix qubit and the exchange buffer");
+    const double c1 = 2 * prob / 3, c2 = 1 - 2 * prob / 3, c3 = 1 - 4 * prob / 3;
+    const uint64_t half = s->numAmps >> 1, same = (uint64_t)(bit & 1u) << qb, other = (uint64_t)(!(bit & 1u)) << qb;
+    double2* amps = s->arr[DFSA_AMPS];
+    const double2* recv = s->arr[DFSA_BUFFER] + half;
+    using Item = Amp3;     // a = mine, b = other half, c = received
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j = insertZeroBit(k, qb);
+        return Item{amps[j | same], amps[j | other], recv[k]};
+    };
+    auto st = [=] __device__(uint64_t k, const Item& v) {
+        uint64_t j = insertZeroBit(k, qb);
+        amps[j | other] = cscale(c3, v.b);
+        amps[j | same]  = make_double2(fma(c1, v.c.x, c2 * v.a.x), fma(c1, v.c.y, c2 * v.a.y));
+    };
+    return launchStream<2, Item>(half, ld, st);
+}
+
+// K20: distributed_densitymatrix.hpp:152-183 (qb1 suffix, qb2 prefix). q0 = qb1, q1 = qb2, q2 = qb1+N, bit = rank bit of qb2's bra.
+// phase 0: scale + pack the pre-summed eighth into buffer[0..A/8); phase 1: combine with buffer[A/8..A/4).
+extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, int phase) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(q0 < q1 && q1 < q2 && q2 < s->logNumAmps && s->arr[DFSA_BUFFER], "bad qubits / no exchange buffer");
+    const double c1 = 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
+    const uint64_t eighth = s->numAmps >> 3;
+    const uint64_t b1 = (uint64_t)(bit & 1u) << q1, b02 = (1ULL << q0) | (1ULL << q2);
+    double2* amps = s->arr[DFSA_AMPS];
+    double2* buf = s->arr[DFSA_BUFFER];
+    if (phase == 0) {
+        const double offFac = 1. + c3;
+        auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
+        auto st = [=] __device__(uint64_t j, const Amp1& v) {
+            unsigned f1 = !(((j >> q0) ^ (j >> q2)) & 1ULL), f2 = (((j >> q1) & 1ULL) == (bit & 1u));
+            if (!(f1 & f2)) amps[j] = cscale(offFac, v.a);
+        };
+        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+        auto ld2 = [=] __device__(uint64_t k) {
+            uint64_t j0b0 = insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | b1;
+            return Amp2{amps[j0b0], amps[j0b0 | b02]};
+        };
+        auto st2 = [=] __device__(uint64_t k, const Amp2& v) { buf[k] = cadd(v.a0, v.a1); };
+        return launchStream<2, Amp2>(eighth, ld2, st2);
+    }
+    DFSA_REQUIRE(phase == 1, "phase must be 0 or 1");
+    using Item = Amp3;     // a = a0b0, b = a1b1, c = received
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j0b0 = insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | b1;
+        return Item{amps[j0b0], amps[j0b0 | b02], buf[k + eighth]};
+    };
+    auto st = [=] __device__(uint64_t k, const Item& v) {
+        uint64_t j0b0 = insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | b1;
+        // literal reference arithmetic, including the read-after-write of :181 -> :182
+        double2 n0 = make_double2(fma(c2, v.b.x + v.c.x, c1 * v.a.x), fma(c2, v.b.y + v.c.y, c1 * v.a.y));
+        double2 n1 = make_double2(fma(c2, n0.x + v.c.x, c1 * v.b.x), fma(c2, n0.y + v.c.y, c1 * v.b.y));
+        amps[j0b0] = n0;
+        amps[j0b0 | b02] = n1;
+    };
+    return launchStream<2, Item>(eighth, ld, st);
+}
+
+// K21: distributed_densitymatrix.hpp:195-237 (both qubits prefix).
+// phase 0: scale + pack quarter; phase 1: a = c1*a + c2*recv, also repacked; phase 2: a = (c2/c1)*recv  (overwrite, as the reference)
+extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, int phase) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(q0 < q1 && q1 < s->logNumAmps && s->arr[DFSA_BUFFER], "bad qubits / no exchange buffer");
+    const double c1 = 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
+    const uint64_t quarter = s->numAmps >> 2;
+    const uint64_t fixed = ((uint64_t)(bit0 & 1u) << q0) | ((uint64_t)(bit1 & 1u) << q1);
+    double2* amps = s->arr[DFSA_AMPS];
+    double2* buf = s->arr[DFSA_BUFFER];
+    if (phase == 0) {
+        const double offFac = 1. + c3;
+        auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
+        auto st = [=] __device__(uint64_t j, const Amp1& v) {
+            unsigned f1 = (((j >> q0) & 1ULL) == (bit0 & 1u)), f2 = (((j >> q1) & 1ULL) == (bit1 & 1u));
+            if (!(f1 & f2)) amps[j] = cscale(offFac, v.a);
+        };
+        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+        auto ld2 = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed]}; };
+        auto st2 = [=] __device__(uint64_t k, const Amp1& v) { buf[k] = v.a; };
+        return launchStream<4, Amp1>(quarter, ld2, st2);
+    }
+    if (phase == 1) {
+        auto ld = [=] __device__(uint64_t k) { return Amp2{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed], buf[k + quarter]}; };
+        auto st = [=] __device__(uint64_t k, const Amp2& v) {
+            double2 n = make_double2(fma(c2, v.a1.x, c1 * v.a0.x), fma(c2, v.a1.y, c1 * v.a0.y));
+            amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = n;
+            buf[k] = n;
+        };
+        return launchStream<2, Amp2>(quarter, ld, st);
+    }
+    DFSA_REQUIRE(phase == 2, "phase must be 0, 1 or 2");
+    const double c4 = c2 / c1;
+    auto ld = [=] __device__(uint64_t k) { return Amp1{buf[k + quarter]}; };
+    auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = cscale(c4, v.a); };
+    return launchStream<4, Amp1>(quarter, ld, st);
+}
+
+// K22: distributed_densitymatrix.hpp:284-313.
+extern "C" int dfsa_k_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int phase) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(qb >= prefixThreshold(s) && qb < s->numQubits && s->arr[DFSA_BUFFER], "needs a prefix qubit and the exchange buffer");
+    const double c1 = sqrt(1 - prob), c2 = 1 - prob;
+    const uint64_t half = s->numAmps >> 1;
+    double2* amps = s->arr[DFSA_AMPS];
+    double2* buf = s->arr[DFSA_BUFFER];
+    if (phase == 0) {           // bit = 1 ranks: pack the ket=1 half, scale it by 1-p
+        const uint64_t one = 1ULL << qb;
+        auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | one]}; };
+        auto st = [=] __device__(uint64_t k, const Amp1& v) { buf[k] = v.a; amps[insertZeroBit(k, qb) | one] = cscale(c2, v.a); };
+        return launchStream<4, Amp1>(half, ld, st);
+    }
+    if (phase == 1) {           // every rank: the half with ket bit != rank bit decays by sqrt(1-p)
+        const uint64_t fixed = (uint64_t)(!(bit & 1u)) << qb;
+        auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | fixed]}; };
+        auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = cscale(c1, v.a); };
+        return launchStream<4, Amp1>(half, ld, st);
+    }
+    DFSA_REQUIRE(phase == 2, "phase must be 0, 1 or 2");   // bit = 0 ranks: a00 += p * a11 (received)
+    auto ld = [=] __device__(uint64_t k) { return Amp2{amps[insertZeroBit(k, qb)], buf[k]}; };
+    auto st = [=] __device__(uint64_t k, const Amp2& v) { amps[insertZeroBit(k, qb)] = make_double2(fma(prob, v.a1.x, v.a0.x), fma(prob, v.a1.y, v.a0.y)); };
+    return launchStream<2, Amp2>(half, ld, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K17: local_densitymatrix.hpp:134-164. out[l] = sum_{k ascending} in[base(l) | spread(k)]; pure additions in the
+// reference's order, so the result is bit-exact. Reads 16*A/2^t, writes 16*A/4^t bytes.
+__global__ void __launch_bounds__(256) partialTraceKernel(const double2* __restrict__ in, double2* __restrict__ out, uint64_t numOut,
+                                                         BitSpec allSorted, BitSpec targs, BitSpec pairs, unsigned t) {
+    for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < numOut; l += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t base = insertZeroBits(l, allSorted);
+        double2 acc = make_double2(0.0, 0.0);
+        for (uint64_t k = 0; k < (1ULL << t); k++) {
+            uint64_t idx = base;
+            for (unsigned b = 0; b < t; b++) {
+                uint64_t bit = (k >> b) & 1ULL;
+                idx |= (bit << targs.pos[b]) | (bit << pairs.pos[b]);
+            }
+            acc = cadd(acc, in[idx]);
+        }
+        out[l] = acc;
+    }
+}
+
+extern "C" int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32_t* targets, const uint32_t* pairTargets, unsigned numTargets) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(in && out && in->isDensity && out->isDensity && targets && pairTargets, "bad argument");
+    DFSA_REQUIRE(numTargets >= 1 && out->numQubits + numTargets == in->numQubits, "output state has the wrong size");
+    DFSA_REQUIRE(out->logNumAmps + 2 * numTargets == in->logNumAmps, "output shard has the wrong size");
+    BitSpec all, tg, pr;
+    std::vector<uint32_t> both(targets, targets + numTargets);
+    both.insert(both.end(), pairTargets, pairTargets + numTargets);
+    std::sort(both.begin(), both.end());
+    all.n = 2 * numTargets; tg.n = pr.n = numTargets;
+    for (unsigned q = 0; q < 2 * numTargets; q++) {
+        DFSA_REQUIRE(both[q] < in->logNumAmps && (q == 0 || both[q] != both[q - 1]), "traced bits must be distinct suffix bits");
+        all.pos[q] = (uint8_t)both[q];
+    }
+    for (unsigned q = 0; q < numTargets; q++) { tg.pos[q] = (uint8_t)targets[q]; pr.pos[q] = (uint8_t)pairTargets[q]; }
+    unsigned grid = dfsaGrid(out->numAmps, 256, 1, 8);
+    partialTraceKernel<<<grid, 256, 0, dfsaCtx().compute>>>(in->arr[DFSA_AMPS], out->arr[DFSA_AMPS], out->numAmps, all, tg, pr, numTargets);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K23: distributed_densitymatrix.hpp:322-344 with the closed form of getPauliTensorElem (misc.hpp:16-38):
+// with lo = row bits, hi = column bits of the flat index, term P contributes only where lo ^ hi == XYmask(P), with
+//   elem = i^{#Y} * (-1)^{popc(~hi & Ymask) + popc(hi & Zmask)}          (SURVEY Appendix B).
+// GATHER form: each term touches exactly one amplitude per column -> numTerms * 2^N / P scattered 16-byte reads
+// (32-byte sectors) instead of a 16*A-byte scan; used when that is the smaller traffic. SCAN form otherwise.
+struct PauliTerm { uint64_t xy, y, z; double2 coeff; /* coeff * i^{#Y} */ };
+
+__device__ __forceinline__ void blockReduceToPartials(double re, double im, double2* partials) {
+    __shared__ double sre[8], sim[8];
+    for (int off = 16; off > 0; off >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, off); im += __shfl_xor_sync(0xffffffffu, im, off); }
+    if ((threadIdx.x & 31) == 0) { sre[threadIdx.x >> 5] = re; sim[threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < 8; w++) { a += sre[w]; b += sim[w]; }
+        partials[blockIdx.x] = make_double2(a, b);
+    }
+}
+
+__global__ void __launch_bounds__(256) expecGatherKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numTerms,
+                                                        unsigned N, unsigned logCols, uint64_t firstCol, double2* partials) {
+    double re = 0.0, im = 0.0;
+    const uint64_t cols = 1ULL << logCols, items = (uint64_t)numTerms << logCols;
+    for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (uint64_t)gridDim.x * blockDim.x) {
+        const PauliTerm tm = terms[w >> logCols];
+        const uint64_t c = w & (cols - 1), hi = firstCol + c, lo = hi ^ tm.xy;
+        const double2 a = amps[(c << N) | lo];
+        const unsigned neg = (unsigned)(__popcll(~hi & tm.y) + __popcll(hi & tm.z)) & 1u;
+        double2 v = cmul(tm.coeff, a);
+        re += neg ? -v.x : v.x;
+        im += neg ? -v.y : v.y;
+    }
+    blockReduceToPartials(re, im, partials);
+}
+
+__global__ void __launch_bounds__(256) expecScanKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numTerms,
+                                                      unsigned N, uint64_t numAmps, uint64_t rankShift, double2* partials) {
+    double re = 0.0, im = 0.0;
+    const uint64_t loMask = (1ULL << N) - 1ULL;
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < numAmps; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = rankShift | j, lo = i & loMask, hi = i >> N, x = lo ^ hi;
+        double2 sum = make_double2(0.0, 0.0);
+        for (unsigned t = 0; t < numTerms; t++) {
+            const PauliTerm tm = terms[t];
+            if (tm.xy == x) {
+                const unsigned neg = (unsigned)(__popcll(~hi & tm.y) + __popcll(hi & tm.z)) & 1u;
+                sum.x += neg ? -tm.coeff.x : tm.coeff.x;
+                sum.y += neg ? -tm.coeff.y : tm.coeff.y;
+            }
+        }
+        if (sum.x != 0.0 || sum.y != 0.0) {
+            double2 v = cmul(sum, amps[j]);
+            re += v.x; im += v.y;
+        }
+    }
+    blockReduceToPartials(re, im, partials);
+}
+
+extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]) {
+    DFSA_DM_ENTRY(s);
+    DFSA_REQUIRE(coeffs && paulis && out && numTerms >= 1, "bad argument");
+    const unsigned N = s->numQubits;
+    std::vector<PauliTerm> terms(numTerms);
+    for (unsigned t = 0; t < numTerms; t++) {
+        PauliTerm tm{0, 0, 0, make_double2(coeffs[t], 0.0)};
+        unsigned numY = 0;
+        for (unsigned q = 0; q < N; q++) {
+            uint32_t code = paulis[(size_t)t * N + q];
+            DFSA_REQUIRE(code <= 3, "Pauli codes are 0..3 (types.hpp:16-18)");
+            if (code == 1 || code == 2) tm.xy |= 1ULL << q;
+            if (code == 2) { tm.y |= 1ULL << q; numY++; }
+            if (code == 3) tm.z |= 1ULL << q;
+        }
+        switch (numY & 3u) { case 1: tm.coeff = make_double2(0.0, coeffs[t]); break; case 2: tm.coeff = make_double2(-coeffs[t], 0.0); break;
+                             case 3: tm.coeff = make_double2(0.0, -coeffs[t]); break; default: break; }
+        terms[t] = tm;
+    }
+    DfsaContext& c = dfsaCtx();
+    const unsigned logCols = s->logNumAmps - N;                 // columns owned by this rank
+    bool gather = ((uint64_t)numTerms << 1) <= (1ULL << N);     // 32-byte sectors per gathered amp vs a 16*A scan
+    if (getenv("DFSA_EXPEC_FORCE_GATHER")) gather = true;
+    if (getenv("DFSA_EXPEC_FORCE_SCAN")) gather = false;
+    const bool scan = !gather;
+    uint64_t items = scan ? s->numAmps : ((uint64_t)numTerms << logCols);
+    unsigned grid = dfsaGrid(items, 256, 1, 8);
+    size_t termBytes = (sizeof(PauliTerm) * numTerms + 255) / 256 * 256;
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(termBytes + grid * sizeof(double2), &scratch));
+    PauliTerm* dTerms = (PauliTerm*)scratch;
+    double2* partials = (double2*)((char*)scratch + termBytes);
+    DFSA_CUDA(cudaMemcpyAsync(dTerms, terms.data(), sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+    if (scan) expecScanKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, s->numAmps, (uint64_t)s->rank << s->logNumAmps, partials);
+    else expecGatherKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, logCols, (uint64_t)s->rank << logCols, partials);
+    DFSA_LAUNCH_CHECK();
+    std::vector<double2> host(grid);
+    DFSA_CUDA(cudaMemcpyAsync(host.data(), partials, grid * sizeof(double2), cudaMemcpyDeviceToHost, c.compute));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));               // also covers the lifetime of `terms`
+    double re = 0.0, im = 0.0;
+    for (const double2& p : host) { re += p.x; im += p.y; }
+    out[0] = re; out[1] = im;
+    return DFSA_OK;
+}

@@ -1,0 +1,457 @@
+// dfsa_kernels_sv.cu -- state-vector kernels K1-K11, K18 for sm_100a.
+// Each extern "C" entry cites the reference loop it replaces; see include/dfsa_b200.h for the contract.
+#include <algorithm>
+#include <vector>
+
+#include "dfsa_stream_kernels.cuh"
+
+namespace {
+
+int sortedSpec(const uint32_t* qubits, unsigned n, unsigned limit, BitSpec* spec, uint64_t* mask) {
+    DFSA_REQUIRE(n <= DFSA_MAX_QUBITS, "too many qubits");
+    std::vector<uint32_t> v(qubits, qubits + n);
+    std::sort(v.begin(), v.end());
+    uint64_t m = 0;
+    for (unsigned q = 0; q < n; q++) {
+        DFSA_REQUIRE(v[q] < limit, "qubit index is not a local (suffix) bit of this shard");
+        DFSA_REQUIRE(q == 0 || v[q] != v[q - 1], "duplicate qubit");
+        spec->pos[q] = (uint8_t)v[q];
+        m |= 1ULL << v[q];
+    }
+    spec->n = n;
+    if (mask) *mask = m;
+    return DFSA_OK;
+}
+
+// spread the low bits of `value` over the sorted positions of `spec`
+uint64_t depositBits(uint64_t value, const BitSpec& spec) {
+    uint64_t out = 0;
+    for (uint32_t q = 0; q < spec.n; q++) out |= ((value >> q) & 1ULL) << spec.pos[q];
+    return out;
+}
+
+inline uint64_t rankShiftOf(const dfsa_state* s, int rank) { return (uint64_t)rank << s->logNumAmps; }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// K1 + K2: local_statevector.hpp:14-29 (oneTarg) and :32-51 (manyCtrlOneTarg).
+// item j -> i1 = insert ones at sorted(ctrls U {target}); i0 = i1 with the target bit cleared.
+// HBM traffic: 32 B per touched amplitude pair half, i.e. 32*A/2^c bytes for c controls.
+template <int NPOS>
+static int launchCtrlOneTarg(double2* amps, uint64_t items, const BitSpec& spec, uint64_t ones, uint64_t targBit, const Gate2& g) {
+    using Item = PairAt;   // idx = i1
+    auto ld = [=] __device__(uint64_t j) {
+        Item it;
+        uint64_t v = (NPOS > 0) ? insertZeroBitsN<(NPOS > 0 ? NPOS : 1)>(j, spec) : insertZeroBits(j, spec);
+        it.idx = v | ones;
+        it.a1 = amps[it.idx];
+        it.a0 = amps[it.idx ^ targBit];
+        return it;
+    };
+    auto st = [=] __device__(uint64_t, const Item& it) {
+        amps[it.idx ^ targBit] = cfma(g.m01, it.a1, cmul(g.m00, it.a0));
+        amps[it.idx]           = cfma(g.m11, it.a1, cmul(g.m10, it.a0));
+    };
+    return launchStream<2, Item>(items, ld, st);
+}
+
+extern "C" int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, unsigned target, const double gate[8]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && gate, "null argument");
+    DFSA_REQUIRE(numCtrls + 1 <= s->logNumAmps, "more qubits than local bits");
+    std::vector<uint32_t> qs(ctrls, ctrls + numCtrls);
+    qs.push_back(target);
+    BitSpec spec;
+    uint64_t ones;
+    DFSA_TRY(sortedSpec(qs.data(), numCtrls + 1, s->logNumAmps, &spec, &ones));
+    Gate2 g{hostAmp(gate), hostAmp(gate + 2), hostAmp(gate + 4), hostAmp(gate + 6)};
+    uint64_t items = s->numAmps >> (numCtrls + 1);
+    uint64_t targBit = 1ULL << target;
+    double2* a = s->arr[DFSA_AMPS];
+    switch (spec.n) {
+        case 1:  return launchCtrlOneTarg<1>(a, items, spec, ones, targBit, g);
+        case 2:  return launchCtrlOneTarg<2>(a, items, spec, ones, targBit, g);
+        case 3:  return launchCtrlOneTarg<3>(a, items, spec, ones, targBit, g);
+        case 4:  return launchCtrlOneTarg<4>(a, items, spec, ones, targBit, g);
+        default: return launchCtrlOneTarg<0>(a, items, spec, ones, targBit, g);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K3: local_statevector.hpp:54-69. Pure permutation (bit-exact): amps[..01..] <-> amps[..10..]. 16*A bytes.
+extern "C" int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    DFSA_REQUIRE(qb1 != qb2 && qb1 < s->logNumAmps && qb2 < s->logNumAmps, "swap needs two distinct suffix qubits");
+    unsigned lo = std::min(qb1, qb2), hi = std::max(qb1, qb2);
+    uint64_t bLo = 1ULL << lo, bHi = 1ULL << hi;
+    double2* amps = s->arr[DFSA_AMPS];
+    using Item = PairAt;   // a0 = amp at ..01.., a1 = amp at ..10.., idx = j10
+    auto ld = [=] __device__(uint64_t k) {
+        Item it;
+        it.idx = insertZeroBit(insertZeroBit(k, lo), hi) | bHi;       // hi qubit = 1, lo qubit = 0
+        it.a1 = amps[it.idx];
+        it.a0 = amps[it.idx ^ bHi ^ bLo];
+        return it;
+    };
+    auto st = [=] __device__(uint64_t, const Item& it) {
+        amps[it.idx] = it.a0;
+        amps[it.idx ^ bHi ^ bLo] = it.a1;
+    };
+    return launchStream<2, Item>(s->numAmps >> 2, ld, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// diagonal-by-parity kernel: amps[j] *= (parity(global(j) & mask) ? c1 : c0).
+// K6 (local_statevector.hpp:138-153) and the X/Y-free Pauli case.
+static int launchDiagParity(dfsa_state* s, uint64_t mask, double2 c0, double2 c1) {
+    double2* amps = s->arr[DFSA_AMPS];
+    uint64_t rs = rankShiftOf(s, s->rank);
+    auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[j] = cmul(v.a, parity64((rs | j) & mask) ? c1 : c0); };
+    return launchStream<4, Amp1>(s->numAmps, ld, st);
+}
+
+extern "C" int dfsa_k_phase(dfsa_state* s, uint64_t targMask, double theta) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    double c = cos(theta), sn = sin(theta);
+    return launchDiagParity(s, targMask, make_double2(c, sn), make_double2(c, -sn));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K5: local_statevector.hpp:102-135. Pairs (j0, j1 = j0 ^ maskXY), j0 has the highest X/Y bit clear.
+//   amps[j0] = f*a0 + (g*b1)*a1,  amps[j1] = f*a1 + (g*b0)*a0,  b = i^numY * (-1)^parity(global & maskYZ)
+// EXACT (pauliTensor, f=0 g=1): pure move + multiplication by a power of i -> bit-exact.
+template <bool EXACT>
+static int launchPauliPairs(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, unsigned numY, double2 f, double2 h) {
+    double2* amps = s->arr[DFSA_AMPS];
+    uint64_t rs = rankShiftOf(s, s->rank);
+    unsigned hiPos = 63u - (unsigned)__builtin_clzll(maskXY);
+    using Item = PairAt;   // idx = j0
+    auto ld = [=] __device__(uint64_t j) {
+        Item it;
+        it.idx = insertZeroBit(j, hiPos);
+        it.a0 = amps[it.idx];
+        it.a1 = amps[it.idx ^ maskXY];
+        return it;
+    };
+    auto st = [=] __device__(uint64_t, const Item& it) {
+        uint64_t j1 = it.idx ^ maskXY;
+        unsigned p0 = parity64((rs | it.idx) & maskYZ), p1 = parity64((rs | j1) & maskYZ);
+        if (EXACT) {
+            amps[it.idx] = mulPowI(it.a1, numY + 2u * p1);
+            amps[j1]    = mulPowI(it.a0, numY + 2u * p0);
+        } else {
+            double2 h1 = p1 ? make_double2(-h.x, -h.y) : h, h0 = p0 ? make_double2(-h.x, -h.y) : h;
+            amps[it.idx] = cfma(h1, it.a1, cmul(f, it.a0));
+            amps[j1]    = cfma(h0, it.a0, cmul(f, it.a1));
+        }
+    };
+    return launchStream<2, Item>(s->numAmps >> 1, ld, st);
+}
+
+static double2 powIHost(unsigned k) {
+    switch (k & 3u) { case 0: return make_double2(1, 0); case 1: return make_double2(0, 1); case 2: return make_double2(-1, 0); default: return make_double2(0, -1); }
+}
+static double2 cmulHost(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
+extern "C" int dfsa_k_pauli(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, unsigned numY, const double f[2], const double g[2], int exact) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && f && g, "null argument");
+    DFSA_REQUIRE((maskXY >> s->logNumAmps) == 0, "maskXY must only hold suffix bits");
+    double2 ff = hostAmp(f), h = cmulHost(hostAmp(g), powIHost(numY));
+    if (maskXY == 0) {
+        // No X/Y on this shard: the operator is diagonal, amps[j] *= f + (+-)g*i^numY.  (The reference's local
+        // loop has 2^0/2 = 0 inner iterations here and silently does nothing; this build applies the operator.)
+        if (exact) {
+            double2 p = powIHost(numY);
+            return launchDiagParity(s, maskYZ, p, make_double2(-p.x, -p.y));
+        }
+        return launchDiagParity(s, maskYZ, make_double2(ff.x + h.x, ff.y + h.y), make_double2(ff.x - h.x, ff.y - h.y));
+    }
+    return exact ? launchPauliPairs<true>(s, maskXY, maskYZ, numY, ff, h) : launchPauliPairs<false>(s, maskXY, maskYZ, numY, ff, h);
+}
+
+// K11: distributed_statevector.hpp:227-241. amps[j0] = f*amps[j0] + g*b1*buffer[j0 ^ maskXY], sign from the
+// partner's global index. 48*A bytes (read amps, read buffer, write amps).
+template <bool EXACT>
+static int launchPauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, double2 f, double2 h) {
+    double2* amps = s->arr[DFSA_AMPS];
+    const double2* buf = s->arr[DFSA_BUFFER];
+    uint64_t rs = rankShiftOf(s, pairRank);
+    auto ld = [=] __device__(uint64_t j0) { return Amp2{amps[j0], buf[j0 ^ maskXY]}; };
+    auto st = [=] __device__(uint64_t j0, const Amp2& v) {
+        unsigned p1 = parity64((rs | (j0 ^ maskXY)) & maskYZ);
+        if (EXACT) amps[j0] = mulPowI(v.a1, numY + 2u * p1);
+        else {
+            double2 h1 = p1 ? make_double2(-h.x, -h.y) : h;
+            amps[j0] = cfma(h1, v.a1, cmul(f, v.a0));
+        }
+    };
+    return launchStream<2, Amp2>(s->numAmps, ld, st);
+}
+
+extern "C" int dfsa_k_pauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, const double f[2], const double g[2], int exact) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && f && g && s->arr[DFSA_BUFFER], "null argument / no exchange buffer");
+    double2 ff = hostAmp(f), h = cmulHost(hostAmp(g), powIHost(numY));
+    return exact ? launchPauliCombine<true>(s, pairRank, maskXY, maskYZ, numY, ff, h) : launchPauliCombine<false>(s, pairRank, maskXY, maskYZ, numY, ff, h);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K7: distributed_statevector.hpp:36-38. amps[i] = f0*amps[i] + f1*buffer[i]. 48*A bytes.
+extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1[2]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && f0 && f1 && s->arr[DFSA_BUFFER], "null argument / no exchange buffer");
+    double2* amps = s->arr[DFSA_AMPS];
+    const double2* buf = s->arr[DFSA_BUFFER];
+    double2 c0 = hostAmp(f0), c1 = hostAmp(f1);
+    auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], buf[i]}; };
+    auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    return launchStream<2, Amp2>(s->numAmps, ld, st);
+}
+
+// K18: distributed_densitymatrix.hpp:44-49 (amp *= -1) generalised to a complex factor.
+extern "C" int dfsa_k_scaleAll(dfsa_state* s, const double factor[2]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && factor, "null argument");
+    double2* amps = s->arr[DFSA_AMPS];
+    double2 c = hostAmp(factor);
+    bool negate = (c.x == -1.0 && c.y == 0.0);
+    auto ld = [=] __device__(uint64_t i) { return Amp1{amps[i]}; };
+    auto st = [=] __device__(uint64_t i, const Amp1& v) { amps[i] = negate ? make_double2(-v.a.x, -v.a.y) : cmul(v.a, c); };
+    return launchStream<4, Amp1>(s->numAmps, ld, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K8 / K10 / K19-K22 building blocks on a sub-cube: k = j with `values` bits inserted at sorted `positions`.
+static int subcubeSpec(dfsa_state* s, const uint32_t* positions, unsigned n, uint64_t values, BitSpec* spec, uint64_t* fixed) {
+    DFSA_REQUIRE(s && s->arr[DFSA_BUFFER], "null state / no exchange buffer");
+    DFSA_REQUIRE(n >= 1 && n <= s->logNumAmps, "bad number of positions");
+    for (unsigned q = 1; q < n; q++) DFSA_REQUIRE(positions[q] > positions[q - 1], "positions must be strictly increasing");
+    DFSA_TRY(sortedSpec(positions, n, s->logNumAmps, spec, nullptr));
+    *fixed = depositBits(values, *spec);
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_k_pack(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t dstStart) {
+    DFSA_TRY(dfsaEnsureDevice());
+    BitSpec spec; uint64_t fixed;
+    DFSA_TRY(subcubeSpec(s, positions, numPositions, values, &spec, &fixed));
+    uint64_t items = s->numAmps >> numPositions;
+    DFSA_REQUIRE(dstStart + items <= s->numAmps, "pack overruns the buffer");
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* buf = s->arr[DFSA_BUFFER] + dstStart;
+    auto ld = [=] __device__(uint64_t j) { return Amp1{amps[insertZeroBits(j, spec) | fixed]}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) { buf[j] = v.a; };
+    return launchStream<4, Amp1>(items, ld, st);
+}
+
+extern "C" int dfsa_k_unpack(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart) {
+    DFSA_TRY(dfsaEnsureDevice());
+    BitSpec spec; uint64_t fixed;
+    DFSA_TRY(subcubeSpec(s, positions, numPositions, values, &spec, &fixed));
+    uint64_t items = s->numAmps >> numPositions;
+    DFSA_REQUIRE(srcStart + items <= s->numAmps, "unpack overruns the buffer");
+    double2* amps = s->arr[DFSA_AMPS];
+    const double2* buf = s->arr[DFSA_BUFFER] + srcStart;
+    auto ld = [=] __device__(uint64_t j) { return Amp1{buf[j]}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[insertZeroBits(j, spec) | fixed] = v.a; };
+    return launchStream<4, Amp1>(items, ld, st);
+}
+
+extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
+                                 const double f0[2], const double f1[2]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    BitSpec spec; uint64_t fixed;
+    DFSA_TRY(subcubeSpec(s, positions, numPositions, values, &spec, &fixed));
+    uint64_t items = s->numAmps >> numPositions;
+    DFSA_REQUIRE(srcStart + items <= s->numAmps && f0 && f1, "combineSub overruns the buffer / null factor");
+    double2* amps = s->arr[DFSA_AMPS];
+    const double2* buf = s->arr[DFSA_BUFFER] + srcStart;
+    double2 c0 = hostAmp(f0), c1 = hostAmp(f1);
+    auto ld = [=] __device__(uint64_t j) { return Amp2{amps[insertZeroBits(j, spec) | fixed], buf[j]}; };
+    auto st = [=] __device__(uint64_t j, const Amp2& v) { amps[insertZeroBits(j, spec) | fixed] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    return launchStream<2, Amp2>(items, ld, st);
+}
+
+// K9: distributed_statevector.hpp:133-135, 152-156
+extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t srcStart, uint64_t num) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && s->arr[DFSA_BUFFER], "null state / no exchange buffer");
+    DFSA_REQUIRE(dstStart + num <= s->numAmps && srcStart + num <= s->numAmps, "copy out of range");
+    DFSA_CUDA(cudaMemcpyAsync(s->arr[DFSA_AMPS] + dstStart, s->arr[DFSA_BUFFER] + srcStart, num * sizeof(double2), cudaMemcpyDeviceToDevice, dfsaCtx().compute));
+    return DFSA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K4: local_statevector.hpp:72-99. Dense 2^t x 2^t gate, row/col bit i <-> targets[i] (caller order).
+//
+// Tile kernel (t <= 6): a tile is the 2^(t+f) amplitudes spanned by the t target bits and the f (<= 5) lowest
+// non-target bits, staged in shared memory as X[row][lane] (row = gate-ordered target bits, lane = the f free
+// bits), so that: global loads/stores are contiguous runs of 2^(low bits) amplitudes; the inner product reads
+// X[l][lane] conflict-free (consecutive lanes -> consecutive 16-byte words) and the gate as a warp-wide
+// broadcast G^T[l][r..r+R). Each thread accumulates R rows of one vector in registers: R*4 DFMA per
+// (1 + R) 16-byte shared loads. 32*A bytes of HBM traffic and 8*2^t flop per amplitude (FP64 pipe bound for t>=5).
+template <int R>
+__global__ void __launch_bounds__(256) manyTargTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec,
+                                                         unsigned t, unsigned f, const double2* __restrict__ gateT,
+                                                         /* role of tile-local bit b: < t -> gate bit, else free bit (role - t) */ BitSpec localPos) {
+    extern __shared__ double2 smem[];
+    const unsigned d = 1u << t, lanes = 1u << f, tileAmps = d << f;
+    double2* G = smem;                 // G^T[l][r], d*d
+    double2* X = smem + (size_t)d * d; // X[row][lane], tileAmps
+    for (unsigned e = threadIdx.x; e < d * d; e += blockDim.x) G[e] = gateT[e];
+
+    // Element e of a tile (ascending address order -> coalesced) always maps to the same address offset and the
+    // same X slot; a thread owns elements e = tid + k*256, k < 8 (tileAmps <= 2^11).
+    uint64_t gOff[8];
+    unsigned xIdx[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned e = threadIdx.x + k * 256;
+        uint64_t g = 0;
+        unsigned row = 0, lane = 0;
+        for (unsigned b = 0; b < t + f; b++) {
+            unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
+            g |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < t) row |= bit << role; else lane |= bit << (role - t);
+        }
+        gOff[k] = g;
+        xIdx[k] = row * lanes + lane;
+    }
+    // one work item per thread: R consecutive gate rows of one lane (host guarantees (d/R)*lanes <= 256)
+    const unsigned myLane = threadIdx.x % lanes, r0 = (threadIdx.x / lanes) * R;
+    const bool active = r0 < d;
+
+    for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const uint64_t base = insertZeroBits(tile, tileSpec);
+        __syncthreads();                             // G staged / previous tile fully written out
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (threadIdx.x + k * 256 < tileAmps) X[xIdx[k]] = amps[base | gOff[k]];
+        __syncthreads();
+        double2 acc[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) acc[i] = make_double2(0.0, 0.0);
+        if (active) {
+            for (unsigned l = 0; l < d; l++) {
+                const double2 x = X[l * lanes + myLane];
+                const double2* grow = G + (size_t)l * d + r0;
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = cfma(grow[i], x, acc[i]);
+            }
+        }
+        __syncthreads();                             // every read of X done before it is overwritten
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < R; i++) X[(r0 + i) * lanes + myLane] = acc[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (threadIdx.x + k * 256 < tileAmps) amps[base | gOff[k]] = X[xIdx[k]];
+    }
+}
+
+// Generic kernel (any t with 2^t amplitudes fitting shared memory): one block per group, gate streamed from
+// global memory (L2-resident), one warp per output row with a shuffle reduction over columns.
+__global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint64_t numGroups, BitSpec sortedTargs, BitSpec callerTargs,
+                                                            unsigned t, const double2* __restrict__ gate) {
+    extern __shared__ double2 smem[];
+    const uint64_t d = 1ULL << t;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, numWarps = blockDim.x >> 5;
+    for (uint64_t grp = blockIdx.x; grp < numGroups; grp += gridDim.x) {
+        uint64_t base = insertZeroBits(grp, sortedTargs);
+        __syncthreads();
+        for (uint64_t l = threadIdx.x; l < d; l += blockDim.x) {
+            uint64_t g = base;
+            for (unsigned b = 0; b < t; b++) g |= ((l >> b) & 1ULL) << callerTargs.pos[b];
+            smem[l] = amps[g];
+        }
+        __syncthreads();
+        for (uint64_t r = warp; r < d; r += numWarps) {
+            double2 acc = make_double2(0.0, 0.0);
+            const double2* grow = gate + r * d;
+            for (uint64_t l = lane; l < d; l += 32) acc = cfma(grow[l], smem[l], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+            }
+            if (lane == 0) {
+                uint64_t g = base;
+                for (unsigned b = 0; b < t; b++) g |= ((r >> b) & 1ULL) << callerTargs.pos[b];
+                amps[g] = acc;
+            }
+        }
+    }
+}
+
+extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && targets && gate, "null argument");
+    const unsigned t = numTargets, L = s->logNumAmps;
+    DFSA_REQUIRE(t >= 1 && t <= L, "manyTargGate needs 1 <= numTargets <= local bits (distributed_statevector.hpp:191)");
+    BitSpec sortedT; uint64_t targMask;
+    DFSA_TRY(sortedSpec(targets, t, L, &sortedT, &targMask));
+    const uint64_t d = 1ULL << t;
+    DfsaContext& ctx = dfsaCtx();
+
+    if (t <= 6) {
+        // transposed gate G^T[l][r] to device scratch
+        std::vector<double2> gt(d * d);
+        for (uint64_t r = 0; r < d; r++) for (uint64_t l = 0; l < d; l++) gt[l * d + r] = hostAmp(gate + 2 * (r * d + l));
+        double2* dev;
+        DFSA_TRY(dfsaScratch(d * d * sizeof(double2), &dev));
+        DFSA_CUDA(cudaMemcpyAsync(dev, gt.data(), d * d * sizeof(double2), cudaMemcpyHostToDevice, ctx.compute));
+        DFSA_CUDA(cudaStreamSynchronize(ctx.compute));   // gt is a stack-lifetime pageable buffer
+
+        unsigned f = std::min(5u, L - t);
+        // tile bits = targets U the f lowest non-target bits, sorted
+        std::vector<uint32_t> tileBits(targets, targets + t);
+        std::vector<uint32_t> freeBits;
+        for (unsigned b = 0; b < L && freeBits.size() < f; b++) if (!((targMask >> b) & 1ULL)) freeBits.push_back(b);
+        tileBits.insert(tileBits.end(), freeBits.begin(), freeBits.end());
+        BitSpec tileSpec;
+        DFSA_TRY(sortedSpec(tileBits.data(), t + f, L, &tileSpec, nullptr));
+        BitSpec localPos; localPos.n = t + f;
+        for (unsigned b = 0; b < t + f; b++) {
+            unsigned q = tileSpec.pos[b], role = 0;
+            bool found = false;
+            for (unsigned i = 0; i < t; i++) if (targets[i] == q) { role = i; found = true; }
+            if (!found) for (unsigned i = 0; i < f; i++) if (freeBits[i] == q) role = t + i;
+            localPos.pos[b] = (uint8_t)role;
+        }
+        const unsigned R = (unsigned)std::max<uint64_t>(1, d / 8);   // (d/R) * 2^f <= 8 * 32 = 256 work items = one per thread
+        size_t smemBytes = (d * d + (d << f)) * sizeof(double2);
+        uint64_t numTiles = s->numAmps >> (t + f);
+        unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 4);
+#define DFSA_LAUNCH_TILE(RR)                                                                                                        \
+        do {                                                                                                                        \
+            DFSA_CUDA(cudaFuncSetAttribute(manyTargTileKernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));    \
+            manyTargTileKernel<RR><<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, t, f, dev, localPos); \
+        } while (0)
+        switch (R) { case 1: DFSA_LAUNCH_TILE(1); break; case 2: DFSA_LAUNCH_TILE(2); break; case 4: DFSA_LAUNCH_TILE(4); break; default: DFSA_LAUNCH_TILE(8); break; }
+#undef DFSA_LAUNCH_TILE
+        DFSA_LAUNCH_CHECK();
+        return DFSA_OK;
+    }
+
+    DFSA_REQUIRE(d * sizeof(double2) <= 200 * 1024, "manyTargGate: 2^numTargets amplitudes must fit shared memory (numTargets <= 13)");
+    BitSpec caller; caller.n = t;
+    for (unsigned i = 0; i < t; i++) caller.pos[i] = (uint8_t)targets[i];
+    double2* dev;
+    DFSA_TRY(dfsaScratch(d * d * sizeof(double2), &dev));
+    DFSA_CUDA(cudaMemcpyAsync(dev, gate, d * d * sizeof(double2), cudaMemcpyHostToDevice, ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(ctx.compute));
+    size_t smemBytes = d * sizeof(double2);
+    DFSA_CUDA(cudaFuncSetAttribute(manyTargGenericKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    uint64_t numGroups = s->numAmps >> t;
+    unsigned grid = (unsigned)std::min<uint64_t>(numGroups, (uint64_t)ctx.numSMs * 2);
+    manyTargGenericKernel<<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numGroups, sortedT, caller, t, dev);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}

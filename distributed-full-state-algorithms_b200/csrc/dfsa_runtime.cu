@@ -1,0 +1,220 @@
+// dfsa_runtime.cu -- context, error reporting and state storage of libdfsa_b200.so.
+// Replaces the std::vector storage of the reference's StateVector/DensityMatrix (src/states.hpp:13-69):
+// each rank's amplitude shard and its equal-size exchange buffer are plain cudaMalloc regions in HBM.
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+
+#include "dfsa_stream_kernels.cuh"
+
+static thread_local char g_err[1024] = "";
+static DfsaContext g_ctx;
+
+DfsaContext& dfsaCtx() { return g_ctx; }
+
+void dfsaSetError(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    if (getenv("DFSA_VERBOSE")) fprintf(stderr, "[dfsa rank %d] %s\n", g_ctx.rank, g_err);
+}
+
+extern "C" const char* dfsa_last_error(void) { return g_err; }
+extern "C" const char* dfsa_version(void) { return "dfsa_b200 0.1 (sm_100a)"; }
+
+int dfsaEnsureDevice() {
+    DfsaContext& c = g_ctx;
+    if (c.compute) return DFSA_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        dfsaSetError("no CUDA device available (%s); libdfsa_b200 has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return DFSA_ERR_CUDA;
+    }
+    if (!c.initialised) c.device = 0;   // single-rank use without dfsa_comm_init
+    DFSA_CUDA(cudaSetDevice(c.device % count));
+    cudaDeviceProp prop;
+    DFSA_CUDA(cudaGetDeviceProperties(&prop, c.device % count));
+    c.numSMs = prop.multiProcessorCount;
+    DFSA_CUDA(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+    DFSA_CUDA(cudaStreamCreateWithFlags(&c.comm, cudaStreamNonBlocking));
+    DFSA_CUDA(cudaEventCreateWithFlags(&c.evCompute, cudaEventDisableTiming));
+    DFSA_CUDA(cudaEventCreateWithFlags(&c.evComm, cudaEventDisableTiming));
+    DFSA_CUDA(cudaHostAlloc((void**)&c.hostPinned, 4096, cudaHostAllocDefault));
+    return DFSA_OK;
+}
+
+int dfsaScratch(size_t bytes, double2** out) {
+    DfsaContext& c = g_ctx;
+    if (bytes > c.devScratchBytes) {
+        // the previous scratch may still be read by an enqueued kernel
+        DFSA_CUDA(cudaStreamSynchronize(c.compute));
+        if (c.devScratch) DFSA_CUDA(cudaFree(c.devScratch));
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        DFSA_CUDA(cudaMalloc((void**)&c.devScratch, want));
+        c.devScratchBytes = want;
+    }
+    *out = c.devScratch;
+    return DFSA_OK;
+}
+
+extern "C" void* dfsa_stream_compute(void) { return dfsaEnsureDevice() == DFSA_OK ? (void*)g_ctx.compute : nullptr; }
+
+extern "C" int dfsa_device_sync(void) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.comm));
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    return DFSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ states
+
+extern "C" int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state** out) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(out, "null out pointer");
+    DfsaContext& c = g_ctx;
+    unsigned k = 0;
+    while ((1 << k) < c.size) k++;
+    DFSA_REQUIRE((1 << k) == c.size, "number of ranks must be a power of 2 (README.md:134)");
+    DFSA_REQUIRE(numQubits >= 1 && numQubits < 63 && (numQubits >= 31 || (1ULL << numQubits) >= (uint64_t)c.size),
+                 "need 2^numQubits >= number of ranks (states.hpp:35)");
+    unsigned bits = isDensity ? 2 * numQubits : numQubits;
+    DFSA_REQUIRE(bits < 63 && bits >= k, "state too large / too small for this many ranks");
+    dfsa_state* s = new dfsa_state();
+    s->isDensity = isDensity ? 1 : 0;
+    s->numQubits = numQubits;
+    s->rank = c.rank;
+    s->numNodes = c.size;
+    s->logNumNodes = k;
+    s->logNumAmps = bits - k;
+    s->numAmps = 1ULL << s->logNumAmps;
+    s->arr[0] = s->arr[1] = nullptr;
+    s->allocId[0] = s->allocId[1] = -1;
+    size_t bytes = s->numAmps * sizeof(double2);
+    int numArrays = (c.size > 1) ? 2 : 1;          // the exchange buffer is only ever touched when P > 1
+    for (int w = 0; w < numArrays; w++) {
+        cudaError_t e = cudaMalloc((void**)&s->arr[w], bytes);
+        if (e != cudaSuccess) {
+            dfsaSetError("cudaMalloc of %zu bytes for the %s failed: %s", bytes, w ? "exchange buffer" : "amplitude shard", cudaGetErrorString(e));
+            if (s->arr[0]) cudaFree(s->arr[0]);
+            delete s;
+            return DFSA_ERR_CUDA;
+        }
+        DFSA_CUDA(cudaMemsetAsync(s->arr[w], 0, bytes, c.compute));
+    }
+    if (c.size > 1)
+        for (int w = 0; w < 2; w++) DFSA_TRY(dfsaRegisterAllocation(s->arr[w], bytes, &s->allocId[w]));
+    *out = s;
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_state_destroy(dfsa_state* s) {
+    if (!s) return DFSA_OK;
+    DFSA_TRY(dfsa_device_sync());
+    if (g_ctx.size > 1)
+        for (int w = 0; w < 2; w++) if (s->allocId[w] >= 0) DFSA_TRY(dfsaUnregisterAllocation(s->allocId[w]));
+    for (int w = 0; w < 2; w++) if (s->arr[w]) DFSA_CUDA(cudaFree(s->arr[w]));
+    delete s;
+    return DFSA_OK;
+}
+
+extern "C" double* dfsa_state_ptr(dfsa_state* s, int which) { return (s && (which == 0 || which == 1)) ? (double*)s->arr[which] : nullptr; }
+extern "C" uint64_t dfsa_state_num_amps_per_node(const dfsa_state* s) { return s ? s->numAmps : 0; }
+extern "C" unsigned dfsa_state_log_num_amps_per_node(const dfsa_state* s) { return s ? s->logNumAmps : 0; }
+extern "C" unsigned dfsa_state_num_qubits(const dfsa_state* s) { return s ? s->numQubits : 0; }
+extern "C" int dfsa_state_is_density(const dfsa_state* s) { return s ? s->isDensity : 0; }
+
+extern "C" int dfsa_state_swap_arrays(dfsa_state* s) {
+    DFSA_REQUIRE(s && s->arr[1], "no exchange buffer to swap with");
+    std::swap(s->arr[0], s->arr[1]);
+    std::swap(s->allocId[0], s->allocId[1]);
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_state_upload(dfsa_state* s, int which, uint64_t first, uint64_t num, const double* host) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && host && (which == 0 || which == 1) && s->arr[which], "bad argument");
+    DFSA_REQUIRE(first + num <= s->numAmps, "range exceeds the shard");
+    DFSA_CUDA(cudaMemcpyAsync(s->arr[which] + first, host, num * sizeof(double2), cudaMemcpyHostToDevice, g_ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_state_download(dfsa_state* s, int which, uint64_t first, uint64_t num, double* host) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && host && (which == 0 || which == 1) && s->arr[which], "bad argument");
+    DFSA_REQUIRE(first + num <= s->numAmps, "range exceeds the shard");
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.comm));
+    DFSA_CUDA(cudaMemcpyAsync(host, s->arr[which] + first, num * sizeof(double2), cudaMemcpyDeviceToHost, g_ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_state_upload_all(dfsa_state* s, const double* hostAll) {
+    DFSA_REQUIRE(s && hostAll, "null argument");
+    return dfsa_state_upload(s, DFSA_AMPS, 0, s->numAmps, hostAll + 2 * (uint64_t)s->rank * s->numAmps);
+}
+
+extern "C" int dfsa_state_init_zero(dfsa_state* s) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    DFSA_CUDA(cudaMemsetAsync(s->arr[0], 0, s->numAmps * sizeof(double2), g_ctx.compute));
+    return DFSA_OK;
+}
+
+// the synthetic state of SURVEY 8(d): amp(i) = hash(seed, global index i), reproducible on the host
+// (oracle/dfsa_oracle.c: orc_init_hash, oracle/ref_driver.cpp: hashReal)
+__device__ __forceinline__ double hashReal(uint64_t seed, uint64_t k) {
+    uint64_t z = seed + (k + 1ULL) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+extern "C" int dfsa_state_init_hash(dfsa_state* s, uint64_t seed) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    double2* amps = s->arr[0];
+    uint64_t first = (uint64_t)s->rank << s->logNumAmps;
+    auto ld = [=] __device__(uint64_t j) { return Amp1{make_double2(hashReal(seed, 2 * (first + j)), hashReal(seed, 2 * (first + j) + 1))}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[j] = v.a; };
+    return launchStream<4, Amp1>(s->numAmps, ld, st);
+}
+
+// sum |amp|^2 : block partials -> host sum (deterministic order)
+__global__ void __launch_bounds__(256) norm2Kernel(const double2* __restrict__ amps, uint64_t n, double* partials) {
+    double acc = 0.0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double2 a = amps[i];
+        acc = fma(a.x, a.x, fma(a.y, a.y, acc));
+    }
+    __shared__ double warpSums[8];
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) warpSums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += warpSums[w];
+        partials[blockIdx.x] = t;
+    }
+}
+
+extern "C" int dfsa_state_norm2(dfsa_state* s, double* out) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && out, "null argument");
+    unsigned grid = dfsaGrid(s->numAmps, 256, 4, 8);
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(grid * sizeof(double), &scratch));
+    norm2Kernel<<<grid, 256, 0, g_ctx.compute>>>(s->arr[0], s->numAmps, (double*)scratch);
+    DFSA_LAUNCH_CHECK();
+    std::vector<double> partials(grid);
+    DFSA_CUDA(cudaMemcpyAsync(partials.data(), scratch, grid * sizeof(double), cudaMemcpyDeviceToHost, g_ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    double reim[2] = {0.0, 0.0};
+    for (double p : partials) reim[0] += p;
+    if (g_ctx.size > 1) DFSA_TRY(dfsa_x_allreduce_amp(reim));
+    *out = reim[0];
+    return DFSA_OK;
+}

@@ -1,0 +1,111 @@
+// dfsa_host_capi.cpp -> libdfsa_host.so : extern "C" face of the drop-in host C++ API (host/*.hpp), so that
+// non-C++ callers (the Python parity tests and bench.py via ctypes, or any FFI) drive exactly the code path a
+// C++ user of distributed_statevector.hpp / distributed_densitymatrix.hpp gets:
+//     ctypes -> these wrappers -> host dispatch (local vs. exchange, relocation) -> C-ABI of libdfsa_b200.so -> CUDA.
+// One function per public entry point of the reference API, same argument order; vectors become (pointer, count),
+// matrices row-major interleaved (re,im) doubles. Handles are StateVector* / DensityMatrix*.
+#include <cstring>
+
+#include "distributed_densitymatrix.hpp"
+#include "distributed_statevector.hpp"
+
+namespace {
+AmpMatrix toMatrix(const double* flat, Index dim) {
+    AmpMatrix m = getZeroMatrix(dim);
+    for (Index r = 0; r < dim; r++)
+        for (Index c = 0; c < dim; c++) m[r][c] = Amp(flat[2 * (r * dim + c)], flat[2 * (r * dim + c) + 1]);
+    return m;
+}
+NatArray toNats(const unsigned* p, unsigned n) { return NatArray(p, p + n); }
+StateVector& sv(void* h) { return *static_cast<StateVector*>(h); }
+DensityMatrix& dm(void* h) { return *static_cast<DensityMatrix*>(h); }
+}  // namespace
+
+extern "C" {
+
+// ---- environment (communication.hpp)
+void dfsa_host_comm_init() { comm_init(); }
+void dfsa_host_comm_end() { comm_end(); }
+unsigned dfsa_host_comm_getRank() { return comm_getRank(); }
+unsigned dfsa_host_comm_getNumNodes() { return comm_getNumNodes(); }
+void dfsa_host_comm_synch() { comm_synch(); }
+
+// ---- states (states.hpp)
+void* dfsa_host_StateVector_new(unsigned numQubits) { return new StateVector(numQubits); }
+void* dfsa_host_DensityMatrix_new(unsigned numQubits) { return new DensityMatrix(numQubits); }
+void dfsa_host_state_delete(void* h) { delete static_cast<StateVector*>(h); }
+void* dfsa_host_state_handle(void* h) { return sv(h).handle; }
+unsigned dfsa_host_state_numQubits(void* h) { return sv(h).numQubits; }
+unsigned long long dfsa_host_state_numAmpsPerNode(void* h) { return sv(h).numAmpsPerNode; }
+unsigned dfsa_host_state_logNumAmpsPerNode(void* h) { return unsigned(sv(h).logNumAmpsPerNode); }
+void dfsa_host_state_getAllVecAmps(void* h, double* out) {
+    AmpArray all = sv(h).getAllVecAmps();
+    std::memcpy(out, all.data(), all.size() * sizeof(Amp));
+}
+void dfsa_host_state_setAllVecAmps(void* h, const double* in) {
+    StateVector& s = sv(h);
+    const Amp* p = reinterpret_cast<const Amp*>(in);
+    s.setAllVecAmps(AmpArray(p, p + Index(s.numNodes) * s.numAmpsPerNode));
+}
+void dfsa_host_state_setHashAmps(void* h, unsigned long long seed) { sv(h).setHashAmps(seed); }
+double dfsa_host_state_getNorm2(void* h) { return sv(h).getNorm2(); }
+
+// ---- state-vector API (distributed_statevector.hpp)
+void dfsa_host_sv_oneTargGate(void* h, unsigned target, const double* gate) {
+    distributed_statevector_oneTargGate(sv(h), target, toMatrix(gate, 2));
+}
+void dfsa_host_sv_manyCtrlOneTargGate(void* h, const unsigned* ctrls, unsigned numCtrls, unsigned target, const double* gate) {
+    distributed_statevector_manyCtrlOneTargGate(sv(h), toNats(ctrls, numCtrls), target, toMatrix(gate, 2));
+}
+void dfsa_host_sv_swapGate(void* h, unsigned qb1, unsigned qb2) { distributed_statevector_swapGate(sv(h), qb1, qb2); }
+void dfsa_host_sv_manyTargGate(void* h, const unsigned* targets, unsigned numTargets, const double* gate) {
+    distributed_statevector_manyTargGate(sv(h), toNats(targets, numTargets), toMatrix(gate, powerOf2(numTargets)));
+}
+void dfsa_host_sv_pauliTensor(void* h, const unsigned* targets, const unsigned* paulis, unsigned n) {
+    distributed_statevector_pauliTensor(sv(h), toNats(targets, n), toNats(paulis, n));
+}
+void dfsa_host_sv_pauliGadget(void* h, const unsigned* targets, const unsigned* paulis, unsigned n, double theta) {
+    distributed_statevector_pauliGadget(sv(h), toNats(targets, n), toNats(paulis, n), theta);
+}
+void dfsa_host_sv_phaseGadget(void* h, const unsigned* targets, unsigned n, double theta) {
+    distributed_statevector_phaseGadget(sv(h), toNats(targets, n), theta);
+}
+
+// ---- density-matrix API (distributed_densitymatrix.hpp)
+void dfsa_host_dm_manyTargGate(void* h, const unsigned* targets, unsigned numTargets, const double* gate) {
+    distributed_densitymatrix_manyTargGate(dm(h), toNats(targets, numTargets), toMatrix(gate, powerOf2(numTargets)));
+}
+void dfsa_host_dm_swapGate(void* h, unsigned qb1, unsigned qb2) { distributed_densitymatrix_swapGate(dm(h), qb1, qb2); }
+void dfsa_host_dm_pauliTensor(void* h, const unsigned* targets, const unsigned* paulis, unsigned n) {
+    distributed_densitymatrix_pauliTensor(dm(h), toNats(targets, n), toNats(paulis, n));
+}
+void dfsa_host_dm_pauliGadget(void* h, const unsigned* targets, const unsigned* paulis, unsigned n, double theta) {
+    distributed_densitymatrix_pauliGadget(dm(h), toNats(targets, n), toNats(paulis, n), theta);
+}
+void dfsa_host_dm_phaseGadget(void* h, const unsigned* targets, unsigned n, double theta) {
+    distributed_densitymatrix_phaseGadget(dm(h), toNats(targets, n), theta);
+}
+void dfsa_host_dm_krausMap(void* h, const double* krausOps, unsigned numOps, const unsigned* targets, unsigned numTargets) {
+    const Index d = powerOf2(numTargets);
+    MatrixArray ops;
+    for (unsigned o = 0; o < numOps; o++) ops.push_back(toMatrix(krausOps + 2 * d * d * o, d));
+    distributed_densitymatrix_krausMap(dm(h), ops, toNats(targets, numTargets));
+}
+void dfsa_host_dm_oneQubitDephasing(void* h, unsigned qb, double prob) { distributed_densitymatrix_oneQubitDephasing(dm(h), qb, prob); }
+void dfsa_host_dm_twoQubitDephasing(void* h, unsigned qb1, unsigned qb2, double prob) { distributed_densitymatrix_twoQubitDephasing(dm(h), qb1, qb2, prob); }
+void dfsa_host_dm_oneQubitDepolarising(void* h, unsigned qb, double prob) { distributed_densitymatrix_oneQubitDepolarising(dm(h), qb, prob); }
+void dfsa_host_dm_twoQubitDepolarising(void* h, unsigned qb1, unsigned qb2, double prob, int corrected) {
+    distributed_densitymatrix_twoQubitDepolarising(dm(h), qb1, qb2, prob, corrected != 0);
+}
+void dfsa_host_dm_damping(void* h, unsigned qb, double prob) { distributed_densitymatrix_damping(dm(h), qb, prob); }
+void dfsa_host_dm_expecPauliString(void* h, const double* coeffs, unsigned numTerms, const unsigned* paulis, double* outReIm) {
+    DensityMatrix& rho = dm(h);
+    Amp v = distributed_densitymatrix_expecPauliString(rho, RealArray(coeffs, coeffs + numTerms), toNats(paulis, numTerms * rho.numQubits));
+    outReIm[0] = v.real();
+    outReIm[1] = v.imag();
+}
+void* dfsa_host_dm_partialTrace(void* h, const unsigned* targets, unsigned numTargets) {
+    return new DensityMatrix(distributed_densitymatrix_partialTrace(dm(h), toNats(targets, numTargets)));
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// distributed_densitymatrix.hpp -- the public density-matrix API of the drop-in host layer.
+// Entry points, signatures and semantics follow the reference's src/distributed_densitymatrix.hpp
+// (:15 manyTargGate, :28 swapGate, :36 pauliTensor, :53 pauliGadget, :67 phaseGadget, :79 krausMap,
+// :92 oneQubitDephasing, :98 twoQubitDephasing, :104 oneQubitDepolarising, :241 twoQubitDepolarising,
+// :266 damping, :322 expecPauliString, :347 partialTrace). A density matrix is a Choi vector, so unitaries are
+// two state-vector passes (U on the ket bits, conj(U) on the bra bits q+N); "prefix" qubits are those whose
+// bra bit indexes the rank: q >= N - log2(P).
+#pragma once
+
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+
+#include "distributed_statevector.hpp"
+#include "local_densitymatrix.hpp"
+
+namespace dfsa_detail {
+inline NatArray shifted(const NatArray& qubits, Nat by) {
+    NatArray out = qubits;
+    for (Nat& q : out) q += by;
+    return out;
+}
+}
+
+static inline void distributed_densitymatrix_manyTargGate(DensityMatrix& rho, NatArray targets, AmpMatrix gate) {
+    assert(2 * targets.size() <= rho.logNumAmpsPerNode);
+    distributed_statevector_manyTargGate(rho, targets, gate);
+    distributed_statevector_manyTargGate(rho, dfsa_detail::shifted(targets, rho.numQubits), getConjugateMatrix(gate));
+}
+
+static inline void distributed_densitymatrix_swapGate(DensityMatrix& rho, Nat qb1, Nat qb2) {
+    distributed_statevector_swapGate(rho, qb1, qb2);
+    distributed_statevector_swapGate(rho, qb1 + rho.numQubits, qb2 + rho.numQubits);
+}
+
+static inline void distributed_densitymatrix_pauliTensor(DensityMatrix& rho, NatArray targets, NatArray paulis) {
+    distributed_statevector_pauliTensor(rho, targets, paulis);
+    distributed_statevector_pauliTensor(rho, dfsa_detail::shifted(targets, rho.numQubits), paulis);
+    if (containsOddNumY(paulis)) {          // conj(Y) = -Y on the bra side
+        const double minusOne[2] = {-1.0, 0.0};
+        DFSA_CHECK(dfsa_k_scaleAll(rho.handle, minusOne));
+    }
+}
+
+static inline void distributed_densitymatrix_pauliGadget(DensityMatrix& rho, NatArray targets, NatArray paulis, Real theta) {
+    distributed_statevector_pauliGadget(rho, targets, paulis, theta);
+    // conj(exp(i theta P)) = exp(-i theta conj(P)), conj(P) = -P for an odd number of Y
+    distributed_statevector_pauliGadget(rho, dfsa_detail::shifted(targets, rho.numQubits), paulis, containsOddNumY(paulis) ? theta : -theta);
+}
+
+static inline void distributed_densitymatrix_phaseGadget(DensityMatrix& rho, NatArray targets, Real theta) {
+    distributed_statevector_phaseGadget(rho, targets, theta);
+    distributed_statevector_phaseGadget(rho, dfsa_detail::shifted(targets, rho.numQubits), -theta);
+}
+
+static inline void distributed_densitymatrix_krausMap(DensityMatrix& rho, MatrixArray krausOps, NatArray targets) {
+    assert(2 * targets.size() <= rho.logNumAmpsPerNode);
+    NatArray extended = targets;
+    for (Nat t : targets) extended.push_back(t + rho.numQubits);
+    distributed_statevector_manyTargGate(rho, extended, getSuperoperator(krausOps));
+}
+
+static inline void distributed_densitymatrix_oneQubitDephasing(DensityMatrix& rho, Nat qb, Real prob) {
+    local_densitymatrix_oneQubitDephasing(rho, qb, prob);      // the kernel handles the prefix case via the rank bit
+}
+
+static inline void distributed_densitymatrix_twoQubitDephasing(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob) {
+    local_densitymatrix_twoQubitDephasing(rho, qb1, qb2, prob);
+}
+
+static inline void distributed_densitymatrix_oneQubitDepolarising(DensityMatrix& rho, Nat qb, Real prob) {
+    const Nat threshold = rho.numQubits - rho.logNumNodes;
+    if (qb < threshold) { local_densitymatrix_oneQubitDepolarising(rho, qb, prob); return; }
+    // the bra bit is a rank bit: swap the ket-bit == rank-bit halves with the partner, then mix
+    const Nat rankQb = qb - threshold, bit = getBit(rho.rank, rankQb);
+    const Nat pairRank = Nat(flipBit(rho.rank, rankQb));
+    const Index half = rho.numAmpsPerNode / 2;
+    DFSA_CHECK(dfsa_k_pack(rho.handle, &qb, 1, bit, 0));
+    comm_exchangeArrays(rho.buffer, 0, rho.buffer, half, half, pairRank);
+    DFSA_CHECK(dfsa_k_depol1Combine(rho.handle, qb, bit, prob));
+}
+
+// As in the reference, the three branches apply the reference's own formulas (SURVEY F2 explains why they are not
+// the textbook channel); `corrected` is only available on the all-suffix branch.
+static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob, bool corrected = false) {
+    if (qb1 > qb2) std::swap(qb1, qb2);
+    const Nat N = rho.numQubits, threshold = N - rho.logNumNodes;
+    if (qb2 < threshold) { local_densitymatrix_twoQubitDepolarising(rho, qb1, qb2, prob, corrected); return; }
+    assert(!corrected && "corrected twoQubitDepolarising is only implemented for suffix qubits");
+
+    if (qb1 < threshold) {
+        // pair: one partner (the rank bit of qb2's bra), an eighth of the shard pre-summed and exchanged
+        const Nat rankQb = qb2 - threshold, bit = getBit(rho.rank, rankQb);
+        const Index eighth = rho.numAmpsPerNode / 8;
+        DFSA_CHECK(dfsa_k_depol2Pair(rho.handle, qb1, qb2, qb1 + N, bit, prob, 0));
+        comm_exchangeArrays(rho.buffer, 0, rho.buffer, eighth, eighth, Nat(flipBit(rho.rank, rankQb)));
+        DFSA_CHECK(dfsa_k_depol2Pair(rho.handle, qb1, qb2, qb1 + N, bit, prob, 1));
+        return;
+    }
+    // quad: two sequential partners, a quarter of the shard each time
+    const Nat rankQb0 = qb1 - threshold, rankQb1 = qb2 - threshold;
+    const Nat bit0 = getBit(rho.rank, rankQb0), bit1 = getBit(rho.rank, rankQb1);
+    const Index quarter = rho.numAmpsPerNode / 4;
+    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 0));
+    comm_exchangeArrays(rho.buffer, 0, rho.buffer, quarter, quarter, Nat(flipBit(rho.rank, rankQb0)));
+    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 1));
+    comm_exchangeArrays(rho.buffer, 0, rho.buffer, quarter, quarter, Nat(flipBit(rho.rank, rankQb1)));
+    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 2));
+}
+
+static inline void distributed_densitymatrix_damping(DensityMatrix& rho, Nat qb, Real prob) {
+    const Nat threshold = rho.numQubits - rho.logNumNodes;
+    if (qb < threshold) { local_densitymatrix_damping(rho, qb, prob); return; }
+    // population flows one way, from the rank holding bra bit 1 to the rank holding bra bit 0
+    const Nat rankQb = qb - threshold, bit = getBit(rho.rank, rankQb);
+    const Nat pairRank = Nat(flipBit(rho.rank, rankQb));
+    const Index half = rho.numAmpsPerNode / 2;
+    if (bit == 1) {
+        DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 0));
+        comm_asynchSendArray(rho.buffer, half, pairRank);
+    }
+    DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 1));
+    if (bit == 0) {
+        comm_receiveArray(rho.buffer, half, pairRank);
+        DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 2));
+    }
+    // the reference needs a global barrier here to protect the sender's buffer; stream order does that job
+}
+
+static inline Amp distributed_densitymatrix_expecPauliString(DensityMatrix& rho, RealArray coeffs, NatArray allPaulis) {
+    assert(allPaulis.size() == coeffs.size() * rho.numQubits);
+    double local[2] = {0.0, 0.0};
+    DFSA_CHECK(dfsa_k_expecPauliString(rho.handle, coeffs.data(), Nat(coeffs.size()), allPaulis.data(), local));
+    Amp value(local[0], local[1]);
+    comm_reduceAmp(value);
+    return value;
+}
+
+static inline DensityMatrix distributed_densitymatrix_partialTrace(DensityMatrix& inRho, NatArray targets) {
+    const Nat N = inRho.numQubits, L = Nat(inRho.logNumAmpsPerNode);
+    assert(N - targets.size() >= inRho.logNumNodes);
+    std::sort(targets.begin(), targets.end());
+    const NatArray braTargets = dfsa_detail::shifted(targets, N);
+
+    if (targets.back() + N < L) return local_densitymatrix_partialTrace(inRho, targets, braTargets);
+
+    // some bra bits are rank bits: swap them into free suffix bits (this MUTATES inRho, as the reference does),
+    // trace locally, then restore the order of the surviving qubits on the output
+    NatArray extended = targets;
+    extended.insert(extended.end(), braTargets.begin(), braTargets.end());
+    const NatArray reordered = getReorderedAllSuffixTargets(extended, L);
+    for (std::size_t q = reordered.size(); q-- != 0;)
+        if (reordered[q] != extended[q]) distributed_statevector_swapGate(inRho, reordered[q], extended[q]);
+
+    const NatArray pairTargets(reordered.begin() + targets.size(), reordered.end());
+    DensityMatrix outRho = local_densitymatrix_partialTrace(inRho, targets, pairTargets);
+
+    NatArray remaining = getNonTargetedQubitOrder(2 * N, extended, reordered);
+    for (Nat q = Nat(remaining.size()); q-- != 0;) {
+        if (remaining[q] == q) continue;
+        const Nat p = Nat(std::find(remaining.begin(), remaining.end(), q) - remaining.begin());
+        distributed_statevector_swapGate(outRho, q, p);
+        std::swap(remaining[q], remaining[p]);
+    }
+    return outRho;
+}

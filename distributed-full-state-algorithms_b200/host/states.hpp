@@ -1,0 +1,149 @@
+// states.hpp -- StateVector / DensityMatrix of the drop-in API, with the amplitudes resident in HBM.
+// Same public fields and constructors as the reference's src/states.hpp (:16-25 fields, :32-48 ctor, :53-69
+// DensityMatrix); `amps` and `buffer` are device-array views instead of std::vector. The test-only members the
+// reference declares here and defines in tests/test_utilities.hpp (:419-524) are implemented with device copies.
+#pragma once
+
+#include <cmath>
+#include <cstdio>
+#include <utility>
+
+#include "bit_maths.hpp"
+#include "communication.hpp"
+#include "misc.hpp"
+#include "types.hpp"
+
+class StateVector {
+public:
+    Nat rank = 0;
+    Nat numNodes = 1;
+    Nat logNumNodes = 0;
+
+    Nat numQubits = 0;
+    Index numAmpsPerNode = 0;
+    Index logNumAmpsPerNode = 0;
+
+    DeviceAmpArray amps;
+    DeviceAmpArray buffer;
+
+    dfsa_state* handle = nullptr;
+
+    explicit StateVector(Nat numQubits) { create(false, numQubits); }
+    virtual ~StateVector() { release(); }
+    StateVector(const StateVector&) = delete;
+    StateVector& operator=(const StateVector&) = delete;
+    StateVector(StateVector&& other) noexcept { adopt(other); }
+    StateVector& operator=(StateVector&& other) noexcept { if (this != &other) { release(); adopt(other); } return *this; }
+
+    // ---- host <-> device (the reference's test-utility members + plain setters)
+    AmpArray getAllVecAmps() {                                   // whole state on every rank
+        AmpArray all(Index(numNodes) * numAmpsPerNode);
+        DFSA_CHECK(dfsa_state_download_all(handle, reinterpret_cast<double*>(all.data())));
+        return all;
+    }
+    void setAllVecAmps(const AmpArray& all) {                    // each rank keeps its slice of the global array
+        assert(all.size() == Index(numNodes) * numAmpsPerNode);
+        comm_synch();
+        DFSA_CHECK(dfsa_state_upload_all(handle, reinterpret_cast<const double*>(all.data())));
+    }
+    AmpArray getLocalAmps() {
+        AmpArray local(numAmpsPerNode);
+        DFSA_CHECK(dfsa_state_download(handle, DFSA_AMPS, 0, numAmpsPerNode, reinterpret_cast<double*>(local.data())));
+        return local;
+    }
+    void setLocalAmps(const AmpArray& local) {
+        assert(local.size() == numAmpsPerNode);
+        DFSA_CHECK(dfsa_state_upload(handle, DFSA_AMPS, 0, numAmpsPerNode, reinterpret_cast<const double*>(local.data())));
+    }
+    // Box-Muller on rand(), every rank drawing every rank's amplitudes so the streams stay in lock-step
+    // (same sequence as tests/test_utilities.hpp:114-122, 438-448 for an identical seed)
+    void setRandomAmps() {
+        comm_synch();
+        AmpArray mine(numAmpsPerNode);
+        for (Nat r = 0; r < numNodes; r++)
+            for (Index j = 0; j < numAmpsPerNode; j++) {
+                Real a = std::rand() / Real(RAND_MAX), b = std::rand() / Real(RAND_MAX);
+                Real radius = std::sqrt(-2 * std::log(a)), angle = 2 * 3.14159265 * b;
+                if (r == rank) mine[j] = Amp(radius * std::cos(angle), radius * std::sin(angle));
+            }
+        setLocalAmps(mine);
+    }
+    void setHashAmps(unsigned long long seed) { DFSA_CHECK(dfsa_state_init_hash(handle, seed)); }
+    void printAmps() {
+        AmpArray all = getAllVecAmps();
+        if (rank == 0)
+            for (Index i = 0; i < all.size(); i++) std::printf("%llu: (%.17g, %.17g)\n", i, all[i].real(), all[i].imag());
+        comm_synch();
+    }
+    // two-sided (the reference's comparison is one-sided and NaN-blind)
+    bool agreesWith(const AmpArray& ref, Real tol = 1E-5) {
+        AmpArray all = getAllVecAmps();
+        if (ref.size() != all.size()) return false;
+        for (Index i = 0; i < ref.size(); i++) {
+            Amp dif = ref[i] - all[i];
+            if (!(std::abs(dif.real()) <= tol) || !(std::abs(dif.imag()) <= tol)) {
+                if (rank == 0) std::printf("disagreement of (%g) + i(%g) at %llu\n", dif.real(), dif.imag(), i);
+                return false;
+            }
+        }
+        return true;
+    }
+    Real getNorm2() { double n = 0; DFSA_CHECK(dfsa_state_norm2(handle, &n)); return n; }
+
+protected:
+    StateVector() = default;
+    void create(bool isDensity, Nat qubits) {
+        DFSA_CHECK(dfsa_state_create(isDensity ? 1 : 0, qubits, &handle));
+        rank = comm_getRank();
+        numNodes = comm_getNumNodes();
+        logNumNodes = logBase2(numNodes);
+        numQubits = qubits;
+        logNumAmpsPerNode = dfsa_state_log_num_amps_per_node(handle);
+        numAmpsPerNode = dfsa_state_num_amps_per_node(handle);
+        amps = DeviceAmpArray{handle, DFSA_AMPS};
+        buffer = DeviceAmpArray{handle, DFSA_BUFFER};
+    }
+    void release() {
+        if (handle) DFSA_CHECK(dfsa_state_destroy(handle));
+        handle = nullptr;
+    }
+    void adopt(StateVector& o) {
+        rank = o.rank; numNodes = o.numNodes; logNumNodes = o.logNumNodes; numQubits = o.numQubits;
+        numAmpsPerNode = o.numAmpsPerNode; logNumAmpsPerNode = o.logNumAmpsPerNode;
+        amps = o.amps; buffer = o.buffer; handle = o.handle;
+        o.handle = nullptr; o.amps = DeviceAmpArray(); o.buffer = DeviceAmpArray();
+    }
+};
+
+// Choi vector of an N-qubit density matrix: 2N index bits, flat = 2^N*col + row; ranks own column blocks.
+class DensityMatrix : public StateVector {
+public:
+    explicit DensityMatrix(Nat numQubits) : StateVector() { create(true, numQubits); }
+    DensityMatrix(DensityMatrix&& other) noexcept : StateVector(std::move(other)) {}
+    DensityMatrix& operator=(DensityMatrix&& other) noexcept { StateVector::operator=(std::move(other)); return *this; }
+
+    AmpMatrix getAllMatrAmps() {
+        const Index dim = powerOf2(numQubits);
+        AmpArray vec = getAllVecAmps();
+        AmpMatrix matr = getZeroMatrix(dim);
+        for (Index c = 0; c < dim; c++)
+            for (Index r = 0; r < dim; r++) matr[r][c] = vec[dim * c + r];
+        return matr;
+    }
+    void setAllMatrAmps(const AmpMatrix& matr) {
+        const Index dim = powerOf2(numQubits);
+        AmpArray vec(dim * dim);
+        for (Index c = 0; c < dim; c++)
+            for (Index r = 0; r < dim; r++) vec[dim * c + r] = matr[r][c];
+        setAllVecAmps(vec);
+    }
+    using StateVector::agreesWith;
+    bool agreesWith(const AmpMatrix& ref, Real tol = 1E-5) {
+        const Index dim = powerOf2(numQubits);
+        if (ref.size() != dim) return false;
+        AmpArray vec(dim * dim);
+        for (Index c = 0; c < dim; c++)
+            for (Index r = 0; r < dim; r++) vec[dim * c + r] = ref[r][c];
+        return StateVector::agreesWith(vec, tol);
+    }
+};

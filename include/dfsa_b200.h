@@ -1,0 +1,155 @@
+/*
+ * dfsa_b200.h -- C-ABI of libdfsa_b200.so: the B200 (sm_100a) device layer behind the reference's
+ * distributed full-state API.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * The reference (TysonRayJones/Distributed-Full-State-Algorithms) is header-only C++; its process boundary
+ * is MPI (src/communication.hpp) and its hot loops are OpenMP (src/local_*.hpp and the inline loops of
+ * src/distributed_*.hpp).  This header is what a host program binds INSTEAD of those loops and of MPI:
+ *   - dfsa_comm_*   replaces src/communication.hpp:16-47,172-177 (init/rank/size/barrier/reduce)
+ *   - dfsa_state_*  replaces the std::vector storage of src/states.hpp:13-69 (amps + equal-size buffer, now in HBM)
+ *   - dfsa_x_*      replaces comm_exchangeArrays / comm_asynchSendArray / comm_receiveArray
+ *                   (src/communication.hpp:77-164): pairwise amplitude exchange, partner = rank XOR mask
+ *   - dfsa_k_*      one entry per OpenMP loop of the reference, run as CUDA kernels
+ * The host-side dispatch (local vs. exchange, relocation planning) stays C++ and lives in the drop-in
+ * headers under distributed-full-state-algorithms_b200/host/, which call only the functions declared here.
+ *
+ * Conventions: amplitudes are interleaved (re,im) doubles, 16 B each (Amp = std::complex<double>,
+ * src/types.hpp:26,37); `idx`/`num` arguments are in amplitudes; qubit q = bit q of the global amplitude
+ * index, rank = top log2(P) bits (src/states.hpp:41-44).  Array selectors: DFSA_AMPS / DFSA_BUFFER.
+ * Every function returns 0 on success or a negative dfsa_status; dfsa_last_error() gives the text.
+ * All kernels are enqueued on the library's compute stream and are asynchronous; dfsa_comm_barrier(),
+ * dfsa_device_sync(), downloads and reductions synchronise.  There is NO CPU fallback: without a
+ * CUDA device every call fails with DFSA_ERR_CUDA.
+ */
+#ifndef DFSA_B200_H
+#define DFSA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dfsa_state dfsa_state;
+
+enum dfsa_status {
+    DFSA_OK = 0,
+    DFSA_ERR_CUDA = -1,        /* a CUDA runtime call failed (or no device) */
+    DFSA_ERR_NCCL = -2,
+    DFSA_ERR_ARG = -3,         /* precondition violated (the reference would assert) */
+    DFSA_ERR_COMM = -4,        /* bootstrap / transport failure */
+    DFSA_ERR_UNSUPPORTED = -5
+};
+
+enum { DFSA_AMPS = 0, DFSA_BUFFER = 1 };
+enum { DFSA_MAX_QUBITS = 64 };
+
+const char* dfsa_last_error(void);
+const char* dfsa_version(void);
+
+/* ---- communication environment: src/communication.hpp:16-47 ------------------------------------------- */
+/* Bootstrap from the environment. RANK/WORLD_SIZE(/LOCAL_RANK) set (torchrun-style launch): join that job.
+ * DFSA_NP=P set: fork P-1 children now (must be the first CUDA-touching call of the process, like MPI_Init
+ * being the first statement of the reference's mains). Neither: single rank.  Idempotent. */
+int dfsa_comm_init(void);
+/* Bootstrap with an externally distributed NCCL unique id (128 bytes from dfsa_comm_get_unique_id on rank 0),
+ * e.g. broadcast by torch.distributed. `device` < 0 means rank % deviceCount. */
+int dfsa_comm_get_unique_id(void* out128);
+int dfsa_comm_init_with_id(int rank, int numRanks, const void* uniqueId128, int device);
+int dfsa_comm_finalize(void);                      /* comm_end(): barrier, then tear down */
+int dfsa_comm_rank(void);                          /* comm_getRank() */
+int dfsa_comm_size(void);                          /* comm_getNumNodes() */
+int dfsa_comm_barrier(void);                       /* comm_synch(): device sync + inter-rank barrier */
+int dfsa_device_sync(void);
+const char* dfsa_comm_transport(void);             /* "single", "nccl" or "ipc" */
+void* dfsa_stream_compute(void);                   /* cudaStream_t the kernels run on (for CUDA-event timing) */
+
+/* ---- state storage: src/states.hpp:13-69 --------------------------------------------------------------- */
+/* Collective. Allocates this rank's shard (2^(n-k) or 2^(2N-k) amps) and, when P>1, the equal-size
+ * exchange buffer, both zero-filled, in HBM. Fails with DFSA_ERR_ARG if 2^numQubits < P (states.hpp:35). */
+int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state** out);
+int dfsa_state_destroy(dfsa_state* s);
+double*  dfsa_state_ptr(dfsa_state* s, int which);                /* device pointer of DFSA_AMPS / DFSA_BUFFER */
+uint64_t dfsa_state_num_amps_per_node(const dfsa_state* s);
+unsigned dfsa_state_log_num_amps_per_node(const dfsa_state* s);
+unsigned dfsa_state_num_qubits(const dfsa_state* s);
+int      dfsa_state_is_density(const dfsa_state* s);
+int dfsa_state_swap_arrays(dfsa_state* s);                        /* amps <-> buffer pointer swap */
+/* host <-> device copies of this rank's shard, [first, first+num) in LOCAL amplitude indices */
+int dfsa_state_upload(dfsa_state* s, int which, uint64_t first, uint64_t num, const double* host);
+int dfsa_state_download(dfsa_state* s, int which, uint64_t first, uint64_t num, double* host);
+/* whole state (all ranks, global order) into host memory of every rank: getAllVecAmps (test_utilities.hpp:419) */
+int dfsa_state_download_all(dfsa_state* s, double* hostAll);
+int dfsa_state_upload_all(dfsa_state* s, const double* hostAll);  /* each rank keeps its slice */
+int dfsa_state_init_zero(dfsa_state* s);
+int dfsa_state_init_hash(dfsa_state* s, uint64_t seed);           /* synthetic state, SURVEY 8(d) */
+int dfsa_state_norm2(dfsa_state* s, double* out);                 /* sum |amp|^2 over all ranks */
+
+/* ---- pairwise exchange: src/communication.hpp:77-164 ---------------------------------------------------- */
+/* comm_exchangeArrays(toSend, sendStart, toReceive, recvStart, num, pairRank): both partners call it with the
+ * same recv array/offset; data lands in the partner's `recvWhich` array at `recvStart`. Ordered after all
+ * previously enqueued kernels; later kernels are ordered after the received data. */
+int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart,
+                    uint64_t num, int pairRank);
+/* one-directional pair used by damping (src/distributed_densitymatrix.hpp:292,306): sender / receiver side */
+int dfsa_x_send(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank);
+int dfsa_x_recv(dfsa_state* s, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank);
+int dfsa_x_allreduce_amp(double reim[2]);                         /* comm_reduceAmp, host value in/out */
+
+/* ---- state-vector kernels (src/local_statevector.hpp, inline loops of src/distributed_statevector.hpp) -- */
+/* gate pointers are HOST pointers to row-major interleaved complex doubles */
+/* K1+K2: 2x2 gate on `target` where all `ctrls` are 1 (numCtrls may be 0). local_statevector.hpp:14,32 */
+int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, unsigned target, const double gate[8]);
+/* K3: swap of two suffix qubits. local_statevector.hpp:54 */
+int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2);
+/* K4: dense 2^t x 2^t gate on suffix targets, gate bit i <-> targets[i]. local_statevector.hpp:72 */
+int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate);
+/* K5: amps[j0] = f*amps[j0] + g*b(j1)*amps[j1], j1 = j0^maskXY, b = i^numY * (-1)^parity(global(j1) & maskYZ);
+ * maskXY==0 is the diagonal case. `exact` selects the move/negate-only path (f=0,g=1: pauliTensor).
+ * local_statevector.hpp:102 */
+int dfsa_k_pauli(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, unsigned numY, const double f[2], const double g[2], int exact);
+/* K6: amps[j] *= exp(+-i theta) by parity of (global index & targMask). local_statevector.hpp:138 */
+int dfsa_k_phase(dfsa_state* s, uint64_t targMask, double theta);
+/* K7: amps[i] = f0*amps[i] + f1*buffer[i]. distributed_statevector.hpp:36-38 */
+int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1[2]);
+/* K8/K10/K19-K22 building blocks on sub-cubes: local index k = insert `values` bits at sorted `positions` into j.
+ *   pack:    buffer[dstStart + j] = amps[k]                          (distributed_statevector.hpp:56,169)
+ *   unpack:  amps[k] = buffer[srcStart + j]                          (distributed_statevector.hpp:180)
+ *   combine: amps[k] = f0*amps[k] + f1*buffer[srcStart + j]          (distributed_statevector.hpp:72) */
+int dfsa_k_pack(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t dstStart);
+int dfsa_k_unpack(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart);
+int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
+                      const double f0[2], const double f1[2]);
+/* K9: amps[dstStart..+num) = buffer[srcStart..+num). distributed_statevector.hpp:133,152 */
+int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t srcStart, uint64_t num);
+/* K11: amps[j0] = f*amps[j0] + g*b*buffer[j0^maskXY], sign from pairRank's global index. distributed_statevector.hpp:227 */
+int dfsa_k_pauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, const double f[2], const double g[2], int exact);
+/* K18: amps *= factor (complex). distributed_densitymatrix.hpp:46 */
+int dfsa_k_scaleAll(dfsa_state* s, const double factor[2]);
+
+/* ---- density-matrix kernels (src/local_densitymatrix.hpp, inline loops of src/distributed_densitymatrix.hpp) */
+int dfsa_k_oneQubitDephasing(dfsa_state* s, unsigned qb, double prob);                 /* K12, local_densitymatrix.hpp:12 */
+int dfsa_k_twoQubitDephasing(dfsa_state* s, unsigned qb1, unsigned qb2, double prob);  /* K13, :45 */
+int dfsa_k_oneQubitDepolarising(dfsa_state* s, unsigned qb, double prob);              /* K14, :63 (suffix case) */
+int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned qb2, double prob, int corrected); /* K15, :83 */
+int dfsa_k_damping(dfsa_state* s, unsigned qb, double prob);                           /* K16, :111 (suffix case) */
+/* K17: out.amps[l] = sum_k in.amps[...]; targets/pairTargets are suffix bit positions in matching order. :134 */
+int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32_t* targets, const uint32_t* pairTargets, unsigned numTargets);
+/* K19: after the half exchange: scale the non-exchanged half by c3, amps[k] = c2*amps[k] + c1*buffer[A/2 + j].
+ * distributed_densitymatrix.hpp:130-141 */
+int dfsa_k_depol1Combine(dfsa_state* s, unsigned qb, unsigned bit, double prob);
+/* K20/K21: the three phases of the prefix twoQubitDepolarising branches, formulas as in the reference.
+ * distributed_densitymatrix.hpp:152-183 (pair), :195-237 (quad); phase = 0,1,2 */
+int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, int phase);
+int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, int phase);
+/* K22: damping across ranks. phase 0 (bit=1 ranks): buffer[j] = amps[k], amps[k] *= 1-p; phase 1 (all): other half *= sqrt(1-p);
+ * phase 2 (bit=0 ranks): amps[k] += p*buffer[j]. distributed_densitymatrix.hpp:284-313 */
+int dfsa_k_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int phase);
+/* K23: local part of sum_t coeff_t Tr(P_t rho); paulis is numTerms x N (codes 0..3, qubit q of term t at [t*N+q]).
+ * Result (this rank's partial sum) is written to out[2]; combine with dfsa_x_allreduce_amp. :322 */
+int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFSA_B200_H */

@@ -1,0 +1,263 @@
+"""GPU parity tests (-m gpu): the CUDA path, driven through the host API / C-ABI, against
+(1) the committed golden outputs of the real reference (tests/golden/), (2) the C oracle on seeded random
+inputs at larger sizes, (3) size-independent properties at sizes the oracle cannot reach.
+Bar (BASELINE.json north_star): permutation / sign-only ops bit-exact, everything else max|delta amp| <= 1e-12
+(relative to the largest reference amplitude), expectation values relative error <= 1e-12."""
+import numpy as np
+import pytest
+
+import cases
+import compare
+import golden_io
+import product
+from oracle import capi, dense
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = golden_io.load("sv") + golden_io.load("dm")
+GOLDEN_1 = [c for c in GOLDEN if c["nodes"] == 1]
+
+
+@pytest.fixture(scope="module")
+def dfsa():
+    m = product.pkg()
+    m.comm_init()
+    assert m.comm_size() == 1
+    return m
+
+
+def check_against(case_op, kind, got_state, got_result, want_amps=None, want_val=None, want_mut=None, mutated=None):
+    name = case_op[0]
+    if name == "dm_expecPauliString":
+        compare.assert_value_close(got_result, want_val, what=name)
+    elif name == "dm_partialTrace":
+        compare.assert_exact(got_result.get_amps(), want_amps, what=name)
+        if want_mut is not None:
+            compare.assert_exact(got_state.get_amps(), want_mut, what=name + " (mutated input)")
+    elif name in cases.EXACT_OPS:
+        compare.assert_exact(got_state.get_amps(), want_amps, what=name)
+    else:
+        compare.assert_close(got_state.get_amps(), want_amps, what=name)
+
+
+@pytest.mark.parametrize("case", GOLDEN_1, ids=golden_io.case_id)
+def test_single_rank_matches_reference_golden(dfsa, case):
+    st = dfsa.DeviceState(case["kind"], case["nq"])
+    st.set_amps(case["amps"])
+    res = cases.apply(st, case["op"])
+    check_against(case["op"], case["kind"], st, res, want_amps=case.get("out"), want_val=(case["val"][0] if "val" in case else None), want_mut=case.get("mut"))
+
+
+def _oracle_run(kind, nq, nodes, amps, op):
+    o = capi.OracleState(kind, nq, nodes)
+    o.set_amps(amps)
+    r = cases.apply(o, op)
+    return o, r
+
+
+@pytest.mark.parametrize("name", cases.SV_OPS)
+@pytest.mark.parametrize("nq", [3, 11, 18])
+def test_sv_ops_match_oracle_at_larger_sizes(dfsa, name, nq):
+    rng = np.random.default_rng(hash((name, nq)) % (2 ** 32))
+    for trial in range(4 if nq < 18 else 2):
+        op = cases.make_op(rng, name, nq, 0)
+        if name == "sv_manyTargGate" and len(op[1]) > 8:
+            op = (name, op[1][:8], cases.random_matrix(rng, 256))
+        amps = cases.random_state(rng, nq)
+        st = dfsa.DeviceState("sv", nq)
+        st.set_amps(amps)
+        cases.apply(st, op)
+        o, _ = _oracle_run("sv", nq, 1, amps, op)
+        if name in cases.EXACT_OPS:
+            compare.assert_exact(st.get_amps(), o.get_amps(), what=name)
+        else:
+            compare.assert_close(st.get_amps(), o.get_amps(), what="%s %r" % (name, op[1]))
+
+
+@pytest.mark.parametrize("name", cases.DM_OPS)
+@pytest.mark.parametrize("nq", [2, 6, 9])
+def test_dm_ops_match_oracle_at_larger_sizes(dfsa, name, nq):
+    rng = np.random.default_rng(hash((name, nq)) % (2 ** 32))
+    for trial in range(3 if nq < 9 else 1):
+        op = cases.make_op(rng, name, nq, 0)
+        if name in ("dm_manyTargGate", "dm_krausMap") and len(op[1]) > 3:
+            nt = 3
+            op = (name, op[1][:nt], cases.random_matrix(rng, 1 << nt)) if name == "dm_manyTargGate" else (name, op[1][:nt], [cases.random_matrix(rng, 1 << nt) for _ in range(2)])
+        if name == "dm_partialTrace" and nq == 2:
+            op = (name, op[1][:1])
+        amps = cases.random_state(rng, 2 * nq)
+        st = dfsa.DeviceState("dm", nq)
+        st.set_amps(amps)
+        res = cases.apply(st, op)
+        o, ores = _oracle_run("dm", nq, 1, amps, op)
+        if name == "dm_expecPauliString":
+            compare.assert_value_close(res, ores, what=name)
+        elif name == "dm_partialTrace":
+            compare.assert_exact(res.get_amps(), ores.get_amps(), what=name)
+        elif name in cases.EXACT_OPS:
+            compare.assert_exact(st.get_amps(), o.get_amps(), what=name)
+        else:
+            compare.assert_close(st.get_amps(), o.get_amps(), what="%s %r" % (name, op[1:3]))
+
+
+def test_every_target_position_one_and_ctrl_gate(dfsa):
+    """BASELINE config 2 in miniature: oneTargGate / manyCtrlOneTargGate over all target positions."""
+    nq = 14
+    rng = np.random.default_rng(5)
+    amps = cases.random_state(rng, nq)
+    st = dfsa.DeviceState("sv", nq)
+    st.set_amps(amps)
+    o = capi.OracleState("sv", nq, 1)
+    o.set_amps(amps)
+    for t in range(nq):
+        g = cases.random_matrix(rng, 2) / 1.5
+        ops = [("sv_oneTargGate", t, g),
+               ("sv_manyCtrlOneTargGate", [int(c) for c in rng.permutation([q for q in range(nq) if q != t])[: 1 + t % 3]], t, g)]
+        for op in ops:
+            cases.apply(st, op)
+            cases.apply(o, op)
+    compare.assert_close(st.get_amps(), o.get_amps(), tol=1e-11, what="target sweep")   # 28 chained non-unitary gates
+
+
+def test_all_z_pauli_string_applies_the_operator(dfsa):
+    """Documented divergence: the reference silently skips X/Y-free Pauli strings; this build applies them."""
+    rng = np.random.default_rng(9)
+    amps = cases.random_state(rng, 7)
+    for op in (("sv_pauliTensor", [0, 3, 6], [3, 3, 3]), ("sv_pauliGadget", [1, 5], [3, 3], 0.81)):
+        st = dfsa.DeviceState("sv", 7)
+        st.set_amps(amps)
+        cases.apply(st, op)
+        compare.assert_close(st.get_amps(), dense.apply_op("sv", 7, amps, op), what=op[0] + " all-Z")
+
+
+def test_expec_gather_and_scan_agree(dfsa, monkeypatch):
+    rng = np.random.default_rng(11)
+    nq = 6
+    amps = cases.random_state(rng, 2 * nq)
+    op = cases.make_op(rng, "dm_expecPauliString", nq, 0)
+    vals = []
+    for force in ("DFSA_EXPEC_FORCE_GATHER", "DFSA_EXPEC_FORCE_SCAN"):
+        monkeypatch.setenv(force, "1")
+        st = dfsa.DeviceState("dm", nq)
+        st.set_amps(amps)
+        vals.append(cases.apply(st, op))
+        monkeypatch.delenv(force)
+    o, want = _oracle_run("dm", nq, 1, amps, op)
+    compare.assert_value_close(vals[0], want)
+    compare.assert_value_close(vals[1], want)
+
+
+def test_corrected_two_qubit_depolarising_is_the_channel(dfsa):
+    rng = np.random.default_rng(13)
+    nq = 4
+    amps = cases.random_state(rng, 2 * nq)
+    st = dfsa.DeviceState("dm", nq)
+    st.set_amps(amps)
+    st.dm_twoQubitDepolarising(1, 3, 0.31, corrected=True)
+    compare.assert_close(st.get_amps(), dense.apply_op("dm", nq, amps, ("dm_twoQubitDepolarising", 1, 3, 0.31)))
+
+
+# ---------------------------------------------------------------- properties at sizes beyond the oracle
+
+def test_large_state_properties(dfsa):
+    """28-qubit state vector (4 GiB): hash init reproducible on the host, unitary layer preserves the norm,
+    U then U^dagger restores the state bit-for-bit-close, swap twice is the identity exactly."""
+    nq = 28
+    st = dfsa.DeviceState("sv", nq)
+    st.init_hash(2024)
+    n0 = st.norm2()
+    # spot-check the device hash against the numpy restatement
+    k = np.arange(2 * 4096, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = np.uint64(2024) + (k + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    vals = (z >> np.uint64(11)).astype(np.float64) / 9007199254740992.0 - 0.5
+    head = np.empty(4096, dtype=np.complex128)
+    import ctypes as C
+    product.pkg().api.check(dfsa.device_lib().dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(4096), head.ctypes.data_as(C.POINTER(C.c_double))))
+    compare.assert_exact(head, vals[0::2] + 1j * vals[1::2], what="hash init")
+
+    rng = np.random.default_rng(3)
+    def unitary(d):
+        q, r = np.linalg.qr(cases.random_matrix(rng, d))
+        return q
+    layer = []
+    for t in (0, 1, 5, 13, 27):
+        layer.append(("sv_oneTargGate", t, unitary(2)))
+    layer.append(("sv_manyCtrlOneTargGate", [2, 20], 9, unitary(2)))
+    layer.append(("sv_manyTargGate", [3, 0, 17, 26, 9], unitary(32)))
+    layer.append(("sv_pauliGadget", [1, 8, 22], [1, 2, 3], 0.4))
+    layer.append(("sv_phaseGadget", [0, 27, 14], -1.1))
+    for op in layer:
+        cases.apply(st, op)
+    assert abs(st.norm2() / n0 - 1) < 1e-12
+    for op in reversed(layer):
+        name = op[0]
+        if name in ("sv_oneTargGate",):
+            cases.apply(st, (name, op[1], op[2].conj().T))
+        elif name == "sv_manyCtrlOneTargGate":
+            cases.apply(st, (name, op[1], op[2], op[3].conj().T))
+        elif name == "sv_manyTargGate":
+            cases.apply(st, (name, op[1], op[2].conj().T))
+        elif name == "sv_pauliGadget":
+            cases.apply(st, (name, op[1], op[2], -op[3]))
+        else:
+            cases.apply(st, (name, op[1], -op[2]))
+    product.pkg().api.check(dfsa.device_lib().dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(4096), head.ctypes.data_as(C.POINTER(C.c_double))))
+    compare.assert_close(head, vals[0::2] + 1j * vals[1::2], tol=1e-13, what="U then U^dagger")
+    st.sv_swapGate(3, 25)
+    st.sv_swapGate(25, 3)
+    tail = np.empty(4096, dtype=np.complex128)
+    product.pkg().api.check(dfsa.device_lib().dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(4096), tail.ctypes.data_as(C.POINTER(C.c_double))))
+    compare.assert_exact(tail, head, what="swap twice")
+
+
+# ---------------------------------------------------------------- multi-rank (NCCL with >= P GPUs, else IPC on one GPU)
+
+def _golden_multirank(nodes):
+    return [c for c in GOLDEN if c["nodes"] == nodes]
+
+
+@pytest.mark.parametrize("nodes", [2, 4, 8])
+def test_multi_rank_matches_reference_golden(nodes):
+    todo = _golden_multirank(nodes)
+    jobs = [dict(kind=c["kind"], nq=c["nq"], op=c["op"], amps=c["amps"]) for c in todo]
+    results = product.run_cases_multirank(jobs, nodes)
+    for c, r in zip(todo, results):
+        name = c["op"][0]
+        if name == "dm_expecPauliString":
+            compare.assert_value_close(r["values"][0], c["val"][0], what=golden_io.case_id(c))
+        elif name == "dm_partialTrace":
+            compare.assert_exact(r["amps"], c["out"], what=golden_io.case_id(c))
+            compare.assert_exact(r["mutated"], c["mut"], what=golden_io.case_id(c) + " mutated")
+        elif name in cases.EXACT_OPS:
+            compare.assert_exact(r["amps"], c["out"], what=golden_io.case_id(c))
+        else:
+            compare.assert_close(r["amps"], c["out"], what=golden_io.case_id(c))
+
+
+@pytest.mark.parametrize("nodes", [2, 4])
+def test_multi_rank_circuit_matches_oracle(nodes):
+    """Chained ops on one state (exercises buffer reuse between exchanges) at a larger size."""
+    rng = np.random.default_rng(40 + nodes)
+    k = nodes.bit_length() - 1
+    jobs, wants = [], []
+    for kind, nq, names in (("sv", 12, cases.SV_OPS), ("dm", 6, [n for n in cases.DM_OPS if n not in ("dm_partialTrace", "dm_expecPauliString")])):
+        ops = []
+        for i in range(3 * len(names)):
+            op = cases.make_op(rng, names[i % len(names)], nq, k)
+            if op[0] in ("sv_manyTargGate", "dm_manyTargGate", "dm_krausMap") and len(op[1]) > 3:
+                continue
+            ops.append(tuple((a / np.linalg.norm(a, 2) if isinstance(a, np.ndarray) and a.ndim == 2 and a.dtype == np.complex128 else a) for a in op))
+        amps = cases.random_state(rng, nq if kind == "sv" else 2 * nq)
+        o = capi.OracleState(kind, nq, nodes)
+        o.set_amps(amps)
+        for op in ops:
+            cases.apply(o, op)
+        jobs.append(dict(kind=kind, nq=nq, ops=ops, amps=amps))
+        wants.append(o.get_amps())
+    results = product.run_cases_multirank(jobs, nodes)
+    for r, w in zip(results, wants):
+        compare.assert_close(r["amps"], w, tol=1e-11, what="circuit np=%d (%s)" % (nodes, r["transport"]))
