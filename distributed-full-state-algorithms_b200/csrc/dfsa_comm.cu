@@ -76,6 +76,19 @@ void napBriefly() {
     nanosleep(&ts, nullptr);
 }
 
+// how long a rank waits for its peers before declaring the job dead (DFSA_COMM_TIMEOUT_S, default 120 s)
+double commTimeoutSeconds() {
+    static double t = -1;
+    if (t < 0) { const char* e = getenv("DFSA_COMM_TIMEOUT_S"); t = e ? atof(e) : 120.0; if (t <= 0) t = 120.0; }
+    return t;
+}
+double nowSeconds() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+#define DFSA_TRACE(...) do { if (getenv("DFSA_TRACE")) { fprintf(stderr, "[dfsa %d] ", dfsaCtx().rank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
+
 int shmBarrier() {
     Shm* m = g_comm.shm;
     if (!m || m->size == 1) return DFSA_OK;
@@ -86,9 +99,12 @@ int shmBarrier() {
         m->barrierSense = g_comm.localSense;
     } else {
         uint64_t spins = 0;
+        const double t0 = nowSeconds();
         while (m->barrierSense != g_comm.localSense) {
-            if (++spins > 2000) napBriefly();
-            if (spins > 40000000ULL) { dfsaSetError("host barrier timed out (a rank died?)"); return DFSA_ERR_COMM; }
+            if (++spins > 2000) {
+                napBriefly();
+                if ((spins & 1023) == 0 && nowSeconds() - t0 > commTimeoutSeconds()) { dfsaSetError("host barrier timed out (a rank died?)"); return DFSA_ERR_COMM; }
+            }
         }
     }
     __sync_synchronize();
@@ -103,9 +119,12 @@ int pairBarrier(int pair) {
     __sync_synchronize();
     m->pairSeq[c.rank][pair] = mine;
     uint64_t spins = 0;
+    const double t0 = nowSeconds();
     while (m->pairSeq[pair][c.rank] < mine) {
-        if (++spins > 2000) napBriefly();
-        if (spins > 40000000ULL) { dfsaSetError("pair barrier with rank %d timed out", pair); return DFSA_ERR_COMM; }
+        if (++spins > 2000) {
+            napBriefly();
+            if ((spins & 1023) == 0 && nowSeconds() - t0 > commTimeoutSeconds()) { dfsaSetError("pair barrier with rank %d timed out", pair); return DFSA_ERR_COMM; }
+        }
     }
     __sync_synchronize();
     return DFSA_OK;
@@ -368,13 +387,14 @@ static int peerPointer(int pair, int slot, double2** out) {
 
 // ------------------------------------------------------------------------------------------------ exchange
 
-static int checkXArgs(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
+static int checkXArgs(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank, bool bothWays = true) {
     DfsaContext& c = dfsaCtx();
     DFSA_REQUIRE(s && c.size > 1, "exchange needs more than one rank");
     DFSA_REQUIRE(pairRank >= 0 && pairRank < c.size && pairRank != c.rank, "bad pair rank");
     DFSA_REQUIRE((sendWhich | 1) == 1 && (recvWhich | 1) == 1, "array selector must be DFSA_AMPS or DFSA_BUFFER");
     DFSA_REQUIRE(sendStart + num <= s->numAmps && recvStart + num <= s->numAmps, "exchange range exceeds the shard");
-    DFSA_REQUIRE(sendWhich != recvWhich || sendStart + num <= recvStart || recvStart + num <= sendStart, "send and receive regions overlap");
+    // a rank that both sends and receives must not receive into what it is still sending (the MPI no-overlap rule)
+    DFSA_REQUIRE(!bothWays || sendWhich != recvWhich || sendStart + num <= recvStart || recvStart + num <= sendStart, "send and receive regions overlap");
     return DFSA_OK;
 }
 
@@ -394,6 +414,7 @@ static int transfer(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWh
         return DFSA_OK;
     }
     // IPC: put into the partner's receive region
+    DFSA_TRACE("ipc transfer pair=%d num=%llu send=%d recv=%d", pairRank, (unsigned long long)num, (int)doSend, (int)doRecv);
     DFSA_CUDA(cudaStreamSynchronize(c.compute));               // my data is final, my receive region is free
     DFSA_TRY(pairBarrier(pairRank));                           // ... and so is the partner's
     if (doSend) {
@@ -413,13 +434,13 @@ extern "C" int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart,
 
 extern "C" int dfsa_x_send(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
     DFSA_TRY(dfsaEnsureDevice());
-    DFSA_TRY(checkXArgs(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank));
+    DFSA_TRY(checkXArgs(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank, false));
     return transfer(s, sendWhich, sendStart, recvWhich, recvStart, num, pairRank, true, false);
 }
 
 extern "C" int dfsa_x_recv(dfsa_state* s, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {
     DFSA_TRY(dfsaEnsureDevice());
-    DFSA_TRY(checkXArgs(s, recvWhich ^ 1, 0, recvWhich, recvStart, num, pairRank));
+    DFSA_TRY(checkXArgs(s, recvWhich, recvStart, recvWhich, recvStart, num, pairRank, false));
     return transfer(s, recvWhich, recvStart, recvWhich, recvStart, num, pairRank, false, true);
 }
 

@@ -77,7 +77,8 @@ extern "C" int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state**
     unsigned k = 0;
     while ((1 << k) < c.size) k++;
     DFSA_REQUIRE((1 << k) == c.size, "number of ranks must be a power of 2 (README.md:134)");
-    DFSA_REQUIRE(numQubits >= 1 && numQubits < 63 && (numQubits >= 31 || (1ULL << numQubits) >= (uint64_t)c.size),
+    // 0 qubits (a single amplitude) is legal: partialTrace may trace out every qubit at 1 rank
+    DFSA_REQUIRE(numQubits < 63 && (numQubits >= 31 || (1ULL << numQubits) >= (uint64_t)c.size),
                  "need 2^numQubits >= number of ranks (states.hpp:35)");
     unsigned bits = isDensity ? 2 * numQubits : numQubits;
     DFSA_REQUIRE(bits < 63 && bits >= k, "state too large / too small for this many ranks");

@@ -19,7 +19,9 @@ def main():
     dfsa = product.pkg()
     dfsa.comm_init()
     results = []
-    for case in todo:
+    for ci, case in enumerate(todo):
+        if os.environ.get("DFSA_TRACE"):
+            print("[worker %d] case %d: %s" % (dfsa.comm_rank(), ci, (case["ops"][0][0] if "ops" in case else case["op"][0])), flush=True)
         st = dfsa.DeviceState(case["kind"], case["nq"])
         if case.get("amps") is not None:
             st.set_amps(case["amps"])

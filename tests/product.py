@@ -43,20 +43,35 @@ def run_cases_multirank(cases, nodes, timeout=600, extra_env=None):
             if extra_env:
                 env.update(extra_env)
             procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "mp_worker.py"), job, out],
-                                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
-        logs = []
-        failed = False
-        for p in procs:
-            try:
-                o, _ = p.communicate(timeout=timeout)
-            except subprocess.TimeoutExpired:
+                                          env=env, stdout=open(os.path.join(tmp, "rank%d.log" % r), "w+"), stderr=subprocess.STDOUT, text=True))
+        # poll: the first rank that dies takes the job down (its partners would otherwise sit in a barrier)
+        import time
+        deadline = time.time() + timeout
+        failed = None
+        while True:
+            codes = [p.poll() for p in procs]
+            if any(c is not None and c != 0 for c in codes):
+                failed = "rank %d exited with %d" % (next(i for i, c in enumerate(codes) if c not in (None, 0)), next(c for c in codes if c not in (None, 0)))
+            elif all(c == 0 for c in codes):
+                break
+            elif time.time() > deadline:
+                failed = "timeout after %ds" % timeout
+            if failed:
+                time.sleep(1.0)
                 for q in procs:
-                    q.kill()
-                o, _ = p.communicate()
-                failed = True
-            logs.append(o)
-            failed = failed or p.returncode != 0
+                    if q.poll() is None:
+                        q.kill()
+                break
+            time.sleep(0.05)
+        logs = []
+        for r, p in enumerate(procs):
+            try:
+                p.wait(timeout=30)
+            except subprocess.TimeoutExpired:
+                p.kill()
+            with open(os.path.join(tmp, "rank%d.log" % r)) as f:
+                logs.append("[rank %d] " % r + f.read()[-4000:])
         if failed:
-            raise RuntimeError("multi-rank worker failed:\n" + "\n---\n".join(logs))
+            raise RuntimeError("multi-rank run failed (%s):\n" % failed + "\n---\n".join(logs))
         with open(out, "rb") as f:
             return pickle.load(f)
