@@ -39,6 +39,8 @@ struct DfsaContext {
 };
 
 DfsaContext& dfsaCtx();
+extern uint64_t g_dfsaLaunches;                      // bumped at every kernel launch site
+#define DFSA_COUNT_LAUNCH() (++g_dfsaLaunches)
 void dfsaSetError(const char* fmt, ...);
 int  dfsaEnsureDevice();                         // lazily create streams etc.; DFSA_ERR_CUDA if no device
 int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
@@ -66,7 +68,7 @@ int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
         if (r_ != DFSA_OK) return r_;                                                                \
     } while (0)
 
-#define DFSA_LAUNCH_CHECK() DFSA_CUDA(cudaGetLastError())
+#define DFSA_LAUNCH_CHECK() do { DFSA_COUNT_LAUNCH(); DFSA_CUDA(cudaGetLastError()); } while (0)
 
 // transport hooks implemented in dfsa_comm.cu
 int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc

@@ -10,6 +10,8 @@
 static thread_local char g_err[1024] = "";
 static DfsaContext g_ctx;
 
+uint64_t g_dfsaLaunches = 0;
+
 DfsaContext& dfsaCtx() { return g_ctx; }
 
 void dfsaSetError(const char* fmt, ...) {
@@ -65,6 +67,46 @@ extern "C" int dfsa_device_sync(void) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_CUDA(cudaStreamSynchronize(g_ctx.comm));
     DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    return DFSA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ measurement helpers
+
+extern "C" int dfsa_event_create(void** event) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(event, "null argument");
+    cudaEvent_t e;
+    DFSA_CUDA(cudaEventCreate(&e));
+    *event = (void*)e;
+    return DFSA_OK;
+}
+extern "C" int dfsa_event_record(void* event) {
+    DFSA_REQUIRE(event, "null event");
+    DFSA_CUDA(cudaEventRecord((cudaEvent_t)event, g_ctx.compute));
+    return DFSA_OK;
+}
+extern "C" int dfsa_event_elapsed_ms(void* start, void* stop, double* ms) {
+    DFSA_REQUIRE(start && stop && ms, "null argument");
+    DFSA_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
+    float f = 0.f;
+    DFSA_CUDA(cudaEventElapsedTime(&f, (cudaEvent_t)start, (cudaEvent_t)stop));
+    *ms = f;
+    return DFSA_OK;
+}
+extern "C" int dfsa_event_destroy(void* event) {
+    if (event) DFSA_CUDA(cudaEventDestroy((cudaEvent_t)event));
+    return DFSA_OK;
+}
+extern "C" uint64_t dfsa_launch_count(void) { return g_dfsaLaunches; }
+
+extern "C" int dfsa_host_alloc_pinned(uint64_t bytes, void** out) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(out && bytes > 0, "bad argument");
+    DFSA_CUDA(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return DFSA_OK;
+}
+extern "C" int dfsa_host_free_pinned(void* ptr) {
+    if (ptr) DFSA_CUDA(cudaFreeHost(ptr));
     return DFSA_OK;
 }
 

@@ -64,6 +64,17 @@ int dfsa_device_sync(void);
 const char* dfsa_comm_transport(void);             /* "single", "nccl" or "ipc" */
 void* dfsa_stream_compute(void);                   /* cudaStream_t the kernels run on (for CUDA-event timing) */
 
+/* ---- measurement helpers (no counterpart in the reference, which times with std::chrono around comm_synch, main.cpp:28-35) */
+/* CUDA events recorded on the compute stream, so a timed region brackets exactly the kernels enqueued between them */
+int dfsa_event_create(void** event);
+int dfsa_event_record(void* event);
+int dfsa_event_elapsed_ms(void* start, void* stop, double* ms);   /* synchronises on `stop` */
+int dfsa_event_destroy(void* event);
+uint64_t dfsa_launch_count(void);                  /* kernels launched by this library so far (this process) */
+/* page-locked host memory for full-bandwidth state upload / download */
+int dfsa_host_alloc_pinned(uint64_t bytes, void** out);
+int dfsa_host_free_pinned(void* ptr);
+
 /* ---- state storage: src/states.hpp:13-69 --------------------------------------------------------------- */
 /* Collective. Allocates this rank's shard (2^(n-k) or 2^(2N-k) amps) and, when P>1, the equal-size
  * exchange buffer, both zero-filled, in HBM. Fails with DFSA_ERR_ARG if 2^numQubits < P (states.hpp:35). */
