@@ -132,3 +132,39 @@ static inline unsigned dfsaGrid(uint64_t workItems, unsigned threads, unsigned i
     if (needed < 1) needed = 1;
     return (unsigned)(needed < cap ? needed : cap);
 }
+
+// ------------------------------------------------------------------------------------------------ host-side helpers
+
+#include <algorithm>
+#include <vector>
+
+// sorted, duplicate-free positions below `limit` -> BitSpec (+ their mask)
+static inline int sortedSpec(const uint32_t* qubits, unsigned n, unsigned limit, BitSpec* spec, uint64_t* mask) {
+    DFSA_REQUIRE(n <= DFSA_MAX_QUBITS, "too many qubits");
+    std::vector<uint32_t> v(qubits, qubits + n);
+    std::sort(v.begin(), v.end());
+    uint64_t m = 0;
+    for (unsigned q = 0; q < n; q++) {
+        DFSA_REQUIRE(v[q] < limit, "qubit index is not a local (suffix) bit of this shard");
+        DFSA_REQUIRE(q == 0 || v[q] != v[q - 1], "duplicate qubit");
+        spec->pos[q] = (uint8_t)v[q];
+        m |= 1ULL << v[q];
+    }
+    spec->n = n;
+    if (mask) *mask = m;
+    return DFSA_OK;
+}
+
+// spread the low bits of `value` over the sorted positions of `spec`
+static inline uint64_t depositBits(uint64_t value, const BitSpec& spec) {
+    uint64_t out = 0;
+    for (uint32_t q = 0; q < spec.n; q++) out |= ((value >> q) & 1ULL) << spec.pos[q];
+    return out;
+}
+
+// Pinned staging ring for small per-call host arguments (gate matrices, Pauli term tables): the caller fills the
+// slot, enqueues its H2D copy on the compute stream and commits; a slot is reused only after its copy has run,
+// so the host never has to block on the stream for argument lifetime.
+constexpr size_t DFSA_STAGING_SLOT_BYTES = 128 * 1024;
+int dfsaStagingAcquire(size_t bytes, void** hostPtr, int* slot);   // DFSA_ERR_UNSUPPORTED if bytes > slot size
+int dfsaStagingCommit(int slot);

@@ -1,0 +1,455 @@
+// dfsa_kernels_manytarg.cu -- K4: the dense 2^t x 2^t gate of local_statevector.hpp:72-99.
+// Row/column bit i of the gate belongs to targets[i] in the CALLER's order; amplitudes outside the targets are
+// enumerated by inserting zeros at the sorted target positions. 32*A bytes of HBM traffic and 8*2^t flop per
+// amplitude: HBM-bound for t <= 4, FP64-pipe-bound from t = 5 (256 flop per 32 bytes vs a ridge of ~5.7 flop/B).
+//
+// Four kernels:
+//   t <= 4  manyTargWarpKernel<T>   warp-private tiles, gate in __constant__ memory (DFMA with constant operands); HBM-bound
+//   t == 5  manyTarg5DmmaKernel     warp-private tiles, FP64 tensor cores (mma.sync m16n8k16.f64 -> DMMA), gate held as
+//                                   A-fragments in registers. ncu showed the DFMA version of this case to be issue/I-cache
+//                                   bound at 18 % FP64-pipe utilisation and 8 % of DRAM bandwidth, i.e. compute- not
+//                                   HBM-bound (profiles/r01_ncu_manytarg.txt), which is when the tensor path is warranted.
+//   t == 6  manyTargTileKernel<8>   block tile, gate transposed in shared memory
+//   t >= 7  manyTargGenericKernel   one block per 2^t group, gate streamed from L2, warp-per-row reduction
+#include <algorithm>
+#include <vector>
+
+#include <string.h>
+#include "dfsa_internal.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// t <= 5. A tile = the 2^(t+f) amplitudes spanned by the t target bits and the f (<= 5) lowest non-target bits.
+// Each WARP owns a tile: the 32 lanes stage it into the warp's private shared-memory slab X[row][lane]
+// (row = gate-ordered target bits, lane = the f free bits) with 2^t independent, coalesced 16-byte loads per
+// lane; then lane v multiplies vector v: acc[r] += G[r][l] * X[l][v], fully unrolled so that every G element is
+// an immediate constant-bank operand of the DFMA (no shared/global traffic for the gate at all) and X[l][v] is one
+// conflict-free LDS.128 per 4*2^t DFMAs; results go back through the slab and out with the same coalesced pattern.
+// No block-level barrier anywhere: warps run tiles independently (only __syncwarp).
+__constant__ double2 cGate[256];    // row-major G[r][l], 2^t x 2^t, t <= 4
+
+template <int T>
+__global__ void __launch_bounds__(128, 4)
+manyTargWarpKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f) {
+    constexpr unsigned D = 1u << T;
+    extern __shared__ double2 smem[];
+    // per-block tables: element e = lane | (i << 5) of a tile -> address offset / X slot, split by lane and i parts
+    __shared__ uint64_t iOff[D];
+    __shared__ unsigned iSlot[D];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
+    const unsigned lanes = 1u << f, tileAmps = D << f, bitsInTile = T + f;
+    double2* X = smem + (size_t)warp * (D * 32u);
+
+    auto decompose = [&](unsigned e, uint64_t& off, unsigned& slot) {
+        off = 0; slot = 0;
+        for (unsigned b = 0; b < bitsInTile; b++) {
+            const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            slot |= (role < (unsigned)T) ? (bit << (role + 5)) : (bit << (role - T));   // X[row][lane] = X[row*32 + lane]
+        }
+    };
+    if (threadIdx.x < D) {
+        uint64_t off; unsigned slot;
+        decompose(threadIdx.x << 5, off, slot);
+        iOff[threadIdx.x] = off; iSlot[threadIdx.x] = slot;
+    }
+    uint64_t laneOff; unsigned laneSlot;
+    decompose(lane, laneOff, laneSlot);
+    __syncthreads();
+    const unsigned elemsPerLane = (tileAmps + 31u) >> 5;          // == D when f == 5
+
+    for (uint64_t tile = (uint64_t)blockIdx.x * warpsPerBlock + warp; tile < numTiles; tile += (uint64_t)gridDim.x * warpsPerBlock) {
+        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+        // stage in (all loads independent)
+#pragma unroll
+        for (unsigned i = 0; i < D; i++)
+            if (i < elemsPerLane && (lane | (i << 5)) < tileAmps) X[laneSlot | iSlot[i]] = amps[base | iOff[i]];
+        __syncwarp();
+        double2 acc[D];
+#pragma unroll
+        for (unsigned r = 0; r < D; r++) acc[r] = make_double2(0.0, 0.0);
+        if (lane < lanes) {
+#pragma unroll
+            for (unsigned l = 0; l < D; l++) {
+                const double2 x = X[l * 32u + lane];
+#pragma unroll
+                for (unsigned r = 0; r < D; r++) acc[r] = cfma(cGate[r * D + l], x, acc[r]);
+            }
+        }
+        __syncwarp();
+        if (lane < lanes) {
+#pragma unroll
+            for (unsigned r = 0; r < D; r++) X[r * 32u + lane] = acc[r];
+        }
+        __syncwarp();
+#pragma unroll
+        for (unsigned i = 0; i < D; i++)
+            if (i < elemsPerLane && (lane | (i << 5)) < tileAmps) amps[base | iOff[i]] = X[laneSlot | iSlot[i]];
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// t == 5 on the FP64 tensor cores. The complex 32x32 matvec over the 32 vectors of a tile is the real GEMM
+//   [C_re; C_im] (64 x 32) = [[G_re, -G_im], [G_im, G_re]] (64 x 64) * [X_re; X_im] (64 x 32),
+// issued as m16n8k16 f64 MMAs (SASS: DMMA.8x8x4 x8). One warp owns one tile; G_re and G_im live in registers as
+// A-fragments for the whole kernel (2 x 2 blocks of 16x16 each: 128 registers), the tile is staged through the warp's
+// private shared-memory slab X[l][n] (row stride 34 amplitudes: the 4x8 B-fragment footprint then hits 8 distinct
+// 16-byte bank groups per quarter-warp), and one LDS.128 yields both the X_re and the X_im fragment element.
+// Fragment maps (m16n8k16.row.col.f64; g = lane/4, q = lane%4):
+//   a[v]: row g + 8(v&1),  col q + 4(v>>1)      b[v]: k = q + 4v, n = g      c[v]: row g + 8(v>>1), col 2q + (v&1)
+__device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], const double (&b)[4]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7,%8,%9,%10,%11}, {%12,%13,%14,%15}, {%0,%1,%2,%3};"
+                 : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
+                 : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
+}
+
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmemSrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr unsigned DMMA_WARPS = 6;        // warps per block; each owns two 32 x 34 amplitude slabs (double buffer)
+constexpr unsigned DMMA_S = 34;           // slab row stride in amplitudes
+
+// Software pipeline per warp: while the tensor cores work on tile k (slab k&1), cp.async (LDGSTS, L2 -> shared,
+// no registers) is already filling the other slab with tile k+1, so HBM latency is hidden although only
+// 6 warps (233 registers each) are resident per SM.
+__global__ void __launch_bounds__(32 * DMMA_WARPS, 1)
+manyTarg5DmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f, const double2* __restrict__ gate) {
+    constexpr unsigned T = 5, D = 32, S = DMMA_S;
+    extern __shared__ double2 smem[];
+    __shared__ uint64_t iOff[D];
+    __shared__ unsigned iRowN[D];                                  // (row << 8) | n contribution of the i part
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
+    const unsigned g = lane >> 2, q = lane & 3u;
+    const unsigned tileAmps = D << f, bitsInTile = T + f;
+    double2* slab = smem + (size_t)warp * (2 * D * S);
+
+    auto decompose = [&](unsigned e, uint64_t& off, unsigned& rowN) {
+        off = 0; rowN = 0;
+        for (unsigned b = 0; b < bitsInTile; b++) {
+            const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            rowN |= (role < T) ? (bit << (role + 8)) : (bit << (role - T));
+        }
+    };
+    if (threadIdx.x < D) {
+        uint64_t off; unsigned rowN;
+        decompose(threadIdx.x << 5, off, rowN);
+        iOff[threadIdx.x] = off; iRowN[threadIdx.x] = rowN;
+    }
+    uint64_t laneOff; unsigned laneRowN;
+    decompose(lane, laneOff, laneRowN);
+
+    // the gate as A-fragments: [mb][kb] blocks of 16 x 16
+    double gr[2][2][8], gi[2][2][8];
+#pragma unroll
+    for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+        for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+            for (int v = 0; v < 8; v++) {
+                const double2 e = gate[(16 * mb + g + 8 * (v & 1)) * D + 16 * kb + q + 4 * (v >> 1)];
+                gr[mb][kb][v] = e.x;
+                gi[mb][kb][v] = e.y;
+            }
+    __syncthreads();
+
+    const uint64_t stride = (uint64_t)gridDim.x * warpsPerBlock;
+    auto prefetch = [&](uint64_t tile, double2* X) {
+        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+#pragma unroll
+        for (unsigned i = 0; i < D; i++)
+            if ((lane | (i << 5)) < tileAmps) {
+                const unsigned rn = laneRowN | iRowN[i];
+                cpAsync16(&X[(rn >> 8) * S + (rn & 255u)], &amps[base | iOff[i]]);
+            }
+        cpAsyncCommit();
+    };
+
+    uint64_t tile = (uint64_t)blockIdx.x * warpsPerBlock + warp;
+    if (tile < numTiles) prefetch(tile, slab);
+    for (unsigned it = 0; tile < numTiles; it++, tile += stride) {
+        double2* X = slab + (size_t)(it & 1u) * (D * S);
+        const bool more = tile + stride < numTiles;
+        if (more) { prefetch(tile + stride, slab + (size_t)((it + 1) & 1u) * (D * S)); cpAsyncWait<1>(); }
+        else cpAsyncWait<0>();
+        __syncwarp();
+#pragma unroll 1
+        for (unsigned nb = 0; nb < 4; nb++) {
+            double cre[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, cim[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++) {
+                double xr[4], xi[4], nxi[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const double2 x = X[(16 * kb + q + 4 * v) * S + nb * 8 + g];
+                    xr[v] = x.x; xi[v] = x.y; nxi[v] = -x.y;
+                }
+                // four independent accumulator chains, issued round-robin so that consecutive MMAs never depend on
+                // each other (a warp issues in order; DMMA latency is covered by the other three chains)
+#pragma unroll
+                for (int mb = 0; mb < 2; mb++) {
+                    dmma16816(cre[mb], gr[mb][kb], xr);
+                    dmma16816(cim[mb], gi[mb][kb], xr);
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; mb++) {
+                    dmma16816(cre[mb], gi[mb][kb], nxi);
+                    dmma16816(cim[mb], gr[mb][kb], xi);
+                }
+            }
+            __syncwarp();                                           // every lane has read this n-block's columns
+#pragma unroll
+            for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    X[(16 * mb + g + 8 * (v >> 1)) * S + nb * 8 + 2 * q + (v & 1)] = make_double2(cre[mb][v], cim[mb][v]);
+        }
+        __syncwarp();
+        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+#pragma unroll
+        for (unsigned i = 0; i < D; i++)
+            if ((lane | (i << 5)) < tileAmps) {
+                const unsigned rn = laneRowN | iRowN[i];
+                amps[base | iOff[i]] = X[(rn >> 8) * S + (rn & 255u)];
+            }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// t == 6: 64 KiB of gate does not fit constant memory; block-wide tile with the gate transposed in shared memory,
+// thread = (8 consecutive rows, one lane).
+template <int R>
+__global__ void __launch_bounds__(256) manyTargTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec,
+                                                         unsigned t, unsigned f, const double2* __restrict__ gateT, BitSpec localPos) {
+    extern __shared__ double2 smem[];
+    const unsigned d = 1u << t, lanes = 1u << f, tileAmps = d << f;
+    double2* G = smem;                 // G^T[l][r], d*d
+    double2* X = smem + (size_t)d * d; // X[row][lane]
+    for (unsigned e = threadIdx.x; e < d * d; e += blockDim.x) G[e] = gateT[e];
+
+    uint64_t gOff[8];
+    unsigned xIdx[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        unsigned e = threadIdx.x + k * 256;
+        uint64_t g = 0;
+        unsigned row = 0, lane = 0;
+        for (unsigned b = 0; b < t + f; b++) {
+            unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
+            g |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < t) row |= bit << role; else lane |= bit << (role - t);
+        }
+        gOff[k] = g;
+        xIdx[k] = row * lanes + lane;
+    }
+    const unsigned myLane = threadIdx.x % lanes, r0 = (threadIdx.x / lanes) * R;
+    const bool active = r0 < d;
+
+    for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+        const uint64_t base = insertZeroBits(tile, tileSpec);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (threadIdx.x + k * 256 < tileAmps) X[xIdx[k]] = amps[base | gOff[k]];
+        __syncthreads();
+        double2 acc[R];
+#pragma unroll
+        for (int i = 0; i < R; i++) acc[i] = make_double2(0.0, 0.0);
+        if (active) {
+            for (unsigned l = 0; l < d; l++) {
+                const double2 x = X[l * lanes + myLane];
+                const double2* grow = G + (size_t)l * d + r0;
+#pragma unroll
+                for (int i = 0; i < R; i++) acc[i] = cfma(grow[i], x, acc[i]);
+            }
+        }
+        __syncthreads();
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < R; i++) X[(r0 + i) * lanes + myLane] = acc[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (threadIdx.x + k * 256 < tileAmps) amps[base | gOff[k]] = X[xIdx[k]];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// t >= 7 (krausMap superoperators): one block per 2^t-amplitude group staged in shared memory,
+// gate rows streamed from global memory (L2-resident), a warp per output row, shuffle reduction over columns.
+__global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint64_t numGroups, BitSpec sortedTargs, BitSpec callerTargs,
+                                                            unsigned t, const double2* __restrict__ gate, double2* __restrict__ outStage) {
+    extern __shared__ double2 smem[];
+    const uint64_t d = 1ULL << t;
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, numWarps = blockDim.x >> 5;
+    double2* out = outStage + (size_t)blockIdx.x * d;           // per-block result slab (results must not overwrite inputs early)
+    for (uint64_t grp = blockIdx.x; grp < numGroups; grp += gridDim.x) {
+        const uint64_t base = insertZeroBits(grp, sortedTargs);
+        __syncthreads();
+        for (uint64_t l = threadIdx.x; l < d; l += blockDim.x) {
+            uint64_t g = base;
+            for (unsigned b = 0; b < t; b++) g |= ((l >> b) & 1ULL) << callerTargs.pos[b];
+            smem[l] = amps[g];
+        }
+        __syncthreads();
+        for (uint64_t r = warp; r < d; r += numWarps) {
+            double2 acc = make_double2(0.0, 0.0);
+            const double2* grow = gate + r * d;
+            for (uint64_t l = lane; l < d; l += 32) acc = cfma(grow[l], smem[l], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+            }
+            if (lane == 0) out[r] = acc;
+        }
+        __syncthreads();
+        for (uint64_t l = threadIdx.x; l < d; l += blockDim.x) {
+            uint64_t g = base;
+            for (unsigned b = 0; b < t; b++) g |= ((l >> b) & 1ULL) << callerTargs.pos[b];
+            amps[g] = out[l];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+
+namespace {
+
+// tile bits = targets U the f lowest non-target bits; localPos.pos[b] = role of the b-th (sorted) tile bit:
+// i < t -> gate bit i (targets[i]), else free bit (role - t)
+int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask, unsigned f, BitSpec* tileSpec, BitSpec* localPos) {
+    std::vector<uint32_t> tileBits(targets, targets + t), freeBits;
+    for (unsigned b = 0; b < L && freeBits.size() < f; b++)
+        if (!((targMask >> b) & 1ULL)) freeBits.push_back(b);
+    tileBits.insert(tileBits.end(), freeBits.begin(), freeBits.end());
+    DFSA_TRY(sortedSpec(tileBits.data(), t + f, L, tileSpec, nullptr));
+    localPos->n = t + f;
+    for (unsigned b = 0; b < t + f; b++) {
+        unsigned q = tileSpec->pos[b], role = 0;
+        bool isTarget = false;
+        for (unsigned i = 0; i < t; i++) if (targets[i] == q) { role = i; isTarget = true; }
+        if (!isTarget) for (unsigned i = 0; i < f; i++) if (freeBits[i] == q) role = t + i;
+        localPos->pos[b] = (uint8_t)role;
+    }
+    return DFSA_OK;
+}
+
+template <int T>
+int launchWarpKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f) {
+    DfsaContext& ctx = dfsaCtx();
+    constexpr unsigned warpsPerBlock = 4;
+    const size_t smemBytes = (size_t)warpsPerBlock * (32u << T) * sizeof(double2);       // 64 KiB at t = 5
+    static bool configured = false;
+    static int blocksPerSM = 1;
+    if (!configured) {
+        DFSA_CUDA(cudaFuncSetAttribute(manyTargWarpKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, manyTargWarpKernel<T>, 128, smemBytes) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 1;
+        configured = true;
+    }
+    uint64_t blocksNeeded = (numTiles + warpsPerBlock - 1) / warpsPerBlock;
+    unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs * blocksPerSM);
+    manyTargWarpKernel<T><<<grid, 128, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}
+
+}  // namespace
+
+extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && targets && gate, "null argument");
+    const unsigned t = numTargets, L = s->logNumAmps;
+    DFSA_REQUIRE(t >= 1 && t <= L, "manyTargGate needs 1 <= numTargets <= local bits (distributed_statevector.hpp:191)");
+    BitSpec sortedT; uint64_t targMask;
+    DFSA_TRY(sortedSpec(targets, t, L, &sortedT, &targMask));
+    const uint64_t d = 1ULL << t;
+    const size_t gateBytes = d * d * sizeof(double2);
+    DfsaContext& ctx = dfsaCtx();
+
+    if (t == 5) {
+        void* stage; int slot;
+        DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
+        memcpy(stage, gate, gateBytes);
+        double2* dev;
+        DFSA_TRY(dfsaScratch(gateBytes, &dev));
+        DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
+        DFSA_TRY(dfsaStagingCommit(slot));
+        const unsigned f = std::min(5u, L - t);
+        BitSpec tileSpec, localPos;
+        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
+        const uint64_t numTiles = s->numAmps >> (t + f);
+        constexpr unsigned warpsPerBlock = DMMA_WARPS;
+        const size_t smemBytes = (size_t)warpsPerBlock * 2 * 32 * DMMA_S * sizeof(double2);   // 204 KiB: one block per SM
+        static bool configured = false;
+        if (!configured) {
+            DFSA_CUDA(cudaFuncSetAttribute(manyTarg5DmmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+            configured = true;
+        }
+        const uint64_t blocksNeeded = (numTiles + warpsPerBlock - 1) / warpsPerBlock;
+        const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs);
+        manyTarg5DmmaKernel<<<grid, 32 * DMMA_WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, dev);
+        DFSA_LAUNCH_CHECK();
+        return DFSA_OK;
+    }
+
+    if (t <= 4) {
+        void* stage; int slot;
+        DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
+        memcpy(stage, gate, gateBytes);
+        DFSA_CUDA(cudaMemcpyToSymbolAsync(cGate, stage, gateBytes, 0, cudaMemcpyHostToDevice, ctx.compute));
+        DFSA_TRY(dfsaStagingCommit(slot));
+        const unsigned f = std::min(5u, L - t);
+        BitSpec tileSpec, localPos;
+        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
+        const uint64_t numTiles = s->numAmps >> (t + f);
+        switch (t) {
+            case 1:  return launchWarpKernel<1>(s, numTiles, tileSpec, localPos, f);
+            case 2:  return launchWarpKernel<2>(s, numTiles, tileSpec, localPos, f);
+            case 3:  return launchWarpKernel<3>(s, numTiles, tileSpec, localPos, f);
+            default: return launchWarpKernel<4>(s, numTiles, tileSpec, localPos, f);
+        }
+    }
+
+    if (t == 6) {
+        void* stage; int slot;
+        DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
+        double2* gt = (double2*)stage;                    // transposed: G^T[l][r]
+        for (uint64_t r = 0; r < d; r++) for (uint64_t l = 0; l < d; l++) gt[l * d + r] = hostAmp(gate + 2 * (r * d + l));
+        double2* dev;
+        DFSA_TRY(dfsaScratch(gateBytes, &dev));
+        DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
+        DFSA_TRY(dfsaStagingCommit(slot));
+        const unsigned f = std::min(5u, L - t);
+        BitSpec tileSpec, localPos;
+        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
+        const size_t smemBytes = (d * d + (d << f)) * sizeof(double2);
+        const uint64_t numTiles = s->numAmps >> (t + f);
+        const unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 2);
+        DFSA_CUDA(cudaFuncSetAttribute(manyTargTileKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        manyTargTileKernel<8><<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, t, f, dev, localPos);
+        DFSA_LAUNCH_CHECK();
+        return DFSA_OK;
+    }
+
+    DFSA_REQUIRE(d * sizeof(double2) <= 200 * 1024, "manyTargGate: 2^numTargets amplitudes must fit shared memory (numTargets <= 13)");
+    BitSpec caller; caller.n = t;
+    for (unsigned i = 0; i < t; i++) caller.pos[i] = (uint8_t)targets[i];
+    const uint64_t numGroups = s->numAmps >> t;
+    const unsigned grid = (unsigned)std::min<uint64_t>(numGroups, (uint64_t)ctx.numSMs * 2);
+    double2* dev;
+    DFSA_TRY(dfsaScratch(gateBytes + (size_t)grid * d * sizeof(double2), &dev));
+    DFSA_CUDA(cudaMemcpyAsync(dev, gate, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(ctx.compute));        // caller-owned pageable source of unbounded size
+    const size_t smemBytes = d * sizeof(double2);
+    DFSA_CUDA(cudaFuncSetAttribute(manyTargGenericKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    manyTargGenericKernel<<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numGroups, sortedT, caller, t, dev, dev + d * d);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}

@@ -5,34 +5,7 @@
 
 #include "dfsa_stream_kernels.cuh"
 
-namespace {
-
-int sortedSpec(const uint32_t* qubits, unsigned n, unsigned limit, BitSpec* spec, uint64_t* mask) {
-    DFSA_REQUIRE(n <= DFSA_MAX_QUBITS, "too many qubits");
-    std::vector<uint32_t> v(qubits, qubits + n);
-    std::sort(v.begin(), v.end());
-    uint64_t m = 0;
-    for (unsigned q = 0; q < n; q++) {
-        DFSA_REQUIRE(v[q] < limit, "qubit index is not a local (suffix) bit of this shard");
-        DFSA_REQUIRE(q == 0 || v[q] != v[q - 1], "duplicate qubit");
-        spec->pos[q] = (uint8_t)v[q];
-        m |= 1ULL << v[q];
-    }
-    spec->n = n;
-    if (mask) *mask = m;
-    return DFSA_OK;
-}
-
-// spread the low bits of `value` over the sorted positions of `spec`
-uint64_t depositBits(uint64_t value, const BitSpec& spec) {
-    uint64_t out = 0;
-    for (uint32_t q = 0; q < spec.n; q++) out |= ((value >> q) & 1ULL) << spec.pos[q];
-    return out;
-}
-
-inline uint64_t rankShiftOf(const dfsa_state* s, int rank) { return (uint64_t)rank << s->logNumAmps; }
-
-}  // namespace
+static inline uint64_t rankShiftOf(const dfsa_state* s, int rank) { return (uint64_t)rank << s->logNumAmps; }
 
 // ---------------------------------------------------------------------------------------------------------
 // K1 + K2: local_statevector.hpp:14-29 (oneTarg) and :32-51 (manyCtrlOneTarg).
@@ -286,172 +259,3 @@ extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t 
     return DFSA_OK;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// K4: local_statevector.hpp:72-99. Dense 2^t x 2^t gate, row/col bit i <-> targets[i] (caller order).
-//
-// Tile kernel (t <= 6): a tile is the 2^(t+f) amplitudes spanned by the t target bits and the f (<= 5) lowest
-// non-target bits, staged in shared memory as X[row][lane] (row = gate-ordered target bits, lane = the f free
-// bits), so that: global loads/stores are contiguous runs of 2^(low bits) amplitudes; the inner product reads
-// X[l][lane] conflict-free (consecutive lanes -> consecutive 16-byte words) and the gate as a warp-wide
-// broadcast G^T[l][r..r+R). Each thread accumulates R rows of one vector in registers: R*4 DFMA per
-// (1 + R) 16-byte shared loads. 32*A bytes of HBM traffic and 8*2^t flop per amplitude (FP64 pipe bound for t>=5).
-template <int R>
-__global__ void __launch_bounds__(256) manyTargTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec,
-                                                         unsigned t, unsigned f, const double2* __restrict__ gateT,
-                                                         /* role of tile-local bit b: < t -> gate bit, else free bit (role - t) */ BitSpec localPos) {
-    extern __shared__ double2 smem[];
-    const unsigned d = 1u << t, lanes = 1u << f, tileAmps = d << f;
-    double2* G = smem;                 // G^T[l][r], d*d
-    double2* X = smem + (size_t)d * d; // X[row][lane], tileAmps
-    for (unsigned e = threadIdx.x; e < d * d; e += blockDim.x) G[e] = gateT[e];
-
-    // Element e of a tile (ascending address order -> coalesced) always maps to the same address offset and the
-    // same X slot; a thread owns elements e = tid + k*256, k < 8 (tileAmps <= 2^11).
-    uint64_t gOff[8];
-    unsigned xIdx[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        unsigned e = threadIdx.x + k * 256;
-        uint64_t g = 0;
-        unsigned row = 0, lane = 0;
-        for (unsigned b = 0; b < t + f; b++) {
-            unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
-            g |= (uint64_t)bit << tileSpec.pos[b];
-            if (role < t) row |= bit << role; else lane |= bit << (role - t);
-        }
-        gOff[k] = g;
-        xIdx[k] = row * lanes + lane;
-    }
-    // one work item per thread: R consecutive gate rows of one lane (host guarantees (d/R)*lanes <= 256)
-    const unsigned myLane = threadIdx.x % lanes, r0 = (threadIdx.x / lanes) * R;
-    const bool active = r0 < d;
-
-    for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const uint64_t base = insertZeroBits(tile, tileSpec);
-        __syncthreads();                             // G staged / previous tile fully written out
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (threadIdx.x + k * 256 < tileAmps) X[xIdx[k]] = amps[base | gOff[k]];
-        __syncthreads();
-        double2 acc[R];
-#pragma unroll
-        for (int i = 0; i < R; i++) acc[i] = make_double2(0.0, 0.0);
-        if (active) {
-            for (unsigned l = 0; l < d; l++) {
-                const double2 x = X[l * lanes + myLane];
-                const double2* grow = G + (size_t)l * d + r0;
-#pragma unroll
-                for (int i = 0; i < R; i++) acc[i] = cfma(grow[i], x, acc[i]);
-            }
-        }
-        __syncthreads();                             // every read of X done before it is overwritten
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < R; i++) X[(r0 + i) * lanes + myLane] = acc[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (threadIdx.x + k * 256 < tileAmps) amps[base | gOff[k]] = X[xIdx[k]];
-    }
-}
-
-// Generic kernel (any t with 2^t amplitudes fitting shared memory): one block per group, gate streamed from
-// global memory (L2-resident), one warp per output row with a shuffle reduction over columns.
-__global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint64_t numGroups, BitSpec sortedTargs, BitSpec callerTargs,
-                                                            unsigned t, const double2* __restrict__ gate) {
-    extern __shared__ double2 smem[];
-    const uint64_t d = 1ULL << t;
-    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31, numWarps = blockDim.x >> 5;
-    for (uint64_t grp = blockIdx.x; grp < numGroups; grp += gridDim.x) {
-        uint64_t base = insertZeroBits(grp, sortedTargs);
-        __syncthreads();
-        for (uint64_t l = threadIdx.x; l < d; l += blockDim.x) {
-            uint64_t g = base;
-            for (unsigned b = 0; b < t; b++) g |= ((l >> b) & 1ULL) << callerTargs.pos[b];
-            smem[l] = amps[g];
-        }
-        __syncthreads();
-        for (uint64_t r = warp; r < d; r += numWarps) {
-            double2 acc = make_double2(0.0, 0.0);
-            const double2* grow = gate + r * d;
-            for (uint64_t l = lane; l < d; l += 32) acc = cfma(grow[l], smem[l], acc);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
-                acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
-            }
-            if (lane == 0) {
-                uint64_t g = base;
-                for (unsigned b = 0; b < t; b++) g |= ((r >> b) & 1ULL) << callerTargs.pos[b];
-                amps[g] = acc;
-            }
-        }
-    }
-}
-
-extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
-    DFSA_TRY(dfsaEnsureDevice());
-    DFSA_REQUIRE(s && targets && gate, "null argument");
-    const unsigned t = numTargets, L = s->logNumAmps;
-    DFSA_REQUIRE(t >= 1 && t <= L, "manyTargGate needs 1 <= numTargets <= local bits (distributed_statevector.hpp:191)");
-    BitSpec sortedT; uint64_t targMask;
-    DFSA_TRY(sortedSpec(targets, t, L, &sortedT, &targMask));
-    const uint64_t d = 1ULL << t;
-    DfsaContext& ctx = dfsaCtx();
-
-    if (t <= 6) {
-        // transposed gate G^T[l][r] to device scratch
-        std::vector<double2> gt(d * d);
-        for (uint64_t r = 0; r < d; r++) for (uint64_t l = 0; l < d; l++) gt[l * d + r] = hostAmp(gate + 2 * (r * d + l));
-        double2* dev;
-        DFSA_TRY(dfsaScratch(d * d * sizeof(double2), &dev));
-        DFSA_CUDA(cudaMemcpyAsync(dev, gt.data(), d * d * sizeof(double2), cudaMemcpyHostToDevice, ctx.compute));
-        DFSA_CUDA(cudaStreamSynchronize(ctx.compute));   // gt is a stack-lifetime pageable buffer
-
-        unsigned f = std::min(5u, L - t);
-        // tile bits = targets U the f lowest non-target bits, sorted
-        std::vector<uint32_t> tileBits(targets, targets + t);
-        std::vector<uint32_t> freeBits;
-        for (unsigned b = 0; b < L && freeBits.size() < f; b++) if (!((targMask >> b) & 1ULL)) freeBits.push_back(b);
-        tileBits.insert(tileBits.end(), freeBits.begin(), freeBits.end());
-        BitSpec tileSpec;
-        DFSA_TRY(sortedSpec(tileBits.data(), t + f, L, &tileSpec, nullptr));
-        BitSpec localPos; localPos.n = t + f;
-        for (unsigned b = 0; b < t + f; b++) {
-            unsigned q = tileSpec.pos[b], role = 0;
-            bool found = false;
-            for (unsigned i = 0; i < t; i++) if (targets[i] == q) { role = i; found = true; }
-            if (!found) for (unsigned i = 0; i < f; i++) if (freeBits[i] == q) role = t + i;
-            localPos.pos[b] = (uint8_t)role;
-        }
-        const unsigned R = (unsigned)std::max<uint64_t>(1, d / 8);   // (d/R) * 2^f <= 8 * 32 = 256 work items = one per thread
-        size_t smemBytes = (d * d + (d << f)) * sizeof(double2);
-        uint64_t numTiles = s->numAmps >> (t + f);
-        unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 4);
-#define DFSA_LAUNCH_TILE(RR)                                                                                                        \
-        do {                                                                                                                        \
-            DFSA_CUDA(cudaFuncSetAttribute(manyTargTileKernel<RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));    \
-            manyTargTileKernel<RR><<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, t, f, dev, localPos); \
-        } while (0)
-        switch (R) { case 1: DFSA_LAUNCH_TILE(1); break; case 2: DFSA_LAUNCH_TILE(2); break; case 4: DFSA_LAUNCH_TILE(4); break; default: DFSA_LAUNCH_TILE(8); break; }
-#undef DFSA_LAUNCH_TILE
-        DFSA_LAUNCH_CHECK();
-        return DFSA_OK;
-    }
-
-    DFSA_REQUIRE(d * sizeof(double2) <= 200 * 1024, "manyTargGate: 2^numTargets amplitudes must fit shared memory (numTargets <= 13)");
-    BitSpec caller; caller.n = t;
-    for (unsigned i = 0; i < t; i++) caller.pos[i] = (uint8_t)targets[i];
-    double2* dev;
-    DFSA_TRY(dfsaScratch(d * d * sizeof(double2), &dev));
-    DFSA_CUDA(cudaMemcpyAsync(dev, gate, d * d * sizeof(double2), cudaMemcpyHostToDevice, ctx.compute));
-    DFSA_CUDA(cudaStreamSynchronize(ctx.compute));
-    size_t smemBytes = d * sizeof(double2);
-    DFSA_CUDA(cudaFuncSetAttribute(manyTargGenericKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-    uint64_t numGroups = s->numAmps >> t;
-    unsigned grid = (unsigned)std::min<uint64_t>(numGroups, (uint64_t)ctx.numSMs * 2);
-    manyTargGenericKernel<<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numGroups, sortedT, caller, t, dev);
-    DFSA_LAUNCH_CHECK();
-    return DFSA_OK;
-}

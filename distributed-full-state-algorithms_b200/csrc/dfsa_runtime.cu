@@ -61,6 +61,31 @@ int dfsaScratch(size_t bytes, double2** out) {
     return DFSA_OK;
 }
 
+namespace {
+constexpr int kStagingSlots = 8;
+struct StagingRing { char* host = nullptr; cudaEvent_t done[kStagingSlots]; bool used[kStagingSlots] = {}; int next = 0; } g_staging;
+}
+
+int dfsaStagingAcquire(size_t bytes, void** hostPtr, int* slot) {
+    if (bytes > DFSA_STAGING_SLOT_BYTES) return DFSA_ERR_UNSUPPORTED;
+    if (!g_staging.host) {
+        DFSA_CUDA(cudaHostAlloc((void**)&g_staging.host, DFSA_STAGING_SLOT_BYTES * kStagingSlots, cudaHostAllocDefault));
+        for (int i = 0; i < kStagingSlots; i++) DFSA_CUDA(cudaEventCreateWithFlags(&g_staging.done[i], cudaEventDisableTiming));
+    }
+    int i = g_staging.next;
+    g_staging.next = (i + 1) % kStagingSlots;
+    if (g_staging.used[i]) DFSA_CUDA(cudaEventSynchronize(g_staging.done[i]));
+    *hostPtr = g_staging.host + (size_t)i * DFSA_STAGING_SLOT_BYTES;
+    *slot = i;
+    return DFSA_OK;
+}
+
+int dfsaStagingCommit(int slot) {
+    DFSA_CUDA(cudaEventRecord(g_staging.done[slot], g_ctx.compute));
+    g_staging.used[slot] = true;
+    return DFSA_OK;
+}
+
 extern "C" void* dfsa_stream_compute(void) { return dfsaEnsureDevice() == DFSA_OK ? (void*)g_ctx.compute : nullptr; }
 
 extern "C" int dfsa_device_sync(void) {

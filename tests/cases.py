@@ -37,8 +37,9 @@ def _paulis_not_all_z(rng, n):
     return p
 
 
-def make_op(rng, name, nq, log_nodes):
-    """One random op for an nq-qubit state (sv: nq amplitude bits; dm: nq = N) spread over 2^log_nodes ranks."""
+def make_op(rng, name, nq, log_nodes, max_targets=None):
+    """One random op for an nq-qubit state (sv: nq amplitude bits; dm: nq = N) spread over 2^log_nodes ranks.
+    max_targets caps the size of dense gates (a 2^t x 2^t matrix is generated for t targets)."""
     if name == "sv_oneTargGate":
         return (name, int(rng.integers(0, nq)), random_matrix(rng, 2))
     if name == "sv_manyCtrlOneTargGate":
@@ -49,10 +50,10 @@ def make_op(rng, name, nq, log_nodes):
         a, b = _unique(rng, 0, nq, 2)
         return (name, a, b)
     if name == "sv_manyTargGate":
-        nt = int(rng.integers(1, nq - log_nodes + 1))
+        nt = int(rng.integers(1, min(nq - log_nodes, max_targets or 64) + 1))
         return (name, _unique(rng, 0, nq, nt), random_matrix(rng, 1 << nt))
     if name in ("dm_manyTargGate", "dm_krausMap"):
-        max_t = nq - (log_nodes + 1) // 2
+        max_t = min(nq - (log_nodes + 1) // 2, max_targets or 64)
         nt = int(rng.integers(1, max_t + 1))
         targets = _unique(rng, 0, nq, nt)
         if name == "dm_manyTargGate":
