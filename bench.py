@@ -271,6 +271,16 @@ def run_product(args, world, rank, local_rank):
                 check(lib.dfsa_event_elapsed_ms(per_gate[s][i][0], per_gate[s][i][1], C.byref(ms)))
                 one_ms.append(ms.value)
     one_avg_ms = float(np.mean(one_ms))
+    if args.per_gate and rank == 0:
+        for i, op in enumerate(ops):
+            acc = 0.0
+            for s_ in range(args.steps):
+                check(lib.dfsa_event_elapsed_ms(per_gate[s_][i][0], per_gate[s_][i][1], C.byref(ms)))
+                acc += ms.value
+            hb, nb = op_algorithmic_bytes(op, nq, k)
+            what = "%s t=%d%s" % (op[0][3:], op[1] if op[0] == "sv_oneTargGate" else op[2], "" if op[0] == "sv_oneTargGate" else " ctrls=%s" % (op[1],))
+            bound = max(hb / (measured_peak()[0] * 1e9), nb / 770e9) * 1e3
+            sys.stderr.write("gate %2d %-48s %9.3f ms  (roofline %8.3f ms, %5.1f%%)\n" % (i, what, acc / args.steps, bound, 100 * bound / (acc / args.steps)))
     peak, peak_src = measured_peak()
     achieved = 32.0 * shard_amps / (one_avg_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
@@ -287,7 +297,24 @@ def run_product(args, world, rank, local_rank):
     shard_bytes = 16 * shard_amps
     e2e = None
     host = C.c_void_p()
-    if lib.dfsa_host_alloc_pinned(C.c_uint64(shard_bytes), C.byref(host)) == 0:
+    # every rank pins a shard-sized host buffer: only when the box has the RAM for it (a box driven out of memory is lost)
+    mem_avail = 0
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable"):
+                    mem_avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    ram_ok = shard_bytes * world <= 0.6 * mem_avail
+    if world > 1:
+        t = torch.tensor([1.0 if ram_ok else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ram_ok = bool(t.item() > 0.5)
+    if not ram_ok:
+        e2e = {"value": None, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "skipped": "host RAM too small to pin %d x %d GiB (MemAvailable %d GiB)" % (world, shard_bytes >> 30, mem_avail >> 30)}
+    if ram_ok and lib.dfsa_host_alloc_pinned(C.c_uint64(shard_bytes), C.byref(host)) == 0:
         hp = C.cast(host, C.POINTER(C.c_double))
         check(lib.dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))     # fill the host buffer (untimed)
         e2e_steps = max(1, min(args.steps, 2))
@@ -345,6 +372,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--qubits", type=int, default=0, help="override the state size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-gate", action="store_true", help="print the mean device time of every gate of the step to stderr")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -64,6 +64,14 @@ def build(force=False, verbose=False):
         if force or _newer(LIB_HOST, [host_src, LIB_DEVICE] + host_headers + headers):
             _run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wall", "-I", INCLUDE, "-I", HOST, host_src, "-o", LIB_HOST,
                   "-L", PKG, "-ldfsa_b200", "-Wl,-rpath,$ORIGIN"])
+    # the reference's timing demo against the drop-in headers: proves the C++ surface compiles and links standalone
+    demo_src = os.path.join(ROOT, "examples", "main.cpp")
+    demo_bin = os.path.join(ROOT, "examples", "main")
+    if os.path.exists(demo_src):
+        host_headers = [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".hpp")]
+        if force or _newer(demo_bin, [demo_src, LIB_DEVICE] + host_headers):
+            _run(["g++", "-std=c++17", "-O2", "-Wall", "-I", INCLUDE, "-I", HOST, demo_src, "-o", demo_bin,
+                  "-L", PKG, "-ldfsa_b200", "-Wl,-rpath," + PKG])
     return LIB_DEVICE, LIB_HOST
 
 

@@ -444,6 +444,86 @@ extern "C" int dfsa_x_recv(dfsa_state* s, int recvWhich, uint64_t recvStart, uin
     return transfer(s, recvWhich, recvStart, recvWhich, recvStart, num, pairRank, false, true);
 }
 
+// ------------------------------------------------------------------------------------------------ pipelined exchange + combine
+
+namespace {
+constexpr int kMaxChunks = 16;
+cudaEvent_t g_chunkEvents[kMaxChunks];
+bool g_chunkEventsReady = false;
+
+// how many pieces the shard travels in: >= 64 MiB each, at most kMaxChunks
+int chunkCountFor(uint64_t numAmps) {
+    const char* e = getenv("DFSA_XCHG_CHUNKS");
+    int want = e ? atoi(e) : kMaxChunks;
+    if (want < 1) want = 1;
+    if (want > kMaxChunks) want = kMaxChunks;
+    const char* m = getenv("DFSA_XCHG_MIN_CHUNK_LOG2");          // smallest chunk, log2 amplitudes (default 2^22 = 64 MiB)
+    const unsigned minLog = m ? (unsigned)atoi(m) : 22u;
+    while (want > 1 && (numAmps / want) < (1ULL << minLog)) want >>= 1;
+    int c = 1;
+    while (c * 2 <= want) c *= 2;          // power of two so chunks tile the (power-of-two) shard exactly
+    return c;
+}
+
+template <class Combine>
+int pipelinedExchange(dfsa_state* s, int pairRank, int chunks, Combine combineRange) {
+    DfsaContext& c = dfsaCtx();
+    if (!g_chunkEventsReady) {
+        for (int i = 0; i < kMaxChunks; i++) DFSA_CUDA(cudaEventCreateWithFlags(&g_chunkEvents[i], cudaEventDisableTiming));
+        g_chunkEventsReady = true;
+    }
+    const uint64_t per = s->numAmps / chunks;
+    DFSA_CUDA(cudaEventRecord(c.evCompute, c.compute));
+    DFSA_CUDA(cudaStreamWaitEvent(c.comm, c.evCompute, 0));
+    for (int k = 0; k < chunks; k++) {
+        const uint64_t first = per * k;
+        DFSA_NCCL(ncclGroupStart());
+        DFSA_NCCL(ncclSend(s->arr[DFSA_AMPS] + first, 2 * per, ncclDouble, pairRank, g_comm.nccl, c.comm));
+        DFSA_NCCL(ncclRecv(s->arr[DFSA_BUFFER] + first, 2 * per, ncclDouble, pairRank, g_comm.nccl, c.comm));
+        DFSA_NCCL(ncclGroupEnd());
+        DFSA_CUDA(cudaEventRecord(g_chunkEvents[k], c.comm));
+        // chunk k of amps has left and chunk k of the partner has arrived: combine it while chunk k+1 is in flight
+        DFSA_CUDA(cudaStreamWaitEvent(c.compute, g_chunkEvents[k], 0));
+        DFSA_TRY(combineRange(first, per));
+    }
+    return DFSA_OK;
+}
+}  // namespace
+
+double2 dfsaPowIHost(unsigned k);
+
+extern "C" int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(f0 && f1, "null factor");
+    DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s ? s->numAmps : 0, pairRank));
+    const double2 c0 = make_double2(f0[0], f0[1]), c1 = make_double2(f1[0], f1[1]);
+    const int chunks = (dfsaCtx().transport == Transport::Nccl) ? chunkCountFor(s->numAmps) : 1;
+    if (chunks == 1) {
+        DFSA_TRY(transfer(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank, true, true));
+        return dfsaLaunchCombineRange(s, 0, s->numAmps, c0, c1);
+    }
+    return pipelinedExchange(s, pairRank, chunks, [&](uint64_t first, uint64_t num) { return dfsaLaunchCombineRange(s, first, num, c0, c1); });
+}
+
+extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
+                                            const double f[2], const double g[2], int exact) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(f && g, "null factor");
+    DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s ? s->numAmps : 0, pairRank));
+    const double2 ff = make_double2(f[0], f[1]), gg = make_double2(g[0], g[1]), pw = dfsaPowIHost(numY);
+    const double2 h = make_double2(gg.x * pw.x - gg.y * pw.y, gg.x * pw.y + gg.y * pw.x);
+    int chunks = (dfsaCtx().transport == Transport::Nccl) ? chunkCountFor(s->numAmps) : 1;
+    // the combine of chunk k reads buffer[j ^ maskXY]: that stays inside chunk k only while maskXY < chunk size
+    while (chunks > 1 && maskXY >= s->numAmps / chunks) chunks >>= 1;
+    if (chunks == 1) {
+        DFSA_TRY(transfer(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank, true, true));
+        return dfsaLaunchPauliCombineRange(s, 0, s->numAmps, pairRank, maskXY, maskYZ, numY, ff, h, exact != 0);
+    }
+    return pipelinedExchange(s, pairRank, chunks, [&](uint64_t first, uint64_t num) {
+        return dfsaLaunchPauliCombineRange(s, first, num, pairRank, maskXY, maskYZ, numY, ff, h, exact != 0);
+    });
+}
+
 extern "C" int dfsa_x_allreduce_amp(double reim[2]) {
     DfsaContext& c = dfsaCtx();
     DFSA_REQUIRE(reim, "null argument");

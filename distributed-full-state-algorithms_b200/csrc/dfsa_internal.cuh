@@ -70,6 +70,11 @@ int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
 
 #define DFSA_LAUNCH_CHECK() do { DFSA_COUNT_LAUNCH(); DFSA_CUDA(cudaGetLastError()); } while (0)
 
+// range forms of the combine kernels (dfsa_kernels_sv.cu), used by the pipelined exchange in dfsa_comm.cu
+int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1);
+int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ,
+                                unsigned numY, double2 f, double2 h, bool exact);
+
 // transport hooks implemented in dfsa_comm.cu
 int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc
 int dfsaUnregisterAllocation(int id);

@@ -125,6 +125,7 @@ static int launchPauliPairs(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, uns
     return launchStream<2, Item>(s->numAmps >> 1, ld, st);
 }
 
+double2 dfsaPowIHost(unsigned k);
 static double2 powIHost(unsigned k) {
     switch (k & 3u) { case 0: return make_double2(1, 0); case 1: return make_double2(0, 1); case 2: return make_double2(-1, 0); default: return make_double2(0, -1); }
 }
@@ -148,14 +149,15 @@ extern "C" int dfsa_k_pauli(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, uns
 }
 
 // K11: distributed_statevector.hpp:227-241. amps[j0] = f*amps[j0] + g*b1*buffer[j0 ^ maskXY], sign from the
-// partner's global index. 48*A bytes (read amps, read buffer, write amps).
+// partner's global index. 48*A bytes (read amps, read buffer, write amps). Range form: j0 in [first, first+num).
 template <bool EXACT>
-static int launchPauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, double2 f, double2 h) {
+static int launchPauliCombine(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, double2 f, double2 h) {
     double2* amps = s->arr[DFSA_AMPS];
     const double2* buf = s->arr[DFSA_BUFFER];
     uint64_t rs = rankShiftOf(s, pairRank);
-    auto ld = [=] __device__(uint64_t j0) { return Amp2{amps[j0], buf[j0 ^ maskXY]}; };
-    auto st = [=] __device__(uint64_t j0, const Amp2& v) {
+    auto ld = [=] __device__(uint64_t k) { uint64_t j0 = first + k; return Amp2{amps[j0], buf[j0 ^ maskXY]}; };
+    auto st = [=] __device__(uint64_t k, const Amp2& v) {
+        uint64_t j0 = first + k;
         unsigned p1 = parity64((rs | (j0 ^ maskXY)) & maskYZ);
         if (EXACT) amps[j0] = mulPowI(v.a1, numY + 2u * p1);
         else {
@@ -163,27 +165,36 @@ static int launchPauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint
             amps[j0] = cfma(h1, v.a1, cmul(f, v.a0));
         }
     };
-    return launchStream<2, Amp2>(s->numAmps, ld, st);
+    return launchStream<2, Amp2>(num, ld, st);
+}
+
+int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ,
+                                unsigned numY, double2 f, double2 h, bool exact) {
+    return exact ? launchPauliCombine<true>(s, first, num, pairRank, maskXY, maskYZ, numY, f, h)
+                 : launchPauliCombine<false>(s, first, num, pairRank, maskXY, maskYZ, numY, f, h);
 }
 
 extern "C" int dfsa_k_pauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, const double f[2], const double g[2], int exact) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && f && g && s->arr[DFSA_BUFFER], "null argument / no exchange buffer");
     double2 ff = hostAmp(f), h = cmulHost(hostAmp(g), powIHost(numY));
-    return exact ? launchPauliCombine<true>(s, pairRank, maskXY, maskYZ, numY, ff, h) : launchPauliCombine<false>(s, pairRank, maskXY, maskYZ, numY, ff, h);
+    return dfsaLaunchPauliCombineRange(s, 0, s->numAmps, pairRank, maskXY, maskYZ, numY, ff, h, exact != 0);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K7: distributed_statevector.hpp:36-38. amps[i] = f0*amps[i] + f1*buffer[i]. 48*A bytes.
+// K7: distributed_statevector.hpp:36-38. amps[i] = f0*amps[i] + f1*buffer[i]. 48*A bytes. Range form: i in [first, first+num).
+int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1) {
+    double2* amps = s->arr[DFSA_AMPS] + first;
+    const double2* buf = s->arr[DFSA_BUFFER] + first;
+    auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], buf[i]}; };
+    auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    return launchStream<2, Amp2>(num, ld, st);
+}
+
 extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1[2]) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && f0 && f1 && s->arr[DFSA_BUFFER], "null argument / no exchange buffer");
-    double2* amps = s->arr[DFSA_AMPS];
-    const double2* buf = s->arr[DFSA_BUFFER];
-    double2 c0 = hostAmp(f0), c1 = hostAmp(f1);
-    auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], buf[i]}; };
-    auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<2, Amp2>(s->numAmps, ld, st);
+    return dfsaLaunchCombineRange(s, 0, s->numAmps, hostAmp(f0), hostAmp(f1));
 }
 
 // K18: distributed_densitymatrix.hpp:44-49 (amp *= -1) generalised to a complex factor.
@@ -255,7 +266,15 @@ extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t 
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && s->arr[DFSA_BUFFER], "null state / no exchange buffer");
     DFSA_REQUIRE(dstStart + num <= s->numAmps && srcStart + num <= s->numAmps, "copy out of range");
+    if (num == s->numAmps && dfsaCtx().transport == Transport::Nccl) {
+        // whole shard: the received buffer simply BECOMES the shard (no 32*A-byte copy). Kernels already enqueued hold
+        // the old pointers by value; everything enqueued later sees the new ones. (With the IPC transport peers cache
+        // mapped addresses per allocation, so there the copy is kept.)
+        return dfsa_state_swap_arrays(s);
+    }
     DFSA_CUDA(cudaMemcpyAsync(s->arr[DFSA_AMPS] + dstStart, s->arr[DFSA_BUFFER] + srcStart, num * sizeof(double2), cudaMemcpyDeviceToDevice, dfsaCtx().compute));
     return DFSA_OK;
 }
 
+
+double2 dfsaPowIHost(unsigned k) { return powIHost(k); }

@@ -23,12 +23,13 @@ inline void ampToArray(const Amp& a, double out[2]) { out[0] = a.real(); out[1] 
 static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMatrix& gate) {
     const Nat rankTarget = target - Nat(psi.logNumAmpsPerNode);
     const Nat pairRank = Nat(flipBit(psi.rank, rankTarget));
-    comm_exchangeArrays(psi.amps, psi.buffer, pairRank);
     const Nat bit = getBit(psi.rank, rankTarget);
     double f0[2], f1[2];
     dfsa_detail::ampToArray(gate[bit][bit], f0);
     dfsa_detail::ampToArray(gate[bit][!bit], f1);
-    DFSA_CHECK(dfsa_k_combine(psi.handle, f0, f1));
+    // comm_exchangeArrays(psi.amps, psi.buffer, pairRank) + the combine loop of the reference (:28-38), fused so that
+    // the shard travels in chunks while the previous chunk is being combined
+    DFSA_CHECK(dfsa_xk_exchangeCombine(psi.handle, int(pairRank), f0, f1));
 }
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
@@ -144,12 +145,12 @@ static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi,
         local_statevector_pauliTensorOrGadget_subroutine(psi, numY, maskXY, maskYZ, thisAmpFac, otherAmpFac);
         return;
     }
-    comm_exchangeArrays(psi.amps, psi.buffer, pairRank);
     double f[2], g[2];
     dfsa_detail::ampToArray(thisAmpFac, f);
     dfsa_detail::ampToArray(otherAmpFac, g);
     const int exact = (thisAmpFac == Amp(0, 0) && otherAmpFac == Amp(1, 0));
-    DFSA_CHECK(dfsa_k_pauliCombine(psi.handle, int(pairRank), maskXY, maskYZ, numY, f, g, exact));
+    // full-shard exchange + combine of the reference (:227-241), chunk-pipelined
+    DFSA_CHECK(dfsa_xk_exchangePauliCombine(psi.handle, int(pairRank), maskXY, maskYZ, numY, f, g, exact));
 }
 
 static inline void distributed_statevector_pauliTensor(StateVector& psi, NatArray targets, NatArray paulis) {

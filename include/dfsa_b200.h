@@ -106,6 +106,13 @@ int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWh
 int dfsa_x_send(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank);
 int dfsa_x_recv(dfsa_state* s, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank);
 int dfsa_x_allreduce_amp(double reim[2]);                         /* comm_reduceAmp, host value in/out */
+/* Fused + pipelined forms of "exchange the whole shard, then combine" (distributed_statevector.hpp:26-38 and :227-241):
+ * the shard travels in chunks on the comm stream while the combine kernel of the previous chunk runs on the compute
+ * stream, so a prefix gate costs ~max(NVLink time, HBM time) instead of their sum. Same results as
+ * dfsa_x_exchange + dfsa_k_combine / dfsa_k_pauliCombine. */
+int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]);
+int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
+                                 const double f[2], const double g[2], int exact);
 
 /* ---- state-vector kernels (src/local_statevector.hpp, inline loops of src/distributed_statevector.hpp) -- */
 /* gate pointers are HOST pointers to row-major interleaved complex doubles */

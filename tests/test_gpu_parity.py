@@ -256,3 +256,25 @@ def test_multi_rank_circuit_matches_oracle(nodes):
     results = product.run_cases_multirank(jobs, nodes)
     for r, w in zip(results, wants):
         compare.assert_close(r["amps"], w, tol=1e-11, what="circuit np=%d (%s)" % (nodes, r["transport"]))
+
+
+def test_chunk_pipelined_exchange_matches_oracle():
+    """Forces the chunked exchange+combine pipeline (16 chunks even on small shards) on the NCCL transport; on a
+    single-GPU box the ranks share the device, the IPC transport is used and the same results must come out."""
+    rng = np.random.default_rng(77)
+    nodes, nq = 2, 12
+    ops = []
+    for i in range(12):
+        ops.append(("sv_oneTargGate", nq - 1, cases.random_matrix(rng, 2) / 1.5))
+        ops.append(("sv_pauliGadget", [nq - 1, 3, 7], [1 + i % 2, 3, 1], float(rng.uniform(-3, 3))))
+        ops.append(("sv_pauliTensor", [nq - 1, 1], [2, 1]))
+        ops.append(("sv_swapGate", nq - 1, nq - 2))
+        ops.append(("sv_manyCtrlOneTargGate", [nq - 2], nq - 1, cases.random_matrix(rng, 2) / 1.5))
+    amps = cases.random_state(rng, nq)
+    o = capi.OracleState("sv", nq, nodes)
+    o.set_amps(amps)
+    for op in ops:
+        cases.apply(o, op)
+    res = product.run_cases_multirank([dict(kind="sv", nq=nq, ops=ops, amps=amps)], nodes,
+                                      extra_env={"DFSA_XCHG_MIN_CHUNK_LOG2": "4", "DFSA_XCHG_CHUNKS": "16"})
+    compare.assert_close(res[0]["amps"], o.get_amps(), tol=1e-11, what="chunked exchange (%s)" % res[0]["transport"])
