@@ -44,6 +44,7 @@ struct Shm {
     double            reduce[MAXP][2];
     volatile uint64_t pairSeq[MAXP][MAXP];
     AllocSlot         alloc[MAXP][MAXALLOC];
+    volatile int      curSlot[MAXP][MAXALLOC][2];   // [rank][state key][amps|buffer] -> registry slot currently playing that role
 };
 
 struct CommState {
@@ -344,7 +345,7 @@ int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut) {
     g_comm.slotUsed[slot] = true;
     g_comm.localPtr[slot] = ptr;
     *idOut = slot;
-    if (c.transport != Transport::Ipc) return DFSA_OK;
+    if (!g_comm.shm) return DFSA_OK;                           // id-only bootstrap: no side channel, no peer mapping
     AllocSlot& a = g_comm.shm->alloc[c.rank][slot];
     DFSA_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t*)&a.handle, ptr));
     a.bytes = bytes;
@@ -353,9 +354,18 @@ int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut) {
     return shmBarrier();                                       // every rank's handle is published
 }
 
+int dfsaPublishArrays(dfsa_state* s) {
+    if (!g_comm.shm || s->key < 0) return DFSA_OK;
+    DfsaContext& c = dfsaCtx();
+    g_comm.shm->curSlot[c.rank][s->key][0] = s->allocId[0];
+    g_comm.shm->curSlot[c.rank][s->key][1] = s->allocId[1];
+    __sync_synchronize();
+    return DFSA_OK;
+}
+
 int dfsaUnregisterAllocation(int id) {
     DfsaContext& c = dfsaCtx();
-    if (c.transport == Transport::Ipc) {
+    if (g_comm.shm) {
         DFSA_TRY(shmBarrier());                                // nobody is still using the mappings
         for (auto it = g_comm.peerMap.begin(); it != g_comm.peerMap.end();) {
             if (it->first.second == id) { cudaIpcCloseMemHandle(it->second); it = g_comm.peerMap.erase(it); }
@@ -383,6 +393,13 @@ static int peerPointer(int pair, int slot, double2** out) {
     }
     *out = (double2*)it->second;
     return DFSA_OK;
+}
+
+// device pointer (mapped into this process) of rank `pair`'s current amps / buffer array of state `s`
+static int peerArray(dfsa_state* s, int pair, int which, double2** out) {
+    if (!g_comm.shm || s->key < 0) { dfsaSetError("no shared side channel: peer arrays are not mapped"); return DFSA_ERR_COMM; }
+    __sync_synchronize();
+    return peerPointer(pair, g_comm.shm->curSlot[pair][s->key][which], out);
 }
 
 // ------------------------------------------------------------------------------------------------ exchange
@@ -419,7 +436,7 @@ static int transfer(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWh
     DFSA_TRY(pairBarrier(pairRank));                           // ... and so is the partner's
     if (doSend) {
         double2* remote;
-        DFSA_TRY(peerPointer(pairRank, s->allocId[recvWhich], &remote));
+        DFSA_TRY(peerArray(s, pairRank, recvWhich, &remote));
         DFSA_CUDA(cudaMemcpyAsync(remote + recvStart, s->arr[sendWhich] + sendStart, num * sizeof(double2), cudaMemcpyDeviceToDevice, c.comm));
         DFSA_CUDA(cudaStreamSynchronize(c.comm));
     }
@@ -492,11 +509,37 @@ int pipelinedExchange(dfsa_state* s, int pairRank, int chunks, Combine combineRa
 
 double2 dfsaPowIHost(unsigned k);
 
+// Fused remote-load form: usable when the ranks share a node-local side channel (peer shards mapped through CUDA IPC).
+// Host protocol per op: [my earlier kernels done] pair barrier [launch: read partner amps over NVLink, write my buffer]
+// [kernel done] pair barrier [swap amps<->buffer]. The second barrier keeps a partner from overwriting the shard this
+// rank is still reading. DFSA_FUSED_EXCHANGE=0 falls back to the staged NCCL / copy-engine path.
+static bool fusedAvailable() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("DFSA_FUSED_EXCHANGE"); on = (e && atoi(e) == 0) ? 0 : 1; }
+    return on == 1 && g_comm.shm != nullptr;
+}
+
+template <class Launch>
+static int fusedExchange(dfsa_state* s, int pairRank, Launch launch) {
+    DfsaContext& c = dfsaCtx();
+    DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    DFSA_TRY(pairBarrier(pairRank));
+    double2* remote;
+    DFSA_TRY(peerArray(s, pairRank, DFSA_AMPS, &remote));
+    DFSA_TRY(launch(remote));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    DFSA_TRY(pairBarrier(pairRank));
+    return dfsa_state_swap_arrays(s);
+}
+
 extern "C" int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(f0 && f1, "null factor");
     DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s ? s->numAmps : 0, pairRank));
     const double2 c0 = make_double2(f0[0], f0[1]), c1 = make_double2(f1[0], f1[1]);
+    if (fusedAvailable())
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedCombine(s, remote, c0, c1); });
     const int chunks = (dfsaCtx().transport == Transport::Nccl) ? chunkCountFor(s->numAmps) : 1;
     if (chunks == 1) {
         DFSA_TRY(transfer(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank, true, true));
@@ -512,6 +555,10 @@ extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_
     DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s ? s->numAmps : 0, pairRank));
     const double2 ff = make_double2(f[0], f[1]), gg = make_double2(g[0], g[1]), pw = dfsaPowIHost(numY);
     const double2 h = make_double2(gg.x * pw.x - gg.y * pw.y, gg.x * pw.y + gg.y * pw.x);
+    if (fusedAvailable())
+        return fusedExchange(s, pairRank, [&](const double2* remote) {
+            return dfsaLaunchFusedPauliCombine(s, remote, pairRank, maskXY, maskYZ, numY, ff, h, exact != 0);
+        });
     int chunks = (dfsaCtx().transport == Transport::Nccl) ? chunkCountFor(s->numAmps) : 1;
     // the combine of chunk k reads buffer[j ^ maskXY]: that stays inside chunk k only while maskXY < chunk size
     while (chunks > 1 && maskXY >= s->numAmps / chunks) chunks >>= 1;
@@ -566,7 +613,7 @@ extern "C" int dfsa_state_download_all(dfsa_state* s, double* hostAll) {
     } else {
         for (int r = 0; r < c.size; r++) {
             double2* src = s->arr[DFSA_AMPS];
-            if (r != c.rank) DFSA_TRY(peerPointer(r, s->allocId[DFSA_AMPS], &src));
+            if (r != c.rank) DFSA_TRY(peerArray(s, r, DFSA_AMPS, &src));
             DFSA_CUDA(cudaMemcpyAsync((char*)hostAll + shardBytes * r, src, shardBytes, cudaMemcpyDeviceToHost, c.comm));
         }
         DFSA_CUDA(cudaStreamSynchronize(c.comm));

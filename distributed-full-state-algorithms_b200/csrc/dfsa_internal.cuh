@@ -18,7 +18,8 @@ struct dfsa_state {
     unsigned logNumAmps;       // per rank
     uint64_t numAmps;          // per rank
     double2* arr[2];           // DFSA_AMPS, DFSA_BUFFER (buffer == nullptr when numNodes == 1)
-    int      allocId[2];       // slot in the IPC allocation registry (-1 if none)
+    int      allocId[2];       // slot in the IPC allocation registry (-1 if none); follows the arrays through swaps
+    int      key;              // registry slot the shard was created with: stable name of this state across ranks
 };
 
 // ------------------------------------------------------------------------------------------------ context
@@ -74,6 +75,12 @@ int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
 int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1);
 int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ,
                                 unsigned numY, double2 f, double2 h, bool exact);
+
+// fused remote-load kernels (dfsa_kernels_sv.cu): buffer[j] = f0*amps[j] + f1*remote[j]  /  the Pauli form; the caller swaps arrays
+int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1);
+int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
+                                unsigned numY, double2 f, double2 h, bool exact);
+int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registry slots are this state's amps / buffer now
 
 // transport hooks implemented in dfsa_comm.cu
 int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc

@@ -197,6 +197,42 @@ extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1
     return dfsaLaunchCombineRange(s, 0, s->numAmps, hostAmp(f0), hostAmp(f1));
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// X1+K7 / X6+K11 as ONE kernel over peer memory: the partner's shard is mapped into this process
+// (CUDA IPC; NVLink peer access between GPUs), so the combine loads the partner's amplitudes directly over NVLink while
+// streaming its own shard from HBM, and writes the result out-of-place into `buffer`; the caller then swaps amps<->buffer.
+// Per rank: 16*A bytes over NVLink, 32*A bytes of HBM traffic (the staged path moves 80*A through HBM), no staging pass.
+int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1) {
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], remote[i]}; };
+    auto st = [=] __device__(uint64_t i, const Amp2& v) { out[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    return launchStream<4, Amp2>(s->numAmps, ld, st);
+}
+
+template <bool EXACT>
+static int launchFusedPauli(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY, double2 f, double2 h) {
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    uint64_t rs = rankShiftOf(s, pairRank);
+    auto ld = [=] __device__(uint64_t j0) { return Amp2{amps[j0], remote[j0 ^ maskXY]}; };
+    auto st = [=] __device__(uint64_t j0, const Amp2& v) {
+        unsigned p1 = parity64((rs | (j0 ^ maskXY)) & maskYZ);
+        if (EXACT) out[j0] = mulPowI(v.a1, numY + 2u * p1);
+        else {
+            double2 h1 = p1 ? make_double2(-h.x, -h.y) : h;
+            out[j0] = cfma(h1, v.a1, cmul(f, v.a0));
+        }
+    };
+    return launchStream<4, Amp2>(s->numAmps, ld, st);
+}
+
+int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
+                                unsigned numY, double2 f, double2 h, bool exact) {
+    return exact ? launchFusedPauli<true>(s, remote, pairRank, maskXY, maskYZ, numY, f, h)
+                 : launchFusedPauli<false>(s, remote, pairRank, maskXY, maskYZ, numY, f, h);
+}
+
 // K18: distributed_densitymatrix.hpp:44-49 (amp *= -1) generalised to a complex factor.
 extern "C" int dfsa_k_scaleAll(dfsa_state* s, const double factor[2]) {
     DFSA_TRY(dfsaEnsureDevice());
@@ -266,10 +302,10 @@ extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t 
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && s->arr[DFSA_BUFFER], "null state / no exchange buffer");
     DFSA_REQUIRE(dstStart + num <= s->numAmps && srcStart + num <= s->numAmps, "copy out of range");
-    if (num == s->numAmps && dfsaCtx().transport == Transport::Nccl) {
+    if (num == s->numAmps) {
         // whole shard: the received buffer simply BECOMES the shard (no 32*A-byte copy). Kernels already enqueued hold
-        // the old pointers by value; everything enqueued later sees the new ones. (With the IPC transport peers cache
-        // mapped addresses per allocation, so there the copy is kept.)
+        // the old pointers by value; everything enqueued later sees the new ones; peers look the current registry
+        // slots of this state up in the shared page (dfsaPublishArrays).
         return dfsa_state_swap_arrays(s);
     }
     DFSA_CUDA(cudaMemcpyAsync(s->arr[DFSA_AMPS] + dstStart, s->arr[DFSA_BUFFER] + srcStart, num * sizeof(double2), cudaMemcpyDeviceToDevice, dfsaCtx().compute));

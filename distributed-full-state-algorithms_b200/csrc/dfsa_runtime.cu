@@ -159,6 +159,7 @@ extern "C" int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state**
     s->numAmps = 1ULL << s->logNumAmps;
     s->arr[0] = s->arr[1] = nullptr;
     s->allocId[0] = s->allocId[1] = -1;
+    s->key = -1;
     size_t bytes = s->numAmps * sizeof(double2);
     int numArrays = (c.size > 1) ? 2 : 1;          // the exchange buffer is only ever touched when P > 1
     for (int w = 0; w < numArrays; w++) {
@@ -171,8 +172,11 @@ extern "C" int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state**
         }
         DFSA_CUDA(cudaMemsetAsync(s->arr[w], 0, bytes, c.compute));
     }
-    if (c.size > 1)
+    if (c.size > 1) {
         for (int w = 0; w < 2; w++) DFSA_TRY(dfsaRegisterAllocation(s->arr[w], bytes, &s->allocId[w]));
+        s->key = s->allocId[0];
+        DFSA_TRY(dfsaPublishArrays(s));
+    }
     *out = s;
     return DFSA_OK;
 }
@@ -197,7 +201,7 @@ extern "C" int dfsa_state_swap_arrays(dfsa_state* s) {
     DFSA_REQUIRE(s && s->arr[1], "no exchange buffer to swap with");
     std::swap(s->arr[0], s->arr[1]);
     std::swap(s->allocId[0], s->allocId[1]);
-    return DFSA_OK;
+    return dfsaPublishArrays(s);
 }
 
 extern "C" int dfsa_state_upload(dfsa_state* s, int which, uint64_t first, uint64_t num, const double* host) {
