@@ -4,8 +4,8 @@
 // amplitude: HBM-bound for t <= 4, FP64-pipe-bound from t = 5 (256 flop per 32 bytes vs a ridge of ~5.7 flop/B).
 //
 // Four kernels:
-//   t <= 4  manyTargWarpKernel<T>   warp-private tiles, gate in __constant__ memory (DFMA with constant operands); HBM-bound
-//   t == 5  manyTarg5DmmaKernel     warp-private tiles, FP64 tensor cores (mma.sync m16n8k16.f64 -> DMMA), gate held as
+//   t <= 2  manyTargWarpKernel<T>   warp-private tiles, gate in __constant__ memory (DFMA with constant operands); HBM-bound
+//   t = 3..5 manyTargDmmaKernel<T>  warp-private tiles, FP64 tensor cores (mma.sync m16n8k16.f64 -> DMMA), gate held as
 //                                   A-fragments in registers. ncu showed the DFMA version of this case to be issue/I-cache
 //                                   bound at 18 % FP64-pipe utilisation and 8 % of DRAM bandwidth, i.e. compute- not
 //                                   HBM-bound (profiles/r01_ncu_manytarg.txt), which is when the tensor path is warranted.
@@ -25,7 +25,7 @@
 // an immediate constant-bank operand of the DFMA (no shared/global traffic for the gate at all) and X[l][v] is one
 // conflict-free LDS.128 per 4*2^t DFMAs; results go back through the slab and out with the same coalesced pattern.
 // No block-level barrier anywhere: warps run tiles independently (only __syncwarp).
-__constant__ double2 cGate[256];    // row-major G[r][l], 2^t x 2^t, t <= 4
+__constant__ double2 cGate[16];     // row-major G[r][l], 2^t x 2^t, t <= 2
 
 template <int T>
 __global__ void __launch_bounds__(128, 4)
@@ -110,15 +110,20 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr unsigned DMMA_WARPS = 6;        // warps per block; each owns two 32 x 34 amplitude slabs (double buffer)
+constexpr unsigned DMMA_WARPS = 6;        // warps per block; each owns two D x 34 amplitude slabs (double buffer)
 constexpr unsigned DMMA_S = 34;           // slab row stride in amplitudes
 
 // Software pipeline per warp: while the tensor cores work on tile k (slab k&1), cp.async (LDGSTS, L2 -> shared,
-// no registers) is already filling the other slab with tile k+1, so HBM latency is hidden although only
-// 6 warps (233 registers each) are resident per SM.
-__global__ void __launch_bounds__(32 * DMMA_WARPS, 1)
-manyTarg5DmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f, const double2* __restrict__ gate) {
-    constexpr unsigned T = 5, D = 32, S = DMMA_S;
+// no registers) is already filling the other slab with tile k+1, so HBM latency is hidden with few resident warps.
+//   T = 5: complex blocks, [mb][kb] = 2 x 2 blocks of 16x16 for G_re and G_im (128 registers), 16 MMAs per 8 vectors
+//   T = 4: one 16x16 block each for G_re, G_im, 4 MMAs per 8 vectors
+//   T = 3: the 8x8 complex gate as ONE real 16x16 A-fragment [[G_re,-G_im],[G_im,G_re]], B = [X_re; X_im] stacked
+//          along k, 1 MMA per 8 vectors
+template <int T>
+__global__ void __launch_bounds__(32 * DMMA_WARPS, (T == 5) ? 1 : (T == 4 ? 2 : 4))
+manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f, const double2* __restrict__ gate) {
+    constexpr unsigned D = 1u << T, S = DMMA_S;
+    constexpr int NB = (T >= 4) ? (int)(D / 16) : 1;              // 16-row blocks of the complex gate (T >= 4)
     extern __shared__ double2 smem[];
     __shared__ uint64_t iOff[D];
     __shared__ unsigned iRowN[D];                                  // (row << 8) | n contribution of the i part
@@ -132,7 +137,7 @@ manyTarg5DmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec 
         for (unsigned b = 0; b < bitsInTile; b++) {
             const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
             off |= (uint64_t)bit << tileSpec.pos[b];
-            rowN |= (role < T) ? (bit << (role + 8)) : (bit << (role - T));
+            rowN |= (role < (unsigned)T) ? (bit << (role + 8)) : (bit << (role - T));
         }
     };
     if (threadIdx.x < D) {
@@ -143,18 +148,29 @@ manyTarg5DmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec 
     uint64_t laneOff; unsigned laneRowN;
     decompose(lane, laneOff, laneRowN);
 
-    // the gate as A-fragments: [mb][kb] blocks of 16 x 16
-    double gr[2][2][8], gi[2][2][8];
+    // the gate as A-fragments (a[v]: row g + 8(v&1), col q + 4(v>>1))
+    double gr[NB][NB][8], gi[NB][NB][8];
+    if constexpr (T >= 4) {
 #pragma unroll
-    for (int mb = 0; mb < 2; mb++)
+        for (int mb = 0; mb < NB; mb++)
 #pragma unroll
-        for (int kb = 0; kb < 2; kb++)
+            for (int kb = 0; kb < NB; kb++)
 #pragma unroll
-            for (int v = 0; v < 8; v++) {
-                const double2 e = gate[(16 * mb + g + 8 * (v & 1)) * D + 16 * kb + q + 4 * (v >> 1)];
-                gr[mb][kb][v] = e.x;
-                gi[mb][kb][v] = e.y;
-            }
+                for (int v = 0; v < 8; v++) {
+                    const double2 e = gate[(16 * mb + g + 8 * (v & 1)) * D + 16 * kb + q + 4 * (v >> 1)];
+                    gr[mb][kb][v] = e.x;
+                    gi[mb][kb][v] = e.y;
+                }
+    } else {
+        // T == 3: real 16x16 matrix R = [[G_re, -G_im], [G_im, G_re]] in gr[0][0]; gi unused
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const unsigned row = g + 8 * (v & 1), col = q + 4 * (v >> 1);
+            const double2 e = gate[(row & 7u) * D + (col & 7u)];
+            gr[0][0][v] = ((row < 8) == (col < 8)) ? e.x : ((row < 8) ? -e.y : e.y);
+            gi[0][0][v] = 0.0;
+        }
+    }
     __syncthreads();
 
     const uint64_t stride = (uint64_t)gridDim.x * warpsPerBlock;
@@ -179,34 +195,49 @@ manyTarg5DmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec 
         __syncwarp();
 #pragma unroll 1
         for (unsigned nb = 0; nb < 4; nb++) {
-            double cre[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}}, cim[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+            if constexpr (T >= 4) {
+                double cre[NB][4], cim[NB][4];
 #pragma unroll
-            for (int kb = 0; kb < 2; kb++) {
-                double xr[4], xi[4], nxi[4];
+                for (int mb = 0; mb < NB; mb++)
 #pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    const double2 x = X[(16 * kb + q + 4 * v) * S + nb * 8 + g];
-                    xr[v] = x.x; xi[v] = x.y; nxi[v] = -x.y;
+                    for (int v = 0; v < 4; v++) { cre[mb][v] = 0.0; cim[mb][v] = 0.0; }
+#pragma unroll
+                for (int kb = 0; kb < NB; kb++) {
+                    double xr[4], xi[4], nxi[4];
+#pragma unroll
+                    for (int v = 0; v < 4; v++) {
+                        const double2 x = X[(16 * kb + q + 4 * v) * S + nb * 8 + g];
+                        xr[v] = x.x; xi[v] = x.y; nxi[v] = -x.y;
+                    }
+                    // independent accumulator chains issued round-robin: consecutive MMAs never depend on each other
+#pragma unroll
+                    for (int mb = 0; mb < NB; mb++) {
+                        dmma16816(cre[mb], gr[mb][kb], xr);
+                        dmma16816(cim[mb], gi[mb][kb], xr);
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < NB; mb++) {
+                        dmma16816(cre[mb], gi[mb][kb], nxi);
+                        dmma16816(cim[mb], gr[mb][kb], xi);
+                    }
                 }
-                // four independent accumulator chains, issued round-robin so that consecutive MMAs never depend on
-                // each other (a warp issues in order; DMMA latency is covered by the other three chains)
+                __syncwarp();                                       // every lane has read this n-block's columns
 #pragma unroll
-                for (int mb = 0; mb < 2; mb++) {
-                    dmma16816(cre[mb], gr[mb][kb], xr);
-                    dmma16816(cim[mb], gi[mb][kb], xr);
-                }
+                for (int mb = 0; mb < NB; mb++)
 #pragma unroll
-                for (int mb = 0; mb < 2; mb++) {
-                    dmma16816(cre[mb], gi[mb][kb], nxi);
-                    dmma16816(cim[mb], gr[mb][kb], xi);
-                }
+                    for (int v = 0; v < 4; v++)
+                        X[(16 * mb + g + 8 * (v >> 1)) * S + nb * 8 + 2 * q + (v & 1)] = make_double2(cre[mb][v], cim[mb][v]);
+            } else {
+                // b[v]: k = q + 4v, n = g ; k < 8 -> X_re row k, k >= 8 -> X_im row k-8
+                const double2 x0 = X[q * S + nb * 8 + g], x1 = X[(q + 4) * S + nb * 8 + g];
+                const double bfrag[4] = {x0.x, x1.x, x0.y, x1.y};
+                double c[4] = {0.0, 0.0, 0.0, 0.0};
+                dmma16816(c, gr[0][0], bfrag);
+                __syncwarp();
+                // c[v]: row g + 8(v>>1) (rows 8..15 = imaginary parts of complex row g), col 2q + (v&1)
+                X[g * S + nb * 8 + 2 * q] = make_double2(c[0], c[2]);
+                X[g * S + nb * 8 + 2 * q + 1] = make_double2(c[1], c[3]);
             }
-            __syncwarp();                                           // every lane has read this n-block's columns
-#pragma unroll
-            for (int mb = 0; mb < 2; mb++)
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    X[(16 * mb + g + 8 * (v >> 1)) * S + nb * 8 + 2 * q + (v & 1)] = make_double2(cre[mb][v], cim[mb][v]);
         }
         __syncwarp();
         const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
@@ -360,6 +391,23 @@ int launchWarpKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, 
     return DFSA_OK;
 }
 
+template <int T>
+int launchDmmaKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
+    DfsaContext& ctx = dfsaCtx();
+    const size_t smemBytes = (size_t)DMMA_WARPS * 2 * (32u >> (5 - T)) * DMMA_S * sizeof(double2);   // 204 / 102 / 51 KiB
+    static int blocksPerSM = 0;
+    if (blocksPerSM == 0) {
+        DFSA_CUDA(cudaFuncSetAttribute(manyTargDmmaKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, manyTargDmmaKernel<T>, 32 * DMMA_WARPS, smemBytes) != cudaSuccess || blocksPerSM < 1)
+            blocksPerSM = 1;
+    }
+    const uint64_t blocksNeeded = (numTiles + DMMA_WARPS - 1) / DMMA_WARPS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs * blocksPerSM);
+    manyTargDmmaKernel<T><<<grid, 32 * DMMA_WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, devGate);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}
+
 }  // namespace
 
 extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
@@ -373,7 +421,7 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
     const size_t gateBytes = d * d * sizeof(double2);
     DfsaContext& ctx = dfsaCtx();
 
-    if (t == 5) {
+    if (t >= 3 && t <= 5) {
         void* stage; int slot;
         DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
         memcpy(stage, gate, gateBytes);
@@ -385,21 +433,14 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         BitSpec tileSpec, localPos;
         DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
         const uint64_t numTiles = s->numAmps >> (t + f);
-        constexpr unsigned warpsPerBlock = DMMA_WARPS;
-        const size_t smemBytes = (size_t)warpsPerBlock * 2 * 32 * DMMA_S * sizeof(double2);   // 204 KiB: one block per SM
-        static bool configured = false;
-        if (!configured) {
-            DFSA_CUDA(cudaFuncSetAttribute(manyTarg5DmmaKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-            configured = true;
+        switch (t) {
+            case 3:  return launchDmmaKernel<3>(s, numTiles, tileSpec, localPos, f, dev);
+            case 4:  return launchDmmaKernel<4>(s, numTiles, tileSpec, localPos, f, dev);
+            default: return launchDmmaKernel<5>(s, numTiles, tileSpec, localPos, f, dev);
         }
-        const uint64_t blocksNeeded = (numTiles + warpsPerBlock - 1) / warpsPerBlock;
-        const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs);
-        manyTarg5DmmaKernel<<<grid, 32 * DMMA_WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, dev);
-        DFSA_LAUNCH_CHECK();
-        return DFSA_OK;
     }
 
-    if (t <= 4) {
+    if (t <= 2) {
         void* stage; int slot;
         DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
         memcpy(stage, gate, gateBytes);
@@ -412,8 +453,7 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         switch (t) {
             case 1:  return launchWarpKernel<1>(s, numTiles, tileSpec, localPos, f);
             case 2:  return launchWarpKernel<2>(s, numTiles, tileSpec, localPos, f);
-            case 3:  return launchWarpKernel<3>(s, numTiles, tileSpec, localPos, f);
-            default: return launchWarpKernel<4>(s, numTiles, tileSpec, localPos, f);
+            default: return launchWarpKernel<2>(s, numTiles, tileSpec, localPos, f);
         }
     }
 

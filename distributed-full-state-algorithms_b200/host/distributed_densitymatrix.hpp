@@ -24,6 +24,15 @@ inline NatArray shifted(const NatArray& qubits, Nat by) {
 
 static inline void distributed_densitymatrix_manyTargGate(DensityMatrix& rho, NatArray targets, AmpMatrix gate) {
     assert(2 * targets.size() <= rho.logNumAmpsPerNode);
+    if (targets.size() <= 2) {
+        // U rho U^dagger in ONE pass over the shard: conj(U) (x) U applied to the 2t bits {targets, targets+N}
+        // (the same 2t-target operator krausMap builds, reference :79-89) is HBM-bound for t <= 2 (<= 128 flop/amp),
+        // so it costs 32*A bytes instead of the 64*A of the reference's two passes (:18-24).
+        NatArray extended = targets;
+        for (Nat t : targets) extended.push_back(t + rho.numQubits);
+        distributed_statevector_manyTargGate(rho, extended, getSuperoperator(MatrixArray{gate}));
+        return;
+    }
     distributed_statevector_manyTargGate(rho, targets, gate);
     distributed_statevector_manyTargGate(rho, dfsa_detail::shifted(targets, rho.numQubits), getConjugateMatrix(gate));
 }
