@@ -28,7 +28,7 @@ extern "C" int dfsa_k_oneQubitDephasing(dfsa_state* s, unsigned qb, double prob)
         const uint64_t fixed = (uint64_t)(!rankBit(s, qb)) << qb;
         auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | fixed]}; };
         auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = cscale(fac, v.a); };
-        return launchStream<4, Amp1>(s->numAmps >> 1, ld, st);
+        return launchStream<2, Amp1>(s->numAmps >> 1, ld, st);
     }
     const unsigned alt = qb + s->numQubits;
     const uint64_t bKet = 1ULL << qb, bBra = 1ULL << alt;
@@ -41,7 +41,7 @@ extern "C" int dfsa_k_oneQubitDephasing(dfsa_state* s, unsigned qb, double prob)
         amps[j00 | bKet] = cscale(fac, v.a0);
         amps[j00 | bBra] = cscale(fac, v.a1);
     };
-    return launchStream<2, Amp2>(s->numAmps >> 2, ld, st);
+    return launchStream<1, Amp2>(s->numAmps >> 2, ld, st);
 }
 
 // K13: local_densitymatrix.hpp:45-60. amps[j] *= 1 - 4p/3 where either qubit's ket/bra bits differ (global index).
@@ -58,7 +58,7 @@ extern "C" int dfsa_k_twoQubitDephasing(dfsa_state* s, unsigned qb1, unsigned qb
         unsigned differ = (unsigned)(((i >> qb1) ^ (i >> (qb1 + N))) | ((i >> qb2) ^ (i >> (qb2 + N)))) & 1u;
         if (differ) amps[j] = cscale(fac, v.a);            // untouched amplitudes are not written back
     };
-    return launchStream<4, Amp1>(s->numAmps, ld, st);
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
 }
 
 // K14: local_densitymatrix.hpp:63-81 (suffix qubit). c1 = 2p/3, c2 = 1-2p/3, c3 = 1-4p/3
@@ -126,7 +126,7 @@ extern "C" int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned
             unsigned differ = (unsigned)(((j >> q0) ^ (j >> q2)) | ((j >> q1) ^ (j >> q3))) & 1u;
             if (differ) amps[j] = cscale(offFac, v.a);
         };
-        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+        DFSA_TRY((launchStream<2, Amp1>(s->numAmps, ld, st)));
     }
     const uint64_t b02 = (1ULL << q0) | (1ULL << q2), b13 = (1ULL << q1) | (1ULL << q3);
     auto ld = [=] __device__(uint64_t k) {
@@ -163,7 +163,7 @@ extern "C" int dfsa_k_depol1Combine(dfsa_state* s, unsigned qb, unsigned bit, do
         amps[j | other] = cscale(c3, v.b);
         amps[j | same]  = make_double2(fma(c1, v.c.x, c2 * v.a.x), fma(c1, v.c.y, c2 * v.a.y));
     };
-    return launchStream<2, Item>(half, ld, st);
+    return launchStream<1, Item>(half, ld, st);
 }
 
 // K20: distributed_densitymatrix.hpp:152-183 (qb1 suffix, qb2 prefix). q0 = qb1, q1 = qb2, q2 = qb1+N, bit = rank bit of qb2's bra.
@@ -183,13 +183,13 @@ extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsign
             unsigned f1 = !(((j >> q0) ^ (j >> q2)) & 1ULL), f2 = (((j >> q1) & 1ULL) == (bit & 1u));
             if (!(f1 & f2)) amps[j] = cscale(offFac, v.a);
         };
-        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+        DFSA_TRY((launchStream<2, Amp1>(s->numAmps, ld, st)));
         auto ld2 = [=] __device__(uint64_t k) {
             uint64_t j0b0 = insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | b1;
             return Amp2{amps[j0b0], amps[j0b0 | b02]};
         };
         auto st2 = [=] __device__(uint64_t k, const Amp2& v) { buf[k] = cadd(v.a0, v.a1); };
-        return launchStream<2, Amp2>(eighth, ld2, st2);
+        return launchStream<1, Amp2>(eighth, ld2, st2);
     }
     DFSA_REQUIRE(phase == 1, "phase must be 0 or 1");
     using Item = Amp3;     // a = a0b0, b = a1b1, c = received
@@ -205,7 +205,7 @@ extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsign
         amps[j0b0] = n0;
         amps[j0b0 | b02] = n1;
     };
-    return launchStream<2, Item>(eighth, ld, st);
+    return launchStream<1, Item>(eighth, ld, st);
 }
 
 // K21: distributed_densitymatrix.hpp:195-237 (both qubits prefix).
@@ -225,10 +225,10 @@ extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsign
             unsigned f1 = (((j >> q0) & 1ULL) == (bit0 & 1u)), f2 = (((j >> q1) & 1ULL) == (bit1 & 1u));
             if (!(f1 & f2)) amps[j] = cscale(offFac, v.a);
         };
-        DFSA_TRY((launchStream<4, Amp1>(s->numAmps, ld, st)));
+        DFSA_TRY((launchStream<2, Amp1>(s->numAmps, ld, st)));
         auto ld2 = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed]}; };
         auto st2 = [=] __device__(uint64_t k, const Amp1& v) { buf[k] = v.a; };
-        return launchStream<4, Amp1>(quarter, ld2, st2);
+        return launchStream<2, Amp1>(quarter, ld2, st2);
     }
     if (phase == 1) {
         auto ld = [=] __device__(uint64_t k) { return Amp2{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed], buf[k + quarter]}; };
@@ -237,13 +237,13 @@ extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsign
             amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = n;
             buf[k] = n;
         };
-        return launchStream<2, Amp2>(quarter, ld, st);
+        return launchStream<1, Amp2>(quarter, ld, st);
     }
     DFSA_REQUIRE(phase == 2, "phase must be 0, 1 or 2");
     const double c4 = c2 / c1;
     auto ld = [=] __device__(uint64_t k) { return Amp1{buf[k + quarter]}; };
     auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = cscale(c4, v.a); };
-    return launchStream<4, Amp1>(quarter, ld, st);
+    return launchStream<2, Amp1>(quarter, ld, st);
 }
 
 // K22: distributed_densitymatrix.hpp:284-313.
@@ -258,18 +258,18 @@ extern "C" int dfsa_k_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, do
         const uint64_t one = 1ULL << qb;
         auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | one]}; };
         auto st = [=] __device__(uint64_t k, const Amp1& v) { buf[k] = v.a; amps[insertZeroBit(k, qb) | one] = cscale(c2, v.a); };
-        return launchStream<4, Amp1>(half, ld, st);
+        return launchStream<2, Amp1>(half, ld, st);
     }
     if (phase == 1) {           // every rank: the half with ket bit != rank bit decays by sqrt(1-p)
         const uint64_t fixed = (uint64_t)(!(bit & 1u)) << qb;
         auto ld = [=] __device__(uint64_t k) { return Amp1{amps[insertZeroBit(k, qb) | fixed]}; };
         auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = cscale(c1, v.a); };
-        return launchStream<4, Amp1>(half, ld, st);
+        return launchStream<2, Amp1>(half, ld, st);
     }
     DFSA_REQUIRE(phase == 2, "phase must be 0, 1 or 2");   // bit = 0 ranks: a00 += p * a11 (received)
     auto ld = [=] __device__(uint64_t k) { return Amp2{amps[insertZeroBit(k, qb)], buf[k]}; };
     auto st = [=] __device__(uint64_t k, const Amp2& v) { amps[insertZeroBit(k, qb)] = make_double2(fma(prob, v.a1.x, v.a0.x), fma(prob, v.a1.y, v.a0.y)); };
-    return launchStream<2, Amp2>(half, ld, st);
+    return launchStream<1, Amp2>(half, ld, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

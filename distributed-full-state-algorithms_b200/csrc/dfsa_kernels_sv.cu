@@ -26,7 +26,7 @@ static int launchCtrlOneTarg(double2* amps, uint64_t items, const BitSpec& spec,
         amps[it.idx ^ targBit] = cfma(g.m01, it.a1, cmul(g.m00, it.a0));
         amps[it.idx]           = cfma(g.m11, it.a1, cmul(g.m10, it.a0));
     };
-    return launchStream<2, Item>(items, ld, st);
+    return launchStream<1, Item>(items, ld, st);
 }
 
 extern "C" int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, unsigned target, const double gate[8]) {
@@ -60,7 +60,7 @@ extern "C" int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2) {
     unsigned lo = std::min(qb1, qb2), hi = std::max(qb1, qb2);
     uint64_t bLo = 1ULL << lo, bHi = 1ULL << hi;
     double2* amps = s->arr[DFSA_AMPS];
-    using Item = PairAt;   // a0 = amp at ..01.., a1 = amp at ..10.., idx = j10
+    using Item = MovePair;   // a0 = amp at ..01.., a1 = amp at ..10.., idx = j10
     auto ld = [=] __device__(uint64_t k) {
         Item it;
         it.idx = insertZeroBit(insertZeroBit(k, lo), hi) | bHi;       // hi qubit = 1, lo qubit = 0
@@ -83,7 +83,7 @@ static int launchDiagParity(dfsa_state* s, uint64_t mask, double2 c0, double2 c1
     uint64_t rs = rankShiftOf(s, s->rank);
     auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[j] = cmul(v.a, parity64((rs | j) & mask) ? c1 : c0); };
-    return launchStream<4, Amp1>(s->numAmps, ld, st);
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
 }
 
 extern "C" int dfsa_k_phase(dfsa_state* s, uint64_t targMask, double theta) {
@@ -122,7 +122,7 @@ static int launchPauliPairs(dfsa_state* s, uint64_t maskXY, uint64_t maskYZ, uns
             amps[j1]    = cfma(h0, it.a0, cmul(f, it.a1));
         }
     };
-    return launchStream<2, Item>(s->numAmps >> 1, ld, st);
+    return launchStream<1, Item>(s->numAmps >> 1, ld, st);
 }
 
 double2 dfsaPowIHost(unsigned k);
@@ -165,7 +165,7 @@ static int launchPauliCombine(dfsa_state* s, uint64_t first, uint64_t num, int p
             amps[j0] = cfma(h1, v.a1, cmul(f, v.a0));
         }
     };
-    return launchStream<2, Amp2>(num, ld, st);
+    return launchStream<1, Amp2>(num, ld, st);
 }
 
 int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ,
@@ -188,7 +188,7 @@ int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 
     const double2* buf = s->arr[DFSA_BUFFER] + first;
     auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], buf[i]}; };
     auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<2, Amp2>(num, ld, st);
+    return launchStream<1, Amp2>(num, ld, st);
 }
 
 extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1[2]) {
@@ -207,7 +207,7 @@ int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, dou
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], remote[i]}; };
     auto st = [=] __device__(uint64_t i, const Amp2& v) { out[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<4, Amp2>(s->numAmps, ld, st);
+    return launchStream<1, Amp2>(s->numAmps, ld, st);
 }
 
 template <bool EXACT>
@@ -224,7 +224,7 @@ static int launchFusedPauli(dfsa_state* s, const double2* remote, int pairRank, 
             out[j0] = cfma(h1, v.a1, cmul(f, v.a0));
         }
     };
-    return launchStream<4, Amp2>(s->numAmps, ld, st);
+    return launchStream<1, Amp2>(s->numAmps, ld, st);
 }
 
 int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
@@ -242,7 +242,7 @@ extern "C" int dfsa_k_scaleAll(dfsa_state* s, const double factor[2]) {
     bool negate = (c.x == -1.0 && c.y == 0.0);
     auto ld = [=] __device__(uint64_t i) { return Amp1{amps[i]}; };
     auto st = [=] __device__(uint64_t i, const Amp1& v) { amps[i] = negate ? make_double2(-v.a.x, -v.a.y) : cmul(v.a, c); };
-    return launchStream<4, Amp1>(s->numAmps, ld, st);
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -266,7 +266,7 @@ extern "C" int dfsa_k_pack(dfsa_state* s, const uint32_t* positions, unsigned nu
     double2* buf = s->arr[DFSA_BUFFER] + dstStart;
     auto ld = [=] __device__(uint64_t j) { return Amp1{amps[insertZeroBits(j, spec) | fixed]}; };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { buf[j] = v.a; };
-    return launchStream<4, Amp1>(items, ld, st);
+    return launchStream<2, Amp1>(items, ld, st);
 }
 
 extern "C" int dfsa_k_unpack(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart) {
@@ -279,7 +279,7 @@ extern "C" int dfsa_k_unpack(dfsa_state* s, const uint32_t* positions, unsigned 
     const double2* buf = s->arr[DFSA_BUFFER] + srcStart;
     auto ld = [=] __device__(uint64_t j) { return Amp1{buf[j]}; };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[insertZeroBits(j, spec) | fixed] = v.a; };
-    return launchStream<4, Amp1>(items, ld, st);
+    return launchStream<2, Amp1>(items, ld, st);
 }
 
 extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
@@ -294,7 +294,7 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
     double2 c0 = hostAmp(f0), c1 = hostAmp(f1);
     auto ld = [=] __device__(uint64_t j) { return Amp2{amps[insertZeroBits(j, spec) | fixed], buf[j]}; };
     auto st = [=] __device__(uint64_t j, const Amp2& v) { amps[insertZeroBits(j, spec) | fixed] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<2, Amp2>(items, ld, st);
+    return launchStream<1, Amp2>(items, ld, st);
 }
 
 // K9: distributed_statevector.hpp:133-135, 152-156

@@ -252,7 +252,7 @@ extern "C" int dfsa_state_init_hash(dfsa_state* s, uint64_t seed) {
     uint64_t first = (uint64_t)s->rank << s->logNumAmps;
     auto ld = [=] __device__(uint64_t j) { return Amp1{make_double2(hashReal(seed, 2 * (first + j)), hashReal(seed, 2 * (first + j) + 1))}; };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[j] = v.a; };
-    return launchStream<4, Amp1>(s->numAmps, ld, st);
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
 }
 
 // sum |amp|^2 : block partials -> host sum (deterministic order)

@@ -8,6 +8,7 @@
 // the SM count.  Loads and stores are passed as two device lambdas so that the in-place read-modify-write
 // cannot serialise the loads of item u+1 behind the stores of item u.
 #pragma once
+#include <stdlib.h>
 #include "dfsa_internal.cuh"
 
 constexpr int DFSA_TPB = 256;
@@ -30,15 +31,25 @@ __global__ void __launch_bounds__(DFSA_TPB) streamKernel(uint64_t numItems, LD l
     }
 }
 
-// blocksPerSM: 2048 resident threads / 256 = 8 when registers allow; the kernels here stay under 32 regs*... the
-// launch helper asks the runtime so the grid is always SMs x resident blocks.
+// How much to keep in flight: measured on B200 (tools/onetarg_sweep.py, tools/microbench_cu/rmw_variants.cu,
+// profiles/r01_rmw_variants.jsonl) the in-place read-modify-write stream is fastest with about 2048 outstanding 16-byte
+// loads per SM spread over MANY threads (1024 threads x 1 pair: 6.18-6.34 TB/s for every target position) and gets
+// slower both with fewer (latency-bound) and with more (full occupancy: 5.8-6.0 TB/s -- more concurrent streams, fewer
+// open-page hits). So the persistent grid is SMs x B with B = inflight / (256 x loads per thread), capped by occupancy;
+// DFSA_STREAM_INFLIGHT (default 2048) overrides the target.
 template <int UNROLL, class T, class LD, class ST>
 static int launchStream(uint64_t numItems, LD ld, ST st) {
     if (numItems == 0) return DFSA_OK;
     static int blocksPerSM = 0;
     if (blocksPerSM == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, streamKernel<UNROLL, T, LD, ST>, DFSA_TPB, 0) != cudaSuccess || blocksPerSM < 1)
-            blocksPerSM = 4;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streamKernel<UNROLL, T, LD, ST>, DFSA_TPB, 0) != cudaSuccess || occ < 1) occ = 4;
+        const char* e = getenv("DFSA_STREAM_INFLIGHT");
+        const int inflight = e ? atoi(e) : 2048;
+        const int loadsPerThread = UNROLL * T::kLoads;
+        int want = inflight / (DFSA_TPB * loadsPerThread);
+        if (want < 1) want = 1;
+        blocksPerSM = want < occ ? want : occ;
     }
     unsigned grid = dfsaGrid(numItems, DFSA_TPB, UNROLL, (unsigned)blocksPerSM);
     streamKernel<UNROLL, T, LD, ST><<<grid, DFSA_TPB, 0, dfsaCtx().compute>>>(numItems, ld, st);
@@ -46,8 +57,11 @@ static int launchStream(uint64_t numItems, LD ld, ST st) {
     return DFSA_OK;
 }
 
-struct Amp1 { double2 a; };
-struct Amp2 { double2 a0, a1; };
-struct Amp4 { double2 a00, a01, a10, a11; };
-struct Amp3 { double2 a, b, c; };
-struct PairAt { double2 a0, a1; uint64_t idx; };   // an amplitude pair plus the index it was loaded from
+// item types; kLoads = 16-byte loads one item keeps in flight (used to size the grid, see launchStream)
+struct Amp1 { static constexpr int kLoads = 1; double2 a; };
+struct Amp2 { static constexpr int kLoads = 2; double2 a0, a1; };
+struct Amp4 { static constexpr int kLoads = 4; double2 a00, a01, a10, a11; };
+struct Amp3 { static constexpr int kLoads = 3; double2 a, b, c; };
+struct PairAt { static constexpr int kLoads = 2; double2 a0, a1; uint64_t idx; };   // an amplitude pair plus the index it was loaded from
+// a pair that is only MOVED (swap): half the traffic per item of a read-modify-write pair, so twice as many in flight
+struct MovePair { static constexpr int kLoads = 1; double2 a0, a1; uint64_t idx; };
