@@ -3,90 +3,24 @@
 // enumerated by inserting zeros at the sorted target positions. 32*A bytes of HBM traffic and 8*2^t flop per
 // amplitude: HBM-bound for t <= 4, FP64-pipe-bound from t = 5 (256 flop per 32 bytes vs a ridge of ~5.7 flop/B).
 //
-// Four kernels:
-//   t <= 2  manyTargWarpKernel<T>   warp-private tiles, gate in __constant__ memory (DFMA with constant operands); HBM-bound
-//   t = 3..5 manyTargDmmaKernel<T>  warp-private tiles, FP64 tensor cores (mma.sync m16n8k16.f64 -> DMMA), gate held as
-//                                   A-fragments in registers. ncu showed the DFMA version of this case to be issue/I-cache
-//                                   bound at 18 % FP64-pipe utilisation and 8 % of DRAM bandwidth, i.e. compute- not
-//                                   HBM-bound (profiles/r01_ncu_manytarg.txt), which is when the tensor path is warranted.
-//   t == 6  manyTargTileKernel<8>   block tile, gate transposed in shared memory
+// Kernels:
+//   t == 1  the pair-stream kernel of K1 (same operator)
+//   t == 2  register-resident 4x4 matvec on the streaming skeleton (quad items, gate in kernel parameters); HBM-bound
+//   t = 3..5 manyTargDmmaKernel<T>  warp-private tiles of 2^t x 32 amplitudes, FP64 tensor cores
+//           (mma.sync m16n8k16.f64 -> SASS DMMA.8x8x4), gate held as A-fragments in registers, cp.async double buffering.
+//           ncu showed the DFMA version of t=5 to be issue/I-cache bound at 18 % FP64-pipe utilisation and 8 % of DRAM
+//           bandwidth, i.e. compute- not HBM-bound (profiles/r01_ncu_manytarg.txt): the case north_star reserves the
+//           tensor path for. t=3,4 use the same pipeline and are HBM-bound.
+//   t == 6  manyTargTileKernel<8>   block tile, gate transposed in shared memory, DFMA
 //   t >= 7  manyTargGenericKernel   one block per 2^t group, gate streamed from L2, warp-per-row reduction
+// A tile = the 2^(t+f) amplitudes spanned by the t target bits and the f (<= 5) lowest non-target bits, so global
+// traffic is contiguous runs and each of the 32 lanes of a warp owns one vector; it is staged as X[row][lane]
+// (row = gate-ordered target bits).
 #include <algorithm>
 #include <vector>
 
 #include <string.h>
-#include "dfsa_internal.cuh"
-
-// ---------------------------------------------------------------------------------------------------------
-// t <= 5. A tile = the 2^(t+f) amplitudes spanned by the t target bits and the f (<= 5) lowest non-target bits.
-// Each WARP owns a tile: the 32 lanes stage it into the warp's private shared-memory slab X[row][lane]
-// (row = gate-ordered target bits, lane = the f free bits) with 2^t independent, coalesced 16-byte loads per
-// lane; then lane v multiplies vector v: acc[r] += G[r][l] * X[l][v], fully unrolled so that every G element is
-// an immediate constant-bank operand of the DFMA (no shared/global traffic for the gate at all) and X[l][v] is one
-// conflict-free LDS.128 per 4*2^t DFMAs; results go back through the slab and out with the same coalesced pattern.
-// No block-level barrier anywhere: warps run tiles independently (only __syncwarp).
-__constant__ double2 cGate[16];     // row-major G[r][l], 2^t x 2^t, t <= 2
-
-template <int T>
-__global__ void __launch_bounds__(128, 4)
-manyTargWarpKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f) {
-    constexpr unsigned D = 1u << T;
-    extern __shared__ double2 smem[];
-    // per-block tables: element e = lane | (i << 5) of a tile -> address offset / X slot, split by lane and i parts
-    __shared__ uint64_t iOff[D];
-    __shared__ unsigned iSlot[D];
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
-    const unsigned lanes = 1u << f, tileAmps = D << f, bitsInTile = T + f;
-    double2* X = smem + (size_t)warp * (D * 32u);
-
-    auto decompose = [&](unsigned e, uint64_t& off, unsigned& slot) {
-        off = 0; slot = 0;
-        for (unsigned b = 0; b < bitsInTile; b++) {
-            const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
-            off |= (uint64_t)bit << tileSpec.pos[b];
-            slot |= (role < (unsigned)T) ? (bit << (role + 5)) : (bit << (role - T));   // X[row][lane] = X[row*32 + lane]
-        }
-    };
-    if (threadIdx.x < D) {
-        uint64_t off; unsigned slot;
-        decompose(threadIdx.x << 5, off, slot);
-        iOff[threadIdx.x] = off; iSlot[threadIdx.x] = slot;
-    }
-    uint64_t laneOff; unsigned laneSlot;
-    decompose(lane, laneOff, laneSlot);
-    __syncthreads();
-    const unsigned elemsPerLane = (tileAmps + 31u) >> 5;          // == D when f == 5
-
-    for (uint64_t tile = (uint64_t)blockIdx.x * warpsPerBlock + warp; tile < numTiles; tile += (uint64_t)gridDim.x * warpsPerBlock) {
-        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
-        // stage in (all loads independent)
-#pragma unroll
-        for (unsigned i = 0; i < D; i++)
-            if (i < elemsPerLane && (lane | (i << 5)) < tileAmps) X[laneSlot | iSlot[i]] = amps[base | iOff[i]];
-        __syncwarp();
-        double2 acc[D];
-#pragma unroll
-        for (unsigned r = 0; r < D; r++) acc[r] = make_double2(0.0, 0.0);
-        if (lane < lanes) {
-#pragma unroll
-            for (unsigned l = 0; l < D; l++) {
-                const double2 x = X[l * 32u + lane];
-#pragma unroll
-                for (unsigned r = 0; r < D; r++) acc[r] = cfma(cGate[r * D + l], x, acc[r]);
-            }
-        }
-        __syncwarp();
-        if (lane < lanes) {
-#pragma unroll
-            for (unsigned r = 0; r < D; r++) X[r * 32u + lane] = acc[r];
-        }
-        __syncwarp();
-#pragma unroll
-        for (unsigned i = 0; i < D; i++)
-            if (i < elemsPerLane && (lane | (i << 5)) < tileAmps) amps[base | iOff[i]] = X[laneSlot | iSlot[i]];
-        __syncwarp();
-    }
-}
+#include "dfsa_stream_kernels.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // t == 5 on the FP64 tensor cores. The complex 32x32 matvec over the 32 vectors of a tile is the real GEMM
@@ -351,6 +285,8 @@ __global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint
 
 // ---------------------------------------------------------------------------------------------------------
 
+struct Gate4 { double2 m[16]; };
+
 namespace {
 
 // tile bits = targets U the f lowest non-target bits; localPos.pos[b] = role of the b-th (sorted) tile bit:
@@ -369,25 +305,6 @@ int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask
         if (!isTarget) for (unsigned i = 0; i < f; i++) if (freeBits[i] == q) role = t + i;
         localPos->pos[b] = (uint8_t)role;
     }
-    return DFSA_OK;
-}
-
-template <int T>
-int launchWarpKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f) {
-    DfsaContext& ctx = dfsaCtx();
-    constexpr unsigned warpsPerBlock = 4;
-    const size_t smemBytes = (size_t)warpsPerBlock * (32u << T) * sizeof(double2);       // 64 KiB at t = 5
-    static bool configured = false;
-    static int blocksPerSM = 1;
-    if (!configured) {
-        DFSA_CUDA(cudaFuncSetAttribute(manyTargWarpKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, manyTargWarpKernel<T>, 128, smemBytes) != cudaSuccess || blocksPerSM < 1) blocksPerSM = 1;
-        configured = true;
-    }
-    uint64_t blocksNeeded = (numTiles + warpsPerBlock - 1) / warpsPerBlock;
-    unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs * blocksPerSM);
-    manyTargWarpKernel<T><<<grid, 128, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f);
-    DFSA_LAUNCH_CHECK();
     return DFSA_OK;
 }
 
@@ -421,6 +338,37 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
     const size_t gateBytes = d * d * sizeof(double2);
     DfsaContext& ctx = dfsaCtx();
 
+    if (t == 1) return dfsa_k_ctrlOneTarg(s, nullptr, 0, targets[0], gate);      // same operator as K1: pair-stream kernel
+
+    if (t == 2) {
+        // register-resident 4x4 complex matvec on the streaming skeleton: item = the four amplitudes spanned by the two
+        // target bits (gate bit 0 <-> targets[0], bit 1 <-> targets[1]); the 16 gate entries ride in the kernel parameters
+        Gate4 g;
+        for (int e = 0; e < 16; e++) g.m[e] = hostAmp(gate + 2 * e);
+        double2* amps = s->arr[DFSA_AMPS];
+        const uint64_t b0 = 1ULL << targets[0], b1 = 1ULL << targets[1];
+        const unsigned lo = sortedT.pos[0], hi = sortedT.pos[1];
+        auto ld = [=] __device__(uint64_t j) {
+            QuadAt q;
+            q.idx = insertZeroBit(insertZeroBit(j, lo), hi);
+            q.v0 = amps[q.idx]; q.v1 = amps[q.idx | b0]; q.v2 = amps[q.idx | b1]; q.v3 = amps[q.idx | b0 | b1];
+            return q;
+        };
+        auto st = [=] __device__(uint64_t, const QuadAt& q) {
+            const double2 x[4] = {q.v0, q.v1, q.v2, q.v3};
+            double2 y[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                double2 acc = cmul(g.m[4 * r], x[0]);
+#pragma unroll
+                for (int l = 1; l < 4; l++) acc = cfma(g.m[4 * r + l], x[l], acc);
+                y[r] = acc;
+            }
+            amps[q.idx] = y[0]; amps[q.idx | b0] = y[1]; amps[q.idx | b1] = y[2]; amps[q.idx | b0 | b1] = y[3];
+        };
+        return launchStream<1, QuadAt>(s->numAmps >> 2, ld, st);
+    }
+
     if (t >= 3 && t <= 5) {
         void* stage; int slot;
         DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
@@ -437,23 +385,6 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
             case 3:  return launchDmmaKernel<3>(s, numTiles, tileSpec, localPos, f, dev);
             case 4:  return launchDmmaKernel<4>(s, numTiles, tileSpec, localPos, f, dev);
             default: return launchDmmaKernel<5>(s, numTiles, tileSpec, localPos, f, dev);
-        }
-    }
-
-    if (t <= 2) {
-        void* stage; int slot;
-        DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
-        memcpy(stage, gate, gateBytes);
-        DFSA_CUDA(cudaMemcpyToSymbolAsync(cGate, stage, gateBytes, 0, cudaMemcpyHostToDevice, ctx.compute));
-        DFSA_TRY(dfsaStagingCommit(slot));
-        const unsigned f = std::min(5u, L - t);
-        BitSpec tileSpec, localPos;
-        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
-        const uint64_t numTiles = s->numAmps >> (t + f);
-        switch (t) {
-            case 1:  return launchWarpKernel<1>(s, numTiles, tileSpec, localPos, f);
-            case 2:  return launchWarpKernel<2>(s, numTiles, tileSpec, localPos, f);
-            default: return launchWarpKernel<2>(s, numTiles, tileSpec, localPos, f);
         }
     }
 

@@ -297,6 +297,15 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
     return launchStream<1, Amp2>(items, ld, st);
 }
 
+// unpack half a shard from an arbitrary (possibly peer-mapped) source: amps[insert(k, qb, bitValue)] = src[k]
+int dfsaLaunchUnpackFrom(dfsa_state* s, unsigned qb, unsigned bitValue, const double2* src) {
+    double2* amps = s->arr[DFSA_AMPS];
+    const uint64_t fixed = (uint64_t)(bitValue & 1u) << qb;
+    auto ld = [=] __device__(uint64_t k) { return Amp1{src[k]}; };
+    auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = v.a; };
+    return launchStream<2, Amp1>(s->numAmps >> 1, ld, st);
+}
+
 // K9: distributed_statevector.hpp:133-135, 152-156
 extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t srcStart, uint64_t num) {
     DFSA_TRY(dfsaEnsureDevice());

@@ -63,5 +63,6 @@ struct Amp2 { static constexpr int kLoads = 2; double2 a0, a1; };
 struct Amp4 { static constexpr int kLoads = 4; double2 a00, a01, a10, a11; };
 struct Amp3 { static constexpr int kLoads = 3; double2 a, b, c; };
 struct PairAt { static constexpr int kLoads = 2; double2 a0, a1; uint64_t idx; };   // an amplitude pair plus the index it was loaded from
+struct QuadAt { static constexpr int kLoads = 4; double2 v0, v1, v2, v3; uint64_t idx; };   // four amplitudes spanned by two target bits
 // a pair that is only MOVED (swap): half the traffic per item of a read-modify-write pair, so twice as many in flight
 struct MovePair { static constexpr int kLoads = 1; double2 a0, a1; uint64_t idx; };

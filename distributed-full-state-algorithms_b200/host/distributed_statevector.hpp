@@ -97,9 +97,8 @@ static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, N
         DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, offset, 0, half));
         return;
     }
-    DFSA_CHECK(dfsa_k_pack(psi.handle, &qb1, 1, movingBit, 0));
-    comm_exchangeArrays(psi.buffer, 0, psi.buffer, half, half, pairRank);
-    DFSA_CHECK(dfsa_k_unpack(psi.handle, &qb1, 1, movingBit, half));
+    // pack the moving half, trade it with the partner, unpack into the same positions (reference :160-186)
+    DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, qb1, movingBit, int(pairRank)));
 }
 
 // relocation plan of manyTargGate: each prefix target (caller order) takes the lowest still-free suffix qubit

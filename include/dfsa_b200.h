@@ -111,6 +111,11 @@ int dfsa_x_allreduce_amp(double reim[2]);                         /* comm_reduce
  * stream, so a prefix gate costs ~max(NVLink time, HBM time) instead of their sum. Same results as
  * dfsa_x_exchange + dfsa_k_combine / dfsa_k_pauliCombine. */
 int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]);
+/* swapGate of a suffix qubit `qb1` with the prefix qubit whose rank bit distinguishes this rank from `pairRank`
+ * (distributed_statevector.hpp:160-186: pack, exchange half, unpack). `movingBit` is the value of qb1 in the half that
+ * leaves this rank (= NOT this rank's bit of the prefix qubit). With peer-mapped shards the partner's packed half is
+ * gathered straight over NVLink into place; otherwise pack + dfsa_x_exchange + unpack. */
+int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank);
 int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
                                  const double f[2], const double g[2], int exact);
 
