@@ -108,4 +108,33 @@ void* dfsa_host_dm_partialTrace(void* h, const unsigned* targets, unsigned numTa
     return new DensityMatrix(distributed_densitymatrix_partialTrace(dm(h), toNats(targets, numTargets)));
 }
 
+// ---- host-side plans (pure functions, no device needed): what each rank would exchange for an op
+// out = {kind, pairRank, numAmps, bit}
+void dfsa_host_plan_ctrlOneTarg(unsigned rank, unsigned L, const unsigned* ctrls, unsigned numCtrls, unsigned target, unsigned long long* out) {
+    dfsa_detail::ExchangePlan p = dfsa_detail::planCtrlOneTarg(rank, L, toNats(ctrls, numCtrls), target);
+    out[0] = p.kind; out[1] = p.pairRank; out[2] = p.numAmps; out[3] = p.bit;
+}
+void dfsa_host_plan_swap(unsigned rank, unsigned L, unsigned qb1, unsigned qb2, unsigned long long* out) {
+    dfsa_detail::ExchangePlan p = dfsa_detail::planSwap(rank, L, qb1, qb2);
+    out[0] = p.kind; out[1] = p.pairRank; out[2] = p.numAmps; out[3] = p.bit;
+}
+// out = {pairRank, numY, maskXY, maskYZ}
+void dfsa_host_plan_pauli(unsigned rank, unsigned L, const unsigned* targets, const unsigned* paulis, unsigned n, unsigned long long* out) {
+    dfsa_detail::PauliPlan p = dfsa_detail::planPauli(rank, L, toNats(targets, n), toNats(paulis, n));
+    out[0] = p.pairRank; out[1] = p.numY; out[2] = p.maskXY; out[3] = p.maskYZ;
+}
+void dfsa_host_plan_manyTarg(unsigned L, const unsigned* targets, unsigned n, unsigned* placedOut) {
+    NatArray placed = dfsa_planManyTargRelocation(L, toNats(targets, n));
+    for (unsigned i = 0; i < n; i++) placedOut[i] = placed[i];
+}
+// sortedTargets: the ket targets, ascending; reorderedOut has 2n entries, remainingOut 2N-2n
+void dfsa_host_plan_partialTrace(unsigned N, unsigned L, const unsigned* sortedTargets, unsigned n, unsigned* reorderedOut, unsigned* remainingOut) {
+    NatArray ext = toNats(sortedTargets, n);
+    for (unsigned i = 0; i < n; i++) ext.push_back(sortedTargets[i] + N);
+    NatArray re = getReorderedAllSuffixTargets(ext, L);
+    NatArray rem = getNonTargetedQubitOrder(2 * N, ext, re);
+    for (unsigned i = 0; i < 2 * n; i++) reorderedOut[i] = re[i];
+    for (std::size_t i = 0; i < rem.size(); i++) remainingOut[i] = rem[i];
+}
+
 }  // extern "C"

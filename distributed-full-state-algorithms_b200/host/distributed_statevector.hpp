@@ -17,7 +17,84 @@
 
 namespace dfsa_detail {
 inline void ampToArray(const Amp& a, double out[2]) { out[0] = a.real(); out[1] = a.imag(); }
+
+// ---- the host-side decisions of the distributed algorithms as pure functions of (rank, L = logNumAmpsPerNode, args).
+// The entry points below act on exactly these plans; tests/test_gloo_host_plans.py checks on CPU, across ranks, that
+// every planned exchange is symmetric (my partner plans the same exchange with me, same size).
+
+struct ExchangePlan {
+    enum Kind { Local = 0, Skip = 1, FullShard = 2, SubCube = 3, HalfContiguous = 4, HalfPacked = 5 };
+    int kind = Local;
+    Nat pairRank = 0;
+    Index numAmps = 0;       // amplitudes that travel per direction
+    Nat bit = 0;             // this rank's bit of the prefix qubit involved (FullShard / SubCube), or the moving bit (Half*)
+};
+
+// oneTargGate / manyCtrlOneTargGate (reference :18-39, :81-106)
+inline ExchangePlan planCtrlOneTarg(Nat rank, Nat L, const NatArray& controls, Nat target, NatArray* suffixCtrlsOut = nullptr) {
+    ExchangePlan plan;
+    NatArray suffixCtrls;
+    Index prefixCtrlMask = 0;
+    for (Nat q : controls) {
+        if (q >= L) prefixCtrlMask |= Index(1) << (q - L);
+        else suffixCtrls.push_back(q);
+    }
+    std::sort(suffixCtrls.begin(), suffixCtrls.end());
+    if (suffixCtrlsOut) *suffixCtrlsOut = suffixCtrls;
+    // a rank whose index fails a prefix control holds no amplitude the gate touches; its partner (same control
+    // bits) fails too, so skipping before any communication cannot deadlock (reference :92-93)
+    if ((Index(rank) & prefixCtrlMask) != prefixCtrlMask) { plan.kind = ExchangePlan::Skip; return plan; }
+    if (target < L) { plan.kind = ExchangePlan::Local; return plan; }
+    plan.pairRank = Nat(flipBit(rank, target - L));
+    plan.bit = getBit(rank, target - L);
+    plan.kind = suffixCtrls.empty() ? ExchangePlan::FullShard : ExchangePlan::SubCube;
+    plan.numAmps = (Index(1) << L) >> suffixCtrls.size();
+    return plan;
 }
+
+// swapGate (reference :109-187)
+inline ExchangePlan planSwap(Nat rank, Nat L, Nat qb1, Nat qb2) {
+    ExchangePlan plan;
+    if (qb1 > qb2) std::swap(qb1, qb2);
+    const Index A = Index(1) << L;
+    if (qb2 < L) { plan.kind = ExchangePlan::Local; return plan; }
+    if (qb1 >= L) {
+        // both prefix: ranks whose two bits differ trade whole shards with the rank that has them exchanged
+        if (getBit(rank, qb1 - L) == getBit(rank, qb2 - L)) { plan.kind = ExchangePlan::Skip; return plan; }
+        plan.kind = ExchangePlan::FullShard;
+        plan.pairRank = Nat(flipBit(flipBit(rank, qb1 - L), qb2 - L));
+        plan.numAmps = A;
+        return plan;
+    }
+    // one suffix, one prefix qubit: the half of the shard whose qb1 bit differs from this rank's qb2 bit moves
+    plan.pairRank = Nat(flipBit(rank, qb2 - L));
+    plan.numAmps = A / 2;
+    plan.bit = !getBit(rank, qb2 - L);
+    plan.kind = (qb1 == L - 1) ? ExchangePlan::HalfContiguous : ExchangePlan::HalfPacked;
+    return plan;
+}
+
+struct PauliPlan {
+    Nat pairRank = 0, numY = 0;
+    Index maskXY = 0, maskYZ = 0;
+};
+
+// pauliTensor / pauliGadget (reference :244-276)
+inline PauliPlan planPauli(Nat rank, Nat L, const NatArray& targets, const NatArray& paulis) {
+    PauliPlan plan;
+    plan.pairRank = rank;
+    for (std::size_t i = 0; i < targets.size(); i++) {
+        const bool isXY = (paulis[i] == X || paulis[i] == Y), isYZ = (paulis[i] == Y || paulis[i] == Z);
+        if (paulis[i] == Y) plan.numY++;
+        if (isYZ) plan.maskYZ |= Index(1) << targets[i];            // includes prefix bits: the sign uses global indices
+        if (isXY) {
+            if (targets[i] >= L) plan.pairRank = Nat(flipBit(plan.pairRank, targets[i] - L));
+            else plan.maskXY |= Index(1) << targets[i];
+        }
+    }
+    return plan;
+}
+}  // namespace dfsa_detail
 
 // A 2x2 gate on a prefix qubit mixes this shard with the partner's: amps = g[b][b]*amps + g[b][!b]*partner
 static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMatrix& gate) {
@@ -40,65 +117,45 @@ inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, Am
 static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi, NatArray controls, Nat target, AmpMatrix gate) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
     NatArray suffixCtrls;
-    Index prefixCtrlMask = 0;
-    for (Nat q : controls) {
-        if (q >= L) prefixCtrlMask |= Index(1) << (q - L);
-        else suffixCtrls.push_back(q);
+    const dfsa_detail::ExchangePlan plan = dfsa_detail::planCtrlOneTarg(psi.rank, L, controls, target, &suffixCtrls);
+    switch (plan.kind) {
+        case dfsa_detail::ExchangePlan::Skip: return;
+        case dfsa_detail::ExchangePlan::Local: local_statevector_manyCtrlOneTargGate(psi, suffixCtrls, target, gate); return;
+        case dfsa_detail::ExchangePlan::FullShard: dfsa_prefixOneTarg(psi, target, gate); return;
+        default: break;
     }
-    // a rank whose index fails a prefix control holds no amplitude the gate touches; its partner (same control
-    // bits) fails too, so returning before any communication cannot deadlock (reference :92-93)
-    if ((Index(psi.rank) & prefixCtrlMask) != prefixCtrlMask) return;
-
-    if (target < L) { local_statevector_manyCtrlOneTargGate(psi, suffixCtrls, target, gate); return; }
-    if (suffixCtrls.empty()) { dfsa_prefixOneTarg(psi, target, gate); return; }
-
     // prefix target, suffix controls: only the ctrl=1 sub-cube (A / 2^c amplitudes) travels
-    std::sort(suffixCtrls.begin(), suffixCtrls.end());
-    const Nat rankTarget = target - L;
-    const Nat pairRank = Nat(flipBit(psi.rank, rankTarget));
-    const Index numAmpsToMod = psi.numAmpsPerNode >> suffixCtrls.size();
     const Index allOnes = (Index(1) << suffixCtrls.size()) - 1;
     DFSA_CHECK(dfsa_k_pack(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), allOnes, 0));
-    comm_exchangeArrays(psi.buffer, 0, psi.buffer, numAmpsToMod, numAmpsToMod, pairRank);
-    const Nat bit = getBit(psi.rank, rankTarget);
+    comm_exchangeArrays(psi.buffer, 0, psi.buffer, plan.numAmps, plan.numAmps, plan.pairRank);
     double f0[2], f1[2];
-    dfsa_detail::ampToArray(gate[bit][bit], f0);
-    dfsa_detail::ampToArray(gate[bit][!bit], f1);
-    DFSA_CHECK(dfsa_k_combineSub(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), allOnes, numAmpsToMod, f0, f1));
+    dfsa_detail::ampToArray(gate[plan.bit][plan.bit], f0);
+    dfsa_detail::ampToArray(gate[plan.bit][!plan.bit], f1);
+    DFSA_CHECK(dfsa_k_combineSub(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), allOnes, plan.numAmps, f0, f1));
 }
 
 static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, Nat qb2) {
     if (qb1 > qb2) std::swap(qb1, qb2);
-    const Nat L = Nat(psi.logNumAmpsPerNode);
-
-    if (qb2 < L) { local_statevector_swapGate(psi, qb1, qb2); return; }
-
-    if (qb1 >= L) {
-        // both prefix: ranks whose two bits differ trade whole shards with the rank that has them exchanged
-        const Nat alt1 = qb1 - L, alt2 = qb2 - L;
-        if (getBit(psi.rank, alt1) != getBit(psi.rank, alt2)) {
-            const Nat pairRank = Nat(flipBit(flipBit(psi.rank, alt1), alt2));
-            comm_exchangeArrays(psi.amps, psi.buffer, pairRank);
-            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, 0, 0, psi.numAmpsPerNode));
+    const dfsa_detail::ExchangePlan plan = dfsa_detail::planSwap(psi.rank, Nat(psi.logNumAmpsPerNode), qb1, qb2);
+    switch (plan.kind) {
+        case dfsa_detail::ExchangePlan::Local: local_statevector_swapGate(psi, qb1, qb2); return;
+        case dfsa_detail::ExchangePlan::Skip: return;
+        case dfsa_detail::ExchangePlan::FullShard:
+            comm_exchangeArrays(psi.amps, psi.buffer, plan.pairRank);
+            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, 0, 0, psi.numAmpsPerNode));      // whole shard: becomes a pointer swap
+            return;
+        case dfsa_detail::ExchangePlan::HalfContiguous: {
+            // qb1 is the top suffix qubit: the moving half is contiguous, no packing
+            const Index offset = plan.numAmps * plan.bit;
+            comm_exchangeArrays(psi.amps, offset, psi.buffer, 0, plan.numAmps, plan.pairRank);
+            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, offset, 0, plan.numAmps));
+            return;
         }
-        return;
+        default:
+            // pack the moving half, trade it with the partner, unpack into the same positions (reference :160-186)
+            DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, qb1, plan.bit, int(plan.pairRank)));
+            return;
     }
-
-    // one suffix, one prefix qubit: the half of the shard whose qb1 bit differs from this rank's qb2 bit moves
-    const Nat alt2 = qb2 - L;
-    const Nat pairRank = Nat(flipBit(psi.rank, alt2));
-    const Index half = psi.numAmpsPerNode / 2;
-    const Nat movingBit = !getBit(psi.rank, alt2);
-
-    if (qb1 == L - 1) {
-        // that half is contiguous: no packing
-        const Index offset = half * movingBit;
-        comm_exchangeArrays(psi.amps, offset, psi.buffer, 0, half, pairRank);
-        DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, offset, 0, half));
-        return;
-    }
-    // pack the moving half, trade it with the partner, unpack into the same positions (reference :160-186)
-    DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, qb1, movingBit, int(pairRank)));
 }
 
 // relocation plan of manyTargGate: each prefix target (caller order) takes the lowest still-free suffix qubit
@@ -128,28 +185,17 @@ static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArr
 
 static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi, const NatArray& targets, const NatArray& paulis, Amp thisAmpFac, Amp otherAmpFac) {
     assert(targets.size() == paulis.size());
-    const Nat L = Nat(psi.logNumAmpsPerNode);
-    Nat numY = 0, pairRank = psi.rank;
-    Index maskXY = 0, maskYZ = 0;
-    for (std::size_t i = 0; i < targets.size(); i++) {
-        const bool isXY = (paulis[i] == X || paulis[i] == Y), isYZ = (paulis[i] == Y || paulis[i] == Z);
-        if (paulis[i] == Y) numY++;
-        if (isYZ) maskYZ |= Index(1) << targets[i];                 // includes prefix bits: the sign uses global indices
-        if (isXY) {
-            if (targets[i] >= L) pairRank = Nat(flipBit(pairRank, targets[i] - L));
-            else maskXY |= Index(1) << targets[i];
-        }
-    }
-    if (pairRank == psi.rank) {
-        local_statevector_pauliTensorOrGadget_subroutine(psi, numY, maskXY, maskYZ, thisAmpFac, otherAmpFac);
+    const dfsa_detail::PauliPlan plan = dfsa_detail::planPauli(psi.rank, Nat(psi.logNumAmpsPerNode), targets, paulis);
+    if (plan.pairRank == psi.rank) {
+        local_statevector_pauliTensorOrGadget_subroutine(psi, plan.numY, plan.maskXY, plan.maskYZ, thisAmpFac, otherAmpFac);
         return;
     }
     double f[2], g[2];
     dfsa_detail::ampToArray(thisAmpFac, f);
     dfsa_detail::ampToArray(otherAmpFac, g);
     const int exact = (thisAmpFac == Amp(0, 0) && otherAmpFac == Amp(1, 0));
-    // full-shard exchange + combine of the reference (:227-241), chunk-pipelined
-    DFSA_CHECK(dfsa_xk_exchangePauliCombine(psi.handle, int(pairRank), maskXY, maskYZ, numY, f, g, exact));
+    // full-shard exchange + combine of the reference (:227-241), fused over peer memory / chunk-pipelined
+    DFSA_CHECK(dfsa_xk_exchangePauliCombine(psi.handle, int(plan.pairRank), plan.maskXY, plan.maskYZ, plan.numY, f, g, exact));
 }
 
 static inline void distributed_statevector_pauliTensor(StateVector& psi, NatArray targets, NatArray paulis) {
