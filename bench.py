@@ -200,6 +200,10 @@ def cpu_baseline_sample(budget_s=25.0):
 
 def run_product(args, world, rank, local_rank):
     import cases
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch                                  # load torch's NCCL before ours; torch.distributed = plumbing only
         import torch.distributed as dist
@@ -356,7 +360,7 @@ def run_product(args, world, rank, local_rank):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     st.close()
     if world > 1:
         dist.barrier()

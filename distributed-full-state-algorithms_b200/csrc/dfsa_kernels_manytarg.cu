@@ -44,8 +44,47 @@ __device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr unsigned DMMA_WARPS = 6;        // warps per block; each owns two D x 34 amplitude slabs (double buffer)
-constexpr unsigned DMMA_S = 34;           // slab row stride in amplitudes
+// ---- TMA-style 1-D bulk copies (cp.async.bulk, SASS UBLKCP) with mbarrier completion: one instruction moves a whole
+// 512-byte tile row between global and shared memory through the async proxy
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* smemDst, const void* gmemSrc, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smemAddr(smemDst)), "l"(gmemSrc), "r"(bytes), "r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bulkStore(void* gmemDst, const void* smemSrc, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmemDst), "r"(smemAddr(smemSrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitRead0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsync() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Per-T geometry. A warp owns two slabs (double buffer) of D rows x VEC vectors, row stride VEC + 2 amplitudes (the 4x8
+// B-fragment footprint then hits 8 distinct 16-byte bank groups per quarter-warp). t = 5 is register-limited to 8 warps
+// per SM (238 registers), so it uses 16-vector tiles: 8 x 2 x 32 x 18 x 16 B = 144 KiB lets all 8 warps (2 per
+// scheduler) be resident; t = 3, 4 use 32-vector tiles and 6-warp blocks (4 resp. 2 blocks per SM).
+template <int T> struct DmmaGeom {
+    static constexpr unsigned F = (T == 5) ? 4 : 5;          // free (vector) bits per tile
+    static constexpr unsigned VEC = 1u << F;
+    static constexpr unsigned S = VEC + 2;
+    static constexpr unsigned WARPS = (T == 5) ? 8 : 6;
+    static constexpr unsigned D = 1u << T;
+    static constexpr size_t smemBytes = (size_t)WARPS * 2 * D * S * sizeof(double2);
+};
 
 // Software pipeline per warp: while the tensor cores work on tile k (slab k&1), cp.async (LDGSTS, L2 -> shared,
 // no registers) is already filling the other slab with tile k+1, so HBM latency is hidden with few resident warps.
@@ -53,10 +92,13 @@ constexpr unsigned DMMA_S = 34;           // slab row stride in amplitudes
 //   T = 4: one 16x16 block each for G_re, G_im, 4 MMAs per 8 vectors
 //   T = 3: the 8x8 complex gate as ONE real 16x16 A-fragment [[G_re,-G_im],[G_im,G_re]], B = [X_re; X_im] stacked
 //          along k, 1 MMA per 8 vectors
-template <int T>
-__global__ void __launch_bounds__(32 * DMMA_WARPS, (T == 5) ? 1 : (T == 4 ? 2 : 4))
+//   BULK: the tile's 32 vectors are contiguous in memory (all targets >= bit 5, f == 5), so each of the 2^T tile rows is
+//         one 512-byte run: lane i moves row i with a single bulk async copy in (mbarrier completion) and out
+//         (bulk async-group), instead of 32 per-lane 16-byte cp.async / st.global each.
+template <int T, bool BULK>
+__global__ void __launch_bounds__(32 * DmmaGeom<T>::WARPS, (T == 5) ? 1 : (T == 4 ? 2 : 4))
 manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f, const double2* __restrict__ gate) {
-    constexpr unsigned D = 1u << T, S = DMMA_S;
+    constexpr unsigned D = 1u << T, S = DmmaGeom<T>::S, VEC = DmmaGeom<T>::VEC, WARPS = DmmaGeom<T>::WARPS;
     constexpr int NB = (T >= 4) ? (int)(D / 16) : 1;              // 16-row blocks of the complex gate (T >= 4)
     extern __shared__ double2 smem[];
     __shared__ uint64_t iOff[D];
@@ -108,27 +150,59 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
     __syncthreads();
 
     const uint64_t stride = (uint64_t)gridDim.x * warpsPerBlock;
-    auto prefetch = [&](uint64_t tile, double2* X) {
-        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+    __shared__ uint64_t bars[WARPS][2];                            // BULK: one mbarrier per warp and slab
+    __shared__ uint64_t rowOff[D];                                 // BULK: global offset of tile row r (element r << f)
+    __shared__ unsigned rowSlab[D];                                //       and the slab row it lands in
+    unsigned phase[2] = {0u, 0u};
+    if constexpr (BULK) {
+        if (threadIdx.x < D) {
+            uint64_t off; unsigned rowN;
+            decompose(threadIdx.x << f, off, rowN);
+            rowOff[threadIdx.x] = off; rowSlab[threadIdx.x] = rowN >> 8;
+        }
+        __syncthreads();
+        if (lane == 0) { mbarInit(&bars[warp][0], 1); mbarInit(&bars[warp][1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    // row i of a tile (BULK): global run at base | iOff[i], slab row iRowN[i] >> 8
+    auto prefetch = [&](uint64_t tile, double2* X, unsigned b) {
+        if constexpr (BULK) {
+            const uint64_t base = insertZeroBits(tile, tileSpec);
+            if (lane == 0) mbarExpectTx(&bars[warp][b], D * VEC * 16u);
+            if (lane < D) bulkLoad(&X[rowSlab[lane] * S], &amps[base | rowOff[lane]], VEC * 16u, &bars[warp][b]);
+        } else {
+            const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
 #pragma unroll
-        for (unsigned i = 0; i < D; i++)
-            if ((lane | (i << 5)) < tileAmps) {
-                const unsigned rn = laneRowN | iRowN[i];
-                cpAsync16(&X[(rn >> 8) * S + (rn & 255u)], &amps[base | iOff[i]]);
-            }
-        cpAsyncCommit();
+            for (unsigned i = 0; i < D; i++)
+                if ((lane | (i << 5)) < tileAmps) {
+                    const unsigned rn = laneRowN | iRowN[i];
+                    cpAsync16(&X[(rn >> 8) * S + (rn & 255u)], &amps[base | iOff[i]]);
+                }
+            cpAsyncCommit();
+        }
     };
 
     uint64_t tile = (uint64_t)blockIdx.x * warpsPerBlock + warp;
-    if (tile < numTiles) prefetch(tile, slab);
+    if (tile < numTiles) prefetch(tile, slab, 0);
     for (unsigned it = 0; tile < numTiles; it++, tile += stride) {
-        double2* X = slab + (size_t)(it & 1u) * (D * S);
+        const unsigned cur = it & 1u;
+        double2* X = slab + (size_t)cur * (D * S);
         const bool more = tile + stride < numTiles;
-        if (more) { prefetch(tile + stride, slab + (size_t)((it + 1) & 1u) * (D * S)); cpAsyncWait<1>(); }
-        else cpAsyncWait<0>();
-        __syncwarp();
+        if constexpr (BULK) {
+            // the other slab was the source of the previous tile's bulk stores: they must have finished reading it
+            bulkWaitRead0();
+            __syncwarp();
+            if (more) prefetch(tile + stride, slab + (size_t)(cur ^ 1u) * (D * S), cur ^ 1u);
+            mbarWait(&bars[warp][cur], phase[cur]);
+            phase[cur] ^= 1u;
+        } else {
+            if (more) { prefetch(tile + stride, slab + (size_t)(cur ^ 1u) * (D * S), cur ^ 1u); cpAsyncWait<1>(); }
+            else cpAsyncWait<0>();
+            __syncwarp();
+        }
 #pragma unroll 1
-        for (unsigned nb = 0; nb < 4; nb++) {
+        for (unsigned nb = 0; nb < VEC / 8; nb++) {
             if constexpr (T >= 4) {
                 double cre[NB][4], cim[NB][4];
 #pragma unroll
@@ -173,16 +247,25 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
                 X[g * S + nb * 8 + 2 * q + 1] = make_double2(c[1], c[3]);
             }
         }
-        __syncwarp();
-        const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+        if constexpr (BULK) {
+            fenceProxyAsync();                                      // results written with st.shared -> visible to the async proxy
+            __syncwarp();
+            const uint64_t base = insertZeroBits(tile, tileSpec);
+            if (lane < D) bulkStore(&amps[base | rowOff[lane]], &X[rowSlab[lane] * S], VEC * 16u);
+            bulkCommit();
+        } else {
+            __syncwarp();
+            const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
 #pragma unroll
-        for (unsigned i = 0; i < D; i++)
-            if ((lane | (i << 5)) < tileAmps) {
-                const unsigned rn = laneRowN | iRowN[i];
-                amps[base | iOff[i]] = X[(rn >> 8) * S + (rn & 255u)];
-            }
-        __syncwarp();
+            for (unsigned i = 0; i < D; i++)
+                if ((lane | (i << 5)) < tileAmps) {
+                    const unsigned rn = laneRowN | iRowN[i];
+                    amps[base | iOff[i]] = X[(rn >> 8) * S + (rn & 255u)];
+                }
+            __syncwarp();
+        }
     }
+    if constexpr (BULK) bulkWaitRead0();
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -308,21 +391,31 @@ int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask
     return DFSA_OK;
 }
 
-template <int T>
-int launchDmmaKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
+template <int T, bool BULK>
+int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
     DfsaContext& ctx = dfsaCtx();
-    const size_t smemBytes = (size_t)DMMA_WARPS * 2 * (32u >> (5 - T)) * DMMA_S * sizeof(double2);   // 204 / 102 / 51 KiB
+    constexpr unsigned WARPS = DmmaGeom<T>::WARPS;
+    const size_t smemBytes = DmmaGeom<T>::smemBytes;                // 144 KiB (t=5), 102 KiB (t=4), 51 KiB (t=3)
     static int blocksPerSM = 0;
     if (blocksPerSM == 0) {
-        DFSA_CUDA(cudaFuncSetAttribute(manyTargDmmaKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, manyTargDmmaKernel<T>, 32 * DMMA_WARPS, smemBytes) != cudaSuccess || blocksPerSM < 1)
+        DFSA_CUDA(cudaFuncSetAttribute(manyTargDmmaKernel<T, BULK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSM, manyTargDmmaKernel<T, BULK>, 32 * WARPS, smemBytes) != cudaSuccess || blocksPerSM < 1)
             blocksPerSM = 1;
     }
-    const uint64_t blocksNeeded = (numTiles + DMMA_WARPS - 1) / DMMA_WARPS;
+    const uint64_t blocksNeeded = (numTiles + WARPS - 1) / WARPS;
     const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs * blocksPerSM);
-    manyTargDmmaKernel<T><<<grid, 32 * DMMA_WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, devGate);
+    manyTargDmmaKernel<T, BULK><<<grid, 32 * WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, devGate);
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
+}
+
+template <int T>
+int launchDmmaKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
+    // bulk rows need the 32 vectors of a tile row to be one contiguous 512-byte run: free bits = address bits 0..4
+    bool contiguous = (f == DmmaGeom<T>::F) && !getenv("DFSA_MANYTARG_NO_BULK");
+    for (unsigned b = 0; b < f && contiguous; b++) contiguous = (tileSpec.pos[b] == b) && (localPos.pos[b] >= (unsigned)T);
+    return contiguous ? launchDmmaKernelImpl<T, true>(s, numTiles, tileSpec, localPos, f, devGate)
+                      : launchDmmaKernelImpl<T, false>(s, numTiles, tileSpec, localPos, f, devGate);
 }
 
 }  // namespace
@@ -377,7 +470,7 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         DFSA_TRY(dfsaScratch(gateBytes, &dev));
         DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
         DFSA_TRY(dfsaStagingCommit(slot));
-        const unsigned f = std::min(5u, L - t);
+        const unsigned f = std::min(t == 5 ? DmmaGeom<5>::F : 5u, L - t);
         BitSpec tileSpec, localPos;
         DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
         const uint64_t numTiles = s->numAmps >> (t + f);
