@@ -315,6 +315,7 @@ extern "C" int dfsa_comm_finalize(void) {
     DfsaContext& c = dfsaCtx();
     if (!c.initialised) return DFSA_OK;
     DFSA_TRY(dfsa_comm_barrier());                            // comm_end: Barrier then Finalize (communication.hpp:24-27)
+    DFSA_TRY(dfsaPoolDrain());                                // recycled shards: unregister (collective) and free
     for (auto& kv : g_comm.peerMap) cudaIpcCloseMemHandle(kv.second);
     g_comm.peerMap.clear();
     if (g_comm.nccl) { ncclCommDestroy(g_comm.nccl); g_comm.nccl = nullptr; }
@@ -351,7 +352,11 @@ int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut) {
     a.bytes = bytes;
     __sync_synchronize();
     a.valid = 1;
-    return shmBarrier();                                       // every rank's handle is published
+    // No barrier: a peer only ever looks a handle up inside an exchange, after the pair (or global) barrier that opens it,
+    // and this rank reaches that barrier after this line in program order. State creation stays a local operation,
+    // like the reference's constructor (states.hpp:31-48).
+    __sync_synchronize();
+    return DFSA_OK;
 }
 
 int dfsaPublishArrays(dfsa_state* s) {

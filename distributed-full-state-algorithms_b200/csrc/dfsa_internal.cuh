@@ -45,6 +45,7 @@ extern uint64_t g_dfsaLaunches;                      // bumped at every kernel l
 void dfsaSetError(const char* fmt, ...);
 int  dfsaEnsureDevice();                         // lazily create streams etc.; DFSA_ERR_CUDA if no device
 int  dfsaScratch(size_t bytes, double2** out);   // grow-only device scratch
+int  dfsaPoolDrain();                            // release the recycled small shards (collective when P > 1)
 
 #define DFSA_CUDA(call)                                                                              \
     do {                                                                                             \

@@ -336,10 +336,13 @@ __device__ __forceinline__ void blockReduceToPartials(double re, double im, doub
 __global__ void __launch_bounds__(256) expecGatherKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numTerms,
                                                         unsigned N, unsigned logCols, uint64_t firstCol, double2* partials) {
     double re = 0.0, im = 0.0;
-    const uint64_t cols = 1ULL << logCols, items = (uint64_t)numTerms << logCols;
+    const uint64_t items = (uint64_t)numTerms << logCols;
+    // term-major inside a column: the reads of neighbouring threads stay inside one 16 * 2^N-byte column (same DRAM
+    // pages / TLB entry) instead of striding a whole column apart
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (uint64_t)gridDim.x * blockDim.x) {
-        const PauliTerm tm = terms[w >> logCols];
-        const uint64_t c = w & (cols - 1), hi = firstCol + c, lo = hi ^ tm.xy;
+        const uint64_t c = w / numTerms;
+        const PauliTerm tm = terms[w - c * numTerms];
+        const uint64_t hi = firstCol + c, lo = hi ^ tm.xy;
         const double2 a = amps[(c << N) | lo];
         const unsigned neg = (unsigned)(__popcll(~hi & tm.y) + __popcll(hi & tm.z)) & 1u;
         double2 v = cmul(tm.coeff, a);

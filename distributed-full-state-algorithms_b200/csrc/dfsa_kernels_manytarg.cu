@@ -37,10 +37,6 @@ __device__ __forceinline__ void dmma16816(double (&c)[4], const double (&a)[8], 
                  : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(a[4]), "d"(a[5]), "d"(a[6]), "d"(a[7]), "d"(b[0]), "d"(b[1]), "d"(b[2]), "d"(b[3]));
 }
 
-__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gmemSrc) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(smemDst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gmemSrc) : "memory");
-}
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -83,7 +79,17 @@ template <int T> struct DmmaGeom {
     static constexpr unsigned S = VEC + 2;
     static constexpr unsigned WARPS = (T == 5) ? 8 : 6;
     static constexpr unsigned D = 1u << T;
+    static constexpr unsigned EPL = D * VEC / 32;             // tile elements each lane moves (8 or 16)
     static constexpr size_t smemBytes = (size_t)WARPS * 2 * D * S * sizeof(double2);
+};
+
+// Where element (lane | i << 5) of a tile lives, split into its lane part (registers) and its i part (this table). The
+// table rides in the kernel parameters, so after unrolling every entry is a constant-bank operand of the address add:
+// one cp.async / st.global costs three integer instructions instead of two shared-memory table reads plus ~15 ALU ops
+// (ncu, round 1: 1200 non-DMMA instructions per t=5 tile against 512 DMMA slots kept the tensor pipe at 54 %).
+template <int T> struct TileMap {
+    uint64_t gByte[DmmaGeom<T>::EPL];                         // byte offset in the shard
+    uint32_t sByte[DmmaGeom<T>::EPL];                         // byte offset in the slab X[row][n]
 };
 
 // Software pipeline per warp: while the tensor cores work on tile k (slab k&1), cp.async (LDGSTS, L2 -> shared,
@@ -97,32 +103,24 @@ template <int T> struct DmmaGeom {
 //         (bulk async-group), instead of 32 per-lane 16-byte cp.async / st.global each.
 template <int T, bool BULK>
 __global__ void __launch_bounds__(32 * DmmaGeom<T>::WARPS, (T == 5) ? 1 : (T == 4 ? 2 : 4))
-manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, unsigned f, const double2* __restrict__ gate) {
+manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, const double2* __restrict__ gate, TileMap<T> map) {
     constexpr unsigned D = 1u << T, S = DmmaGeom<T>::S, VEC = DmmaGeom<T>::VEC, WARPS = DmmaGeom<T>::WARPS;
+    constexpr unsigned F = DmmaGeom<T>::F, EPL = DmmaGeom<T>::EPL, SLAB_BYTES = D * S * 16u;
     constexpr int NB = (T >= 4) ? (int)(D / 16) : 1;              // 16-row blocks of the complex gate (T >= 4)
     extern __shared__ double2 smem[];
-    __shared__ uint64_t iOff[D];
-    __shared__ unsigned iRowN[D];                                  // (row << 8) | n contribution of the i part
-    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned g = lane >> 2, q = lane & 3u;
-    const unsigned tileAmps = D << f, bitsInTile = T + f;
     double2* slab = smem + (size_t)warp * (2 * D * S);
 
-    auto decompose = [&](unsigned e, uint64_t& off, unsigned& rowN) {
-        off = 0; rowN = 0;
-        for (unsigned b = 0; b < bitsInTile; b++) {
+    // tile element e (bit b of e = b-th lowest tile bit): shard offset, slab row (gate-ordered target bits) and slab column
+    auto decompose = [&](unsigned e, uint64_t& off, unsigned& row, unsigned& n) {
+        off = 0; row = 0; n = 0;
+        for (unsigned b = 0; b < T + F; b++) {
             const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
             off |= (uint64_t)bit << tileSpec.pos[b];
-            rowN |= (role < (unsigned)T) ? (bit << (role + 8)) : (bit << (role - T));
+            if (role < (unsigned)T) row |= bit << role; else n |= bit << (role - T);
         }
     };
-    if (threadIdx.x < D) {
-        uint64_t off; unsigned rowN;
-        decompose(threadIdx.x << 5, off, rowN);
-        iOff[threadIdx.x] = off; iRowN[threadIdx.x] = rowN;
-    }
-    uint64_t laneOff; unsigned laneRowN;
-    decompose(lane, laneOff, laneRowN);
 
     // the gate as A-fragments (a[v]: row g + 8(v&1), col q + 4(v>>1))
     double gr[NB][NB][8], gi[NB][NB][8];
@@ -147,57 +145,67 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
             gi[0][0][v] = 0.0;
         }
     }
-    __syncthreads();
 
-    const uint64_t stride = (uint64_t)gridDim.x * warpsPerBlock;
+    const uint64_t stride = (uint64_t)gridDim.x * WARPS;
     __shared__ uint64_t bars[WARPS][2];                            // BULK: one mbarrier per warp and slab
-    __shared__ uint64_t rowOff[D];                                 // BULK: global offset of tile row r (element r << f)
+    __shared__ uint64_t rowOff[D];                                 // BULK: shard offset of tile row r (element r << F)
     __shared__ unsigned rowSlab[D];                                //       and the slab row it lands in
     unsigned phase[2] = {0u, 0u};
+    // generic path: this lane's share of every element address (the i part comes from `map`)
+    char* laneG = reinterpret_cast<char*>(amps);
+    unsigned laneS = smemAddr(slab);
     if constexpr (BULK) {
         if (threadIdx.x < D) {
-            uint64_t off; unsigned rowN;
-            decompose(threadIdx.x << f, off, rowN);
-            rowOff[threadIdx.x] = off; rowSlab[threadIdx.x] = rowN >> 8;
+            uint64_t off; unsigned row, n;
+            decompose(threadIdx.x << F, off, row, n);
+            rowOff[threadIdx.x] = off; rowSlab[threadIdx.x] = row;
         }
         __syncthreads();
         if (lane == 0) { mbarInit(&bars[warp][0], 1); mbarInit(&bars[warp][1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
+    } else {
+        uint64_t off; unsigned row, n;
+        decompose(lane, off, row, n);
+        laneG += off << 4;
+        laneS += (row * S + n) << 4;
     }
-    // row i of a tile (BULK): global run at base | iOff[i], slab row iRowN[i] >> 8
-    auto prefetch = [&](uint64_t tile, double2* X, unsigned b) {
+    // row i of a tile (BULK): global run at base | rowOff[i], slab row rowSlab[i]
+    auto prefetch = [&](uint64_t base, unsigned b) {
         if constexpr (BULK) {
-            const uint64_t base = insertZeroBits(tile, tileSpec);
+            double2* X = slab + (size_t)b * (D * S);
             if (lane == 0) mbarExpectTx(&bars[warp][b], D * VEC * 16u);
             if (lane < D) bulkLoad(&X[rowSlab[lane] * S], &amps[base | rowOff[lane]], VEC * 16u, &bars[warp][b]);
         } else {
-            const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+            const char* src = laneG + (base << 4);
+            const unsigned dst = laneS + b * SLAB_BYTES;
 #pragma unroll
-            for (unsigned i = 0; i < D; i++)
-                if ((lane | (i << 5)) < tileAmps) {
-                    const unsigned rn = laneRowN | iRowN[i];
-                    cpAsync16(&X[(rn >> 8) * S + (rn & 255u)], &amps[base | iOff[i]]);
-                }
+            for (unsigned i = 0; i < EPL; i++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + map.sByte[i]), "l"(src + map.gByte[i]) : "memory");
             cpAsyncCommit();
         }
     };
 
-    uint64_t tile = (uint64_t)blockIdx.x * warpsPerBlock + warp;
-    if (tile < numTiles) prefetch(tile, slab, 0);
+    // shard offset of a tile's element 0: the tile counter with zeros inserted at the T + F tile bits (positions are
+    // constant-bank operands after unrolling); computed once per tile, when it is prefetched, and carried to its store
+    uint64_t tile = (uint64_t)blockIdx.x * WARPS + warp;
+    uint64_t base = 0, nextBase = insertZeroBitsN<T + F>(tile, tileSpec);
+    if (tile < numTiles) prefetch(nextBase, 0);
     for (unsigned it = 0; tile < numTiles; it++, tile += stride) {
         const unsigned cur = it & 1u;
         double2* X = slab + (size_t)cur * (D * S);
         const bool more = tile + stride < numTiles;
+        base = nextBase;
+        nextBase = insertZeroBitsN<T + F>(tile + stride, tileSpec);
         if constexpr (BULK) {
             // the other slab was the source of the previous tile's bulk stores: they must have finished reading it
             bulkWaitRead0();
             __syncwarp();
-            if (more) prefetch(tile + stride, slab + (size_t)(cur ^ 1u) * (D * S), cur ^ 1u);
+            if (more) prefetch(nextBase, cur ^ 1u);
             mbarWait(&bars[warp][cur], phase[cur]);
             phase[cur] ^= 1u;
         } else {
-            if (more) { prefetch(tile + stride, slab + (size_t)(cur ^ 1u) * (D * S), cur ^ 1u); cpAsyncWait<1>(); }
+            if (more) { prefetch(nextBase, cur ^ 1u); cpAsyncWait<1>(); }
             else cpAsyncWait<0>();
             __syncwarp();
         }
@@ -250,18 +258,21 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
         if constexpr (BULK) {
             fenceProxyAsync();                                      // results written with st.shared -> visible to the async proxy
             __syncwarp();
-            const uint64_t base = insertZeroBits(tile, tileSpec);
             if (lane < D) bulkStore(&amps[base | rowOff[lane]], &X[rowSlab[lane] * S], VEC * 16u);
             bulkCommit();
         } else {
             __syncwarp();
-            const uint64_t base = insertZeroBits(tile, tileSpec) | laneOff;
+            char* dst = laneG + (base << 4);
+            const unsigned src = laneS + cur * SLAB_BYTES;
 #pragma unroll
-            for (unsigned i = 0; i < D; i++)
-                if ((lane | (i << 5)) < tileAmps) {
-                    const unsigned rn = laneRowN | iRowN[i];
-                    amps[base | iOff[i]] = X[(rn >> 8) * S + (rn & 255u)];
-                }
+            for (unsigned i0 = 0; i0 < EPL; i0 += 4) {                // four shared loads in flight, then their four stores
+                double2 v[4];
+#pragma unroll
+                for (unsigned i = 0; i < 4; i++)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[i].x), "=d"(v[i].y) : "r"(src + map.sByte[i0 + i]) : "memory");
+#pragma unroll
+                for (unsigned i = 0; i < 4; i++) *reinterpret_cast<double2*>(dst + map.gByte[i0 + i]) = v[i];
+            }
             __syncwarp();
         }
     }
@@ -392,7 +403,7 @@ int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask
 }
 
 template <int T, bool BULK>
-int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
+int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, const double2* devGate, const TileMap<T>& map) {
     DfsaContext& ctx = dfsaCtx();
     constexpr unsigned WARPS = DmmaGeom<T>::WARPS;
     const size_t smemBytes = DmmaGeom<T>::smemBytes;                // 144 KiB (t=5), 102 KiB (t=4), 51 KiB (t=3)
@@ -404,18 +415,37 @@ int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSp
     }
     const uint64_t blocksNeeded = (numTiles + WARPS - 1) / WARPS;
     const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs * blocksPerSM);
-    manyTargDmmaKernel<T, BULK><<<grid, 32 * WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, f, devGate);
+    manyTargDmmaKernel<T, BULK><<<grid, 32 * WARPS, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, devGate, map);
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
 }
 
+// full tiles only (f == DmmaGeom<T>::F free bits): shards too small for one are the caller's business
 template <int T>
-int launchDmmaKernel(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, unsigned f, const double2* devGate) {
-    // bulk rows need the 32 vectors of a tile row to be one contiguous 512-byte run: free bits = address bits 0..4
-    bool contiguous = (f == DmmaGeom<T>::F) && !getenv("DFSA_MANYTARG_NO_BULK");
-    for (unsigned b = 0; b < f && contiguous; b++) contiguous = (tileSpec.pos[b] == b) && (localPos.pos[b] >= (unsigned)T);
-    return contiguous ? launchDmmaKernelImpl<T, true>(s, numTiles, tileSpec, localPos, f, devGate)
-                      : launchDmmaKernelImpl<T, false>(s, numTiles, tileSpec, localPos, f, devGate);
+int launchDmmaKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const double2* devGate) {
+    constexpr unsigned F = DmmaGeom<T>::F, S = DmmaGeom<T>::S;
+    const unsigned L = s->logNumAmps;
+    BitSpec tileSpec, localPos;
+    DFSA_TRY(buildTile(targets, T, L, targMask, F, &tileSpec, &localPos));
+    // i part of element (lane | i << 5): tile bits 5.. of the element index
+    TileMap<T> map;
+    for (unsigned i = 0; i < DmmaGeom<T>::EPL; i++) {
+        uint64_t off = 0;
+        unsigned row = 0, n = 0;
+        for (unsigned b = 5; b < T + F; b++) {
+            const unsigned bit = (i >> (b - 5)) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < (unsigned)T) row |= bit << role; else n |= bit << (role - T);
+        }
+        map.gByte[i] = off << 4;
+        map.sByte[i] = (row * S + n) << 4;
+    }
+    // bulk rows need the VEC vectors of a tile row to be one contiguous run: free bits = address bits 0..F-1
+    bool contiguous = !getenv("DFSA_MANYTARG_NO_BULK");
+    for (unsigned b = 0; b < F && contiguous; b++) contiguous = (tileSpec.pos[b] == b) && (localPos.pos[b] >= (unsigned)T);
+    const uint64_t numTiles = s->numAmps >> (T + F);
+    return contiguous ? launchDmmaKernelImpl<T, true>(s, numTiles, tileSpec, localPos, devGate, map)
+                      : launchDmmaKernelImpl<T, false>(s, numTiles, tileSpec, localPos, devGate, map);
 }
 
 }  // namespace
@@ -462,7 +492,8 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         return launchStream<1, QuadAt>(s->numAmps >> 2, ld, st);
     }
 
-    if (t >= 3 && t <= 5) {
+    // tensor-core tiles need t + F local bits; a smaller shard (< 2^10 amplitudes) goes to the generic kernel below
+    if (t >= 3 && t <= 5 && L >= t + (t == 5 ? DmmaGeom<5>::F : DmmaGeom<3>::F)) {
         void* stage; int slot;
         DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
         memcpy(stage, gate, gateBytes);
@@ -470,14 +501,10 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         DFSA_TRY(dfsaScratch(gateBytes, &dev));
         DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
         DFSA_TRY(dfsaStagingCommit(slot));
-        const unsigned f = std::min(t == 5 ? DmmaGeom<5>::F : 5u, L - t);
-        BitSpec tileSpec, localPos;
-        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
-        const uint64_t numTiles = s->numAmps >> (t + f);
         switch (t) {
-            case 3:  return launchDmmaKernel<3>(s, numTiles, tileSpec, localPos, f, dev);
-            case 4:  return launchDmmaKernel<4>(s, numTiles, tileSpec, localPos, f, dev);
-            default: return launchDmmaKernel<5>(s, numTiles, tileSpec, localPos, f, dev);
+            case 3:  return launchDmmaKernel<3>(s, targets, targMask, dev);
+            case 4:  return launchDmmaKernel<4>(s, targets, targMask, dev);
+            default: return launchDmmaKernel<5>(s, targets, targMask, dev);
         }
     }
 

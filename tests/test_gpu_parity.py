@@ -116,6 +116,30 @@ def test_every_target_position_one_and_ctrl_gate(dfsa):
     compare.assert_close(st.get_amps(), o.get_amps(), tol=1e-11, what="target sweep")   # 28 chained non-unitary gates
 
 
+@pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 6, 7])
+def test_many_targ_gate_every_kernel_variant(dfsa, nt):
+    """manyTargGate (local_statevector.hpp:72-99) picks its kernel by target count and placement: tensor-core tiles with
+    bulk row copies (targets above the tile's free bits), the gather form (targets among the low bits), the generic kernel
+    on shards too small for a tile. Every variant against the oracle, targets in caller order (not sorted)."""
+    rng = np.random.default_rng(100 + nt)
+    for nq in (nt, nt + 2, 13, 16):
+        if nq < nt:
+            continue
+        placements = [list(range(nt)), list(range(nq - nt, nq))[::-1], [int(x) for x in rng.permutation(nq)[:nt]]]
+        if nq >= nt + 6:
+            placements.append([5 + i for i in range(nt)][::-1])                 # just above the free bits
+            placements.append([0] + [nq - 1 - i for i in range(nt - 1)])        # one low target, the rest on top
+        for targets in placements:
+            amps = cases.random_state(rng, nq)
+            gate = cases.random_matrix(rng, 1 << nt) / (1 << nt) ** 0.5
+            st = dfsa.DeviceState("sv", nq)
+            st.set_amps(amps)
+            st.sv_manyTargGate(targets, gate)
+            o, _ = _oracle_run("sv", nq, 1, amps, ("sv_manyTargGate", targets, gate))
+            compare.assert_close(st.get_amps(), o.get_amps(), what="manyTargGate nq=%d targets=%r" % (nq, targets))
+            st.close()
+
+
 def test_all_z_pauli_string_applies_the_operator(dfsa):
     """Documented divergence: the reference silently skips X/Y-free Pauli strings; this build applies them."""
     rng = np.random.default_rng(9)
