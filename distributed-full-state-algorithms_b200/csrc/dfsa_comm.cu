@@ -555,24 +555,22 @@ extern "C" int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double
 
 extern "C" int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank) {
     DFSA_TRY(dfsaEnsureDevice());
-    DFSA_REQUIRE(s && qb1 + 1 < s->logNumAmps + 1 && qb1 < s->logNumAmps, "qb1 must be a suffix qubit");
+    DFSA_REQUIRE(s && qb1 < s->logNumAmps, "qb1 must be a suffix qubit");
     const uint64_t half = s->numAmps >> 1;
     DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, half, half, pairRank));
-    const uint32_t pos = qb1;
-    DFSA_TRY(dfsa_k_pack(s, &pos, 1, movingBit & 1u, 0));                 // buffer[0..A/2) = the half that leaves
-    if (fusedAvailable()) {
-        DfsaContext& c = dfsaCtx();
-        DFSA_CUDA(cudaStreamSynchronize(c.comm));
-        DFSA_CUDA(cudaStreamSynchronize(c.compute));
-        DFSA_TRY(pairBarrier(pairRank));                                   // both halves are packed
-        double2* remote;
-        DFSA_TRY(peerArray(s, pairRank, DFSA_BUFFER, &remote));
-        DFSA_TRY(dfsaLaunchUnpackFrom(s, qb1, movingBit, remote));         // gather the partner's packed half over NVLink
-        DFSA_CUDA(cudaStreamSynchronize(c.compute));
-        return pairBarrier(pairRank);                                      // the partner is done reading my buffer
+    movingBit &= 1u;
+    if (fusedAvailable())                                                  // one pass: keep my half, read the partner's over NVLink
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedSwap(s, remote, qb1, movingBit ^ 1u); });
+    if (qb1 + 1 == s->logNumAmps) {
+        // top suffix qubit: the moving half is contiguous, no packing (distributed_statevector.hpp:140-157)
+        const uint64_t offset = half * movingBit;
+        DFSA_TRY(transfer(s, DFSA_AMPS, offset, DFSA_BUFFER, 0, half, pairRank, true, true));
+        return dfsa_k_copyFromBuffer(s, offset, 0, half);
     }
+    const uint32_t pos = qb1;
+    DFSA_TRY(dfsa_k_pack(s, &pos, 1, movingBit, 0));                       // buffer[0..A/2) = the half that leaves
     DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, half, half, pairRank, true, true));
-    return dfsa_k_unpack(s, &pos, 1, movingBit & 1u, half);
+    return dfsa_k_unpack(s, &pos, 1, movingBit, half);
 }
 
 extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,

@@ -81,7 +81,7 @@ int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int
 int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1);
 int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
                                 unsigned numY, double2 f, double2 h, bool exact);
-int dfsaLaunchUnpackFrom(dfsa_state* s, unsigned qb, unsigned bitValue, const double2* src);   // amps[insert(k, qb, bitValue)] = src[k], k < A/2
+int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit);   // buffer = shard after swapping suffix qubit qb with this pair's prefix qubit
 int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registry slots are this state's amps / buffer now
 
 // transport hooks implemented in dfsa_comm.cu

@@ -124,6 +124,7 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
 
     // the gate as A-fragments (a[v]: row g + 8(v&1), col q + 4(v>>1))
     double gr[NB][NB][8], gi[NB][NB][8];
+    double gd[8], gs[8];                                           // T == 4 (3M form): G_im - G_re and G_re + G_im
     if constexpr (T >= 4) {
 #pragma unroll
         for (int mb = 0; mb < NB; mb++)
@@ -135,6 +136,10 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
                     gr[mb][kb][v] = e.x;
                     gi[mb][kb][v] = e.y;
                 }
+        if constexpr (T == 4) {
+#pragma unroll
+            for (int v = 0; v < 8; v++) { gd[v] = gi[0][0][v] - gr[0][0][v]; gs[v] = gr[0][0][v] + gi[0][0][v]; }
+        }
     } else {
         // T == 3: real 16x16 matrix R = [[G_re, -G_im], [G_im, G_re]] in gr[0][0]; gi unused
 #pragma unroll
@@ -211,7 +216,24 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
         }
 #pragma unroll 1
         for (unsigned nb = 0; nb < VEC / 8; nb++) {
-            if constexpr (T >= 4) {
+            if constexpr (T == 4) {
+                // 3M complex product: k1 = G_re (X_re + X_im), k2 = (G_im - G_re) X_re, k3 = (G_re + G_im) X_im;
+                // re = k1 - k3, im = k1 + k2 -- three real MMAs per 8 vectors instead of four
+                double k1[4] = {0.0, 0.0, 0.0, 0.0}, k2[4] = {0.0, 0.0, 0.0, 0.0}, k3[4] = {0.0, 0.0, 0.0, 0.0};
+                double xr[4], xi[4], xs[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    const double2 x = X[(q + 4 * v) * S + nb * 8 + g];
+                    xr[v] = x.x; xi[v] = x.y; xs[v] = x.x + x.y;
+                }
+                dmma16816(k1, gr[0][0], xs);
+                dmma16816(k2, gd, xr);
+                dmma16816(k3, gs, xi);
+                __syncwarp();                                       // every lane has read this n-block's columns
+#pragma unroll
+                for (int v = 0; v < 4; v++)
+                    X[(g + 8 * (v >> 1)) * S + nb * 8 + 2 * q + (v & 1)] = make_double2(k1[v] - k3[v], k1[v] + k2[v]);
+            } else if constexpr (T == 5) {
                 double cre[NB][4], cim[NB][4];
 #pragma unroll
                 for (int mb = 0; mb < NB; mb++)
@@ -277,6 +299,118 @@ manyTargDmmaKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
         }
     }
     if constexpr (BULK) bulkWaitRead0();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// t == 5, second form: 3M complex product, gate rows split across a WARP PAIR.
+// The one-warp kernel above needs all of G_re and G_im as A-fragments (128 registers), which caps the SM at 8 warps and
+// rules out a third matrix. Here two warps share a tile and each owns 16 of the 32 gate rows, so the three matrices of the
+// 3M product -- G_re, G_im - G_re, G_re + G_im -- cost 96 registers, 12 warps fit, and the tensor pipe does 3 real MMAs
+// where the 4M form does 4 (FP64 bound 192 instead of 256 flop per amplitude, about level with the HBM bound):
+//   k1 = G_re (X_re + X_im), k2 = (G_im - G_re) X_re, k3 = (G_re + G_im) X_im;  Y_re = k1 - k3, Y_im = k1 + k2.
+// Per pair: two input slabs (cp.async double buffer; each warp fetches half of the tile) and one output slab, so results
+// never overwrite operands and two named barriers per tile suffice: A = "tile landed, output slab free",
+// B = "output slab complete". Element (lane | h << 5 | j << 6) of a tile, h = warp of the pair: the lane and h parts of
+// its addresses are per-thread registers, the j part is the table in the kernel parameters.
+struct Pair5 {
+    static constexpr unsigned T = 5, D = 32, F = 4, VEC = 16, S = VEC + 2, PAIRS = 6, EPW = D * VEC / 64;   // 8 elements per thread
+    static constexpr unsigned SLAB = D * S, SLAB_BYTES = SLAB * 16u;
+    static constexpr size_t smemBytes = (size_t)PAIRS * 3 * SLAB_BYTES;       // 162 KiB
+};
+struct Pair5Map { uint64_t gByte[Pair5::EPW]; uint32_t sByte[Pair5::EPW]; };
+
+__global__ void __launch_bounds__(64 * Pair5::PAIRS, 1)
+manyTarg5PairKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, const double2* __restrict__ gate, Pair5Map map) {
+    constexpr unsigned T = Pair5::T, D = Pair5::D, F = Pair5::F, S = Pair5::S, VEC = Pair5::VEC, EPW = Pair5::EPW;
+    constexpr unsigned SLAB = Pair5::SLAB, SLAB_BYTES = Pair5::SLAB_BYTES;
+    extern __shared__ double2 smem[];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, pair = warp >> 1, h = warp & 1u;
+    const unsigned g = lane >> 2, q = lane & 3u;
+    double2* in0 = smem + (size_t)pair * (3 * SLAB);
+    double2* out = in0 + 2 * SLAB;
+
+    // this thread's share of every element address: tile bits 0..4 = lane, bit 5 = h
+    uint64_t laneOff = 0;
+    unsigned laneRow = 0, laneN = 0;
+    {
+        const unsigned e = lane | (h << 5);
+#pragma unroll
+        for (unsigned b = 0; b < 6; b++) {
+            const unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
+            laneOff |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < T) laneRow |= bit << role; else laneN |= bit << (role - T);
+        }
+    }
+    char* laneG = reinterpret_cast<char*>(amps) + (laneOff << 4);
+    const unsigned laneS = (laneRow * S + laneN) << 4;
+    const unsigned inS = smemAddr(in0) + laneS, outS = smemAddr(out) + laneS;
+
+    // A-fragments of this warp's 16 gate rows (a[v]: row g + 8(v&1), col q + 4(v>>1)), k-blocks 0 and 1
+    double ar[2][8], ad[2][8], as[2][8];
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const double2 e = gate[(16 * h + g + 8 * (v & 1)) * D + 16 * kb + q + 4 * (v >> 1)];
+            ar[kb][v] = e.x;
+            ad[kb][v] = e.y - e.x;
+            as[kb][v] = e.x + e.y;
+        }
+
+    auto prefetch = [&](uint64_t base, unsigned b) {
+        const char* src = laneG + (base << 4);
+        const unsigned dst = inS + b * SLAB_BYTES;
+#pragma unroll
+        for (unsigned j = 0; j < EPW; j++)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + map.sByte[j]), "l"(src + map.gByte[j]) : "memory");
+        cpAsyncCommit();
+    };
+    auto pairBarrier = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1u) : "memory"); };
+
+    const uint64_t stride = (uint64_t)gridDim.x * Pair5::PAIRS;
+    uint64_t tile = (uint64_t)blockIdx.x * Pair5::PAIRS + pair;
+    uint64_t base = 0, nextBase = insertZeroBitsN<T + F>(tile, tileSpec);
+    if (tile < numTiles) prefetch(nextBase, 0);
+    for (unsigned it = 0; tile < numTiles; it++, tile += stride) {
+        const unsigned cur = it & 1u;
+        const double2* X = in0 + (size_t)cur * SLAB;
+        base = nextBase;
+        nextBase = insertZeroBitsN<T + F>(tile + stride, tileSpec);
+        // the other input slab was last read before barrier B of the previous tile, which this warp has passed
+        if (tile + stride < numTiles) { prefetch(nextBase, cur ^ 1u); cpAsyncWait<1>(); }
+        else cpAsyncWait<0>();
+        pairBarrier();                                              // A: both halves of this tile landed; output slab drained
+#pragma unroll 1
+        for (unsigned nb = 0; nb < VEC / 8; nb++) {
+            double k1[4] = {0.0, 0.0, 0.0, 0.0}, k2[4] = {0.0, 0.0, 0.0, 0.0}, k3[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++) {
+                double xr[4], xi[4], xs[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) {                       // b[v]: k = q + 4v, n = g
+                    const double2 x = X[(16 * kb + q + 4 * v) * S + nb * 8 + g];
+                    xr[v] = x.x; xi[v] = x.y; xs[v] = x.x + x.y;
+                }
+                dmma16816(k1, ar[kb], xs);
+                dmma16816(k2, ad[kb], xr);
+                dmma16816(k3, as[kb], xi);
+            }
+#pragma unroll
+            for (int v = 0; v < 4; v++)                             // c[v]: row g + 8(v>>1), col 2q + (v&1)
+                out[(16 * h + g + 8 * (v >> 1)) * S + nb * 8 + 2 * q + (v & 1)] = make_double2(k1[v] - k3[v], k1[v] + k2[v]);
+        }
+        pairBarrier();                                              // B: all 32 rows of the output slab are written
+        char* dst = laneG + (base << 4);
+#pragma unroll
+        for (unsigned j0 = 0; j0 < EPW; j0 += 4) {
+            double2 v[4];
+#pragma unroll
+            for (unsigned j = 0; j < 4; j++)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[j].x), "=d"(v[j].y) : "r"(outS + map.sByte[j0 + j]) : "memory");
+#pragma unroll
+            for (unsigned j = 0; j < 4; j++) *reinterpret_cast<double2*>(dst + map.gByte[j0 + j]) = v[j];
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -448,6 +582,43 @@ int launchDmmaKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, 
                       : launchDmmaKernelImpl<T, false>(s, numTiles, tileSpec, localPos, devGate, map);
 }
 
+// t == 5, warp-pair 3M kernel (every target placement; full tiles only)
+int launchPair5(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const double2* devGate) {
+    DfsaContext& ctx = dfsaCtx();
+    const unsigned L = s->logNumAmps;
+    BitSpec tileSpec, localPos;
+    DFSA_TRY(buildTile(targets, Pair5::T, L, targMask, Pair5::F, &tileSpec, &localPos));
+    Pair5Map map;                                                    // j part of element (lane | h << 5 | j << 6): tile bits 6..8
+    for (unsigned j = 0; j < Pair5::EPW; j++) {
+        uint64_t off = 0;
+        unsigned row = 0, n = 0;
+        for (unsigned b = 6; b < Pair5::T + Pair5::F; b++) {
+            const unsigned bit = (j >> (b - 6)) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < Pair5::T) row |= bit << role; else n |= bit << (role - Pair5::T);
+        }
+        map.gByte[j] = off << 4;
+        map.sByte[j] = (row * Pair5::S + n) << 4;
+    }
+    static bool configured = false;
+    if (!configured) {
+        DFSA_CUDA(cudaFuncSetAttribute(manyTarg5PairKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Pair5::smemBytes));
+        configured = true;
+    }
+    const uint64_t numTiles = s->numAmps >> (Pair5::T + Pair5::F);
+    const uint64_t blocksNeeded = (numTiles + Pair5::PAIRS - 1) / Pair5::PAIRS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs);
+    manyTarg5PairKernel<<<grid, 64 * Pair5::PAIRS, Pair5::smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, devGate, map);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}
+
+// DFSA_MANYTARG5=warp selects the one-warp-per-tile 4M kernel for t = 5 (kept for comparison runs); default is the pair kernel
+bool usePair5() {
+    const char* e = getenv("DFSA_MANYTARG5");
+    return !(e && strcmp(e, "warp") == 0);
+}
+
 }  // namespace
 
 extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
@@ -504,7 +675,7 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         switch (t) {
             case 3:  return launchDmmaKernel<3>(s, targets, targMask, dev);
             case 4:  return launchDmmaKernel<4>(s, targets, targMask, dev);
-            default: return launchDmmaKernel<5>(s, targets, targMask, dev);
+            default: return usePair5() ? launchPair5(s, targets, targMask, dev) : launchDmmaKernel<5>(s, targets, targMask, dev);
         }
     }
 

@@ -298,12 +298,22 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
 }
 
 // unpack half a shard from an arbitrary (possibly peer-mapped) source: amps[insert(k, qb, bitValue)] = src[k]
-int dfsaLaunchUnpackFrom(dfsa_state* s, unsigned qb, unsigned bitValue, const double2* src) {
-    double2* amps = s->arr[DFSA_AMPS];
-    const uint64_t fixed = (uint64_t)(bitValue & 1u) << qb;
-    auto ld = [=] __device__(uint64_t k) { return Amp1{src[k]}; };
-    auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(k, qb) | fixed] = v.a; };
-    return launchStream<2, Amp1>(s->numAmps >> 1, ld, st);
+// Suffix<->prefix qubit swap (distributed_statevector.hpp:140-186) as ONE out-of-place pass over peer memory:
+//   buffer[j] = amps[j]                     where bit qb of j equals this rank's bit of the prefix qubit (stays)
+//   buffer[j] = partner_amps[j ^ (1 << qb)] otherwise (the partner's moving half, read over NVLink)
+// then the caller swaps amps <-> buffer. No pack pass, no staging copy; item k touches amps[i], remote[i] with
+// i = k with myBit inserted at qb. Pure moves: bit-exact.
+int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit) {
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    const uint64_t bit = 1ULL << qb, fixed = (uint64_t)(myBit & 1u) << qb;
+    auto ld = [=] __device__(uint64_t k) { const uint64_t i = insertZeroBit(k, qb) | fixed; return Amp2{amps[i], remote[i]}; };
+    auto st = [=] __device__(uint64_t k, const Amp2& v) {
+        const uint64_t i = insertZeroBit(k, qb) | fixed;
+        out[i] = v.a0;
+        out[i ^ bit] = v.a1;
+    };
+    return launchStream<1, Amp2>(s->numAmps >> 1, ld, st);
 }
 
 // K9: distributed_statevector.hpp:133-135, 152-156

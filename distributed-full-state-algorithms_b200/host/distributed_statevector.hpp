@@ -144,31 +144,31 @@ static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, N
             comm_exchangeArrays(psi.amps, psi.buffer, plan.pairRank);
             DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, 0, 0, psi.numAmpsPerNode));      // whole shard: becomes a pointer swap
             return;
-        case dfsa_detail::ExchangePlan::HalfContiguous: {
-            // qb1 is the top suffix qubit: the moving half is contiguous, no packing
-            const Index offset = plan.numAmps * plan.bit;
-            comm_exchangeArrays(psi.amps, offset, psi.buffer, 0, plan.numAmps, plan.pairRank);
-            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, offset, 0, plan.numAmps));
-            return;
-        }
         default:
-            // pack the moving half, trade it with the partner, unpack into the same positions (reference :160-186)
+            // one suffix, one prefix qubit (reference :140-186): the half whose qb1 bit differs from this rank's qb2 bit
+            // trades places with the partner's. Fused over peer memory into a single pass where the ranks share a node;
+            // otherwise contiguous exchange (qb1 top suffix qubit) or pack / exchange / unpack, as the reference does.
             DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, qb1, plan.bit, int(plan.pairRank)));
             return;
     }
 }
 
-// relocation plan of manyTargGate: each prefix target (caller order) takes the lowest still-free suffix qubit
+// Relocation plan of manyTargGate: every prefix target (caller order) is swapped onto a free suffix qubit for the
+// duration of the gate (reference :193-210). The reference takes the LOWEST free suffix qubits; this build takes the
+// HIGHEST ones: the moving half of each swap is then made of long contiguous runs (whole half-shards for the top
+// qubit), so the peer reads over NVLink are fully coalesced, and the relocated targets sit above the tile's free bits,
+// which is the placement the tensor-core kernel's bulk row copies want. The relocation is undone after the gate and the
+// gate's arithmetic does not depend on where its bits live, so the result is identical to the reference's plan.
 static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const NatArray& targets) {
     const Index targetMask = getBitMask(targets);
-    Nat nextFree = 0;
-    auto advance = [&]() { while (getBit(targetMask, nextFree)) nextFree++; };
+    int nextFree = int(logNumAmpsPerNode) - 1;
+    auto advance = [&]() { while (nextFree >= 0 && getBit(targetMask, Nat(nextFree))) nextFree--; };
     advance();
     NatArray placed;
     placed.reserve(targets.size());
     for (Nat t : targets) {
         if (t < logNumAmpsPerNode) placed.push_back(t);
-        else { placed.push_back(nextFree++); advance(); }
+        else { assert(nextFree >= 0); placed.push_back(Nat(nextFree--)); advance(); }
     }
     return placed;
 }

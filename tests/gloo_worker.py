@@ -63,7 +63,15 @@ def main():
             t, n = u32(op[1])
             placed = (C.c_uint * n)()
             host.dfsa_host_plan_manyTarg(L, t, n, placed)
-            assert list(placed) == capi.plan_manyTarg(L, op[1]), "manyTarg relocation plan differs from the oracle's"
+            # the plan moves exactly the targets the reference's plan moves (the prefix ones) onto distinct free suffix
+            # qubits; WHICH free qubits is this build's choice (highest, the reference takes the lowest -- same result)
+            ref_plan = capi.plan_manyTarg(L, op[1])
+            placed = list(placed)
+            assert len(set(placed)) == len(placed) and all(q < L for q in placed), placed
+            for tq, mine, theirs in zip(op[1], placed, ref_plan):
+                assert (mine == tq) == (theirs == tq) and (mine == tq or (tq >= L and mine not in op[1])), (op[1], placed, ref_plan)
+            free = [q for q in range(L - 1, -1, -1) if q not in op[1]]
+            assert [m for tq, m in zip(op[1], placed) if m != tq] == free[: sum(1 for tq in op[1] if tq >= L)]
             # every relocation swap is itself a planned exchange
             for a, b in zip(placed, op[1]):
                 if a != b:
