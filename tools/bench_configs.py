@@ -47,7 +47,9 @@ def op_cost(op, kind, nq, k):
 
     def many_targ(targets):
         npre = sum(1 for t in targets if t >= L)
-        return 32 * A + 2 * npre * swap[0], 2 * npre * swap[1], 8.0 * (1 << len(targets)) * A
+        # FP64 work counted in the cheapest known form of the complex product (3M: three real multiply-adds per complex
+        # one, 6 * 2^t flop per amplitude) -- the count the t = 4, 5 tensor-core kernels issue; the 4M form is 8 * 2^t
+        return 32 * A + 2 * npre * swap[0], 2 * npre * swap[1], 6.0 * (1 << len(targets)) * A
 
     if name == "sv_manyTargGate":
         return many_targ(op[1])
