@@ -414,6 +414,173 @@ manyTarg5PairKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// t == 5, third form: the pair kernel's arithmetic with the memory traffic moved to dedicated MOVER warps.
+// ncu on the pair kernel: tensor pipe 70 % active; the three warps of a scheduler share the pipe fairly, so they drift
+// into lock-step -- all in their DMMA phase together, then all in their load/store phase together with the pipe idle.
+// Here 8 compute warps (4 pairs, gate rows split as above) run nothing but LDS -> DMMA -> STS, and 4 mover warps (one
+// per pair, one per scheduler) do every cp.async, shared-memory drain and global store. Per pair: NIN input slabs
+// and two output slabs, handed over through mbarriers in shared memory:
+//   full[s]    mover -> compute: tile landed in input slab s (cp.async.mbarrier.arrive.noinc of the 32 mover lanes)
+//   done[o]    compute -> mover: output slab o holds the results of a tile and its input slab is free again
+//   drained[o] mover -> compute: output slab o has been read out, it may be overwritten
+// Tile i of a pair uses input slab i % NIN and output slab i % 2; the mover loads tile i + NIN as soon as tile i is
+// done, i.e. NIN - 1 tile-times ahead of its use.
+//
+// Slab layout: X[row][col], 16 columns of 16 bytes per row, NO padding; instead col = n ^ sw(row) with
+// sw(row) = XOR of c[i] over the set bits i of row. c[0] = 5 and c[1] = 6 make the B-fragment reads (rows q + const,
+// columns g + const) and the result writes (rows g + const, columns 2q + const) bank-conflict free; c[2..4] are chosen
+// per launch so that the mover's scatter is conflict free too: its lanes follow ADDRESS order (coalesced global access),
+// and which of the low address bits are gate rows depends on the targets (ncu, low targets, padded layout: 2.6x the
+// L2 read sectors and 1.6x the shared wavefronts of the high-target case, all replays of conflicting cp.async).
+// Slabs are 8 KiB and 8 KiB-aligned, and row / column fields of an offset never overlap, so every address is
+// slab ^ (thread part) ^ (instruction part): one LOP3.
+struct Spec5 {
+    static constexpr unsigned T = 5, D = 32, F = 4, VEC = 16, PAIRS = 4, NOUT = 2;
+    static constexpr unsigned SLAB_BYTES = D * VEC * 16u;                       // 8 KiB
+    static constexpr unsigned THREADS = 32 * (2 * PAIRS + PAIRS);              // 8 compute warps + 4 mover warps
+    static constexpr size_t smemBytes(unsigned nin) { return (size_t)PAIRS * (nin + NOUT) * SLAB_BYTES + SLAB_BYTES; }   // + alignment slack
+};
+struct Spec5Swz { unsigned c[5]; unsigned viaL1; };   // viaL1: cp.async.ca instead of .cg (see launchSpec5)
+
+__host__ __device__ __forceinline__ unsigned spec5Sw(unsigned row, const Spec5Swz& z) {
+    unsigned v = 0;
+#pragma unroll
+    for (unsigned i = 0; i < 5; i++) v ^= ((row >> i) & 1u) ? z.c[i] : 0u;
+    return v;
+}
+// byte offset of (row, n) inside a slab
+__host__ __device__ __forceinline__ unsigned spec5Offset(unsigned row, unsigned n, const Spec5Swz& z) {
+    return (row << 8) | ((n ^ spec5Sw(row, z)) << 4);
+}
+
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void cpAsyncArriveNoinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+
+template <unsigned NIN, bool UNROLL_NB>
+__global__ void __launch_bounds__(Spec5::THREADS, 1)
+manyTarg5SpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, const double2* __restrict__ gate, TileMap<5> map, Spec5Swz swz) {
+    constexpr unsigned T = Spec5::T, D = Spec5::D, F = Spec5::F, VEC = Spec5::VEC, PAIRS = Spec5::PAIRS;
+    constexpr unsigned SLAB_BYTES = Spec5::SLAB_BYTES, NOUT = Spec5::NOUT;
+    extern __shared__ double2 smem[];
+    __shared__ uint64_t full[PAIRS][NIN], done[PAIRS][NOUT], drained[PAIRS][NOUT];
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const bool mover = warp >= 2 * PAIRS;
+    const unsigned pair = mover ? warp - 2 * PAIRS : warp >> 1, h = warp & 1u;
+    // shared-window addresses of this pair's slabs (8 KiB-aligned)
+    const unsigned slab0 = ((smemAddr(smem) + SLAB_BYTES - 1u) & ~(SLAB_BYTES - 1u)) + pair * ((NIN + NOUT) * SLAB_BYTES);
+    const unsigned in0 = slab0, out0 = slab0 + NIN * SLAB_BYTES;
+
+    if (threadIdx.x < PAIRS) {
+        for (unsigned s = 0; s < NIN; s++) mbarInit(&full[threadIdx.x][s], 32);       // the mover's 32 lanes
+        for (unsigned o = 0; o < NOUT; o++) { mbarInit(&done[threadIdx.x][o], 2); mbarInit(&drained[threadIdx.x][o], 1); }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint64_t stride = (uint64_t)gridDim.x * PAIRS;
+    const uint64_t tile0 = (uint64_t)blockIdx.x * PAIRS + pair;
+    const unsigned numMine = tile0 < numTiles ? (unsigned)((numTiles - tile0 + stride - 1) / stride) : 0u;
+
+    if (mover) {
+        // element (lane | i << 5), i < 16: lane part in registers, i part = map (constant bank); slab offsets combine by XOR
+        uint64_t laneOff = 0;
+        unsigned laneRow = 0, laneN = 0;
+#pragma unroll
+        for (unsigned b = 0; b < 5; b++) {
+            const unsigned bit = (lane >> b) & 1u, role = localPos.pos[b];
+            laneOff |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < T) laneRow |= bit << role; else laneN |= bit << (role - T);
+        }
+        char* laneG = reinterpret_cast<char*>(amps) + (laneOff << 4);
+        const unsigned laneS = spec5Offset(laneRow, laneN, swz);
+        auto load = [&](unsigned i) {                                  // tile i of this pair -> input slab i % NIN
+            const char* src = laneG + (insertZeroBitsN<T + F>(tile0 + (uint64_t)i * stride, tileSpec) << 4);
+            const unsigned s = i % NIN, dst = (in0 + s * SLAB_BYTES) ^ laneS;
+            if (swz.viaL1) {
+#pragma unroll
+                for (unsigned e = 0; e < 16; e++)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst ^ map.sByte[e]), "l"(src + map.gByte[e]) : "memory");
+            } else {
+#pragma unroll
+                for (unsigned e = 0; e < 16; e++)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst ^ map.sByte[e]), "l"(src + map.gByte[e]) : "memory");
+            }
+            cpAsyncArriveNoinc(&full[pair][s]);
+        };
+        for (unsigned i = 0; i < NIN && i < numMine; i++) load(i);
+        for (unsigned i = 0; i < numMine; i++) {
+            const unsigned o = i % NOUT;
+            mbarWait(&done[pair][o], (i / NOUT) & 1u);
+            char* dst = laneG + (insertZeroBitsN<T + F>(tile0 + (uint64_t)i * stride, tileSpec) << 4);
+            const unsigned src = (out0 + o * SLAB_BYTES) ^ laneS;
+#pragma unroll
+            for (unsigned e0 = 0; e0 < 16; e0 += 8) {
+                double2 v[8];
+#pragma unroll
+                for (unsigned e = 0; e < 8; e++)
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[e].x), "=d"(v[e].y) : "r"(src ^ map.sByte[e0 + e]) : "memory");
+#pragma unroll
+                for (unsigned e = 0; e < 8; e++) *reinterpret_cast<double2*>(dst + map.gByte[e0 + e]) = v[e];
+            }
+            __syncwarp();                                               // every lane holds its share of the slab in registers
+            if (lane == 0) mbarArrive(&drained[pair][o]);
+            if (i + NIN < numMine) load(i + NIN);                       // input slab i % NIN was released by done
+        }
+        return;
+    }
+
+    // ---- compute warps: A-fragments of this warp's 16 gate rows (3M form), then LDS -> DMMA -> STS per tile
+    const unsigned g = lane >> 2, q = lane & 3u;
+    double ar[2][8], ad[2][8], as[2][8];
+#pragma unroll
+    for (int kb = 0; kb < 2; kb++)
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const double2 e = gate[(16 * h + g + 8 * (v & 1)) * D + 16 * kb + q + 4 * (v >> 1)];
+            ar[kb][v] = e.x;
+            ad[kb][v] = e.y - e.x;
+            as[kb][v] = e.x + e.y;
+        }
+    // thread parts of the operand (row q, column g) and result (row 16h + g, column 2q) offsets
+    const unsigned laneB = spec5Offset(q, g, swz), laneC = spec5Offset(16 * h + g, 2 * q, swz);
+    for (unsigned i = 0; i < numMine; i++) {
+        const unsigned s = i % NIN, o = i % NOUT;
+        const unsigned xB = (in0 + s * SLAB_BYTES) ^ laneB, yC = (out0 + o * SLAB_BYTES) ^ laneC;
+        mbarWait(&full[pair][s], (i / NIN) & 1u);
+        if (i >= NOUT) mbarWait(&drained[pair][o], ((i / NOUT) - 1u) & 1u);
+#pragma unroll(UNROLL_NB ? 2 : 1)
+        for (unsigned nb = 0; nb < VEC / 8; nb++) {
+            double k1[4] = {0.0, 0.0, 0.0, 0.0}, k2[4] = {0.0, 0.0, 0.0, 0.0}, k3[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (unsigned kb = 0; kb < 2; kb++) {
+                double xr[4], xi[4], xs[4];
+#pragma unroll
+                for (unsigned v = 0; v < 4; v++) {                      // b[v]: k = q + 4v (row 16kb + q + 4v), n = nb*8 + g
+                    const unsigned u = spec5Offset(16 * kb + 4 * v, nb * 8, swz);       // warp-uniform instruction part
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(xr[v]), "=d"(xi[v]) : "r"(xB ^ u) : "memory");
+                    xs[v] = xr[v] + xi[v];
+                }
+                // the product that needs the DADD results goes last: the adds retire behind the other two products' DMMAs
+                dmma16816(k2, ad[kb], xr);
+                dmma16816(k3, as[kb], xi);
+                dmma16816(k1, ar[kb], xs);
+            }
+#pragma unroll
+            for (unsigned v = 0; v < 4; v++) {                          // c[v]: row 16h + g + 8(v>>1), column nb*8 + 2q + (v&1)
+                const unsigned u = spec5Offset(8 * (v >> 1), nb * 8 + (v & 1), swz);
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(yC ^ u), "d"(k1[v] - k3[v]), "d"(k1[v] + k2[v]) : "memory");
+            }
+        }
+        __syncwarp();                                                   // all of this warp's reads and writes of the slabs are done
+        if (lane == 0) mbarArrive(&done[pair][o]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // t == 6: 64 KiB of gate does not fit constant memory; block-wide tile with the gate transposed in shared memory,
 // thread = (8 consecutive rows, one lane).
 template <int R>
@@ -536,6 +703,23 @@ int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask
     return DFSA_OK;
 }
 
+// i part of element (lane | i << 5): tile bits 5.. of the element index
+template <int T>
+void fillTileMap(const BitSpec& tileSpec, const BitSpec& localPos, TileMap<T>* map) {
+    constexpr unsigned F = DmmaGeom<T>::F, S = DmmaGeom<T>::S;
+    for (unsigned i = 0; i < DmmaGeom<T>::EPL; i++) {
+        uint64_t off = 0;
+        unsigned row = 0, n = 0;
+        for (unsigned b = 5; b < T + F; b++) {
+            const unsigned bit = (i >> (b - 5)) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < (unsigned)T) row |= bit << role; else n |= bit << (role - T);
+        }
+        map->gByte[i] = off << 4;
+        map->sByte[i] = (row * S + n) << 4;
+    }
+}
+
 template <int T, bool BULK>
 int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, const double2* devGate, const TileMap<T>& map) {
     DfsaContext& ctx = dfsaCtx();
@@ -557,23 +741,12 @@ int launchDmmaKernelImpl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSp
 // full tiles only (f == DmmaGeom<T>::F free bits): shards too small for one are the caller's business
 template <int T>
 int launchDmmaKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const double2* devGate) {
-    constexpr unsigned F = DmmaGeom<T>::F, S = DmmaGeom<T>::S;
+    constexpr unsigned F = DmmaGeom<T>::F;
     const unsigned L = s->logNumAmps;
     BitSpec tileSpec, localPos;
     DFSA_TRY(buildTile(targets, T, L, targMask, F, &tileSpec, &localPos));
-    // i part of element (lane | i << 5): tile bits 5.. of the element index
     TileMap<T> map;
-    for (unsigned i = 0; i < DmmaGeom<T>::EPL; i++) {
-        uint64_t off = 0;
-        unsigned row = 0, n = 0;
-        for (unsigned b = 5; b < T + F; b++) {
-            const unsigned bit = (i >> (b - 5)) & 1u, role = localPos.pos[b];
-            off |= (uint64_t)bit << tileSpec.pos[b];
-            if (role < (unsigned)T) row |= bit << role; else n |= bit << (role - T);
-        }
-        map.gByte[i] = off << 4;
-        map.sByte[i] = (row * S + n) << 4;
-    }
+    fillTileMap<T>(tileSpec, localPos, &map);
     // bulk rows need the VEC vectors of a tile row to be one contiguous run: free bits = address bits 0..F-1
     bool contiguous = !getenv("DFSA_MANYTARG_NO_BULK");
     for (unsigned b = 0; b < F && contiguous; b++) contiguous = (tileSpec.pos[b] == b) && (localPos.pos[b] >= (unsigned)T);
@@ -613,10 +786,84 @@ int launchPair5(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const
     return DFSA_OK;
 }
 
+// Swizzle constants of the warp-specialised kernel: c[0], c[1] are fixed by the fragment access patterns; c[2..4] are
+// picked so that the column fields of the eight lanes of a quarter-warp of the mover (address bits = tile bits 0..2,
+// each either column bit n_j -> value 1 << j, or gate-row bit i -> value c[i]) are linearly independent over GF(2),
+// i.e. the eight 16-byte accesses of a phase fall into eight different bank groups.
+void chooseSpec5Swizzle(const BitSpec& localPos, Spec5Swz* z) {
+    z->c[0] = 5; z->c[1] = 6; z->c[2] = z->c[3] = z->c[4] = 0;
+    bool inSpan[8] = {true, false, false, false, false, false, false, false};
+    auto add = [&](unsigned v) { bool next[8]; for (unsigned x = 0; x < 8; x++) next[x] = inSpan[x] || inSpan[x ^ v]; for (unsigned x = 0; x < 8; x++) inSpan[x] = next[x]; };
+    unsigned pending[3], numPending = 0;
+    for (unsigned b = 0; b < 3; b++) {
+        const unsigned role = localPos.pos[b];
+        if (role >= Spec5::T) { if (role - Spec5::T < 3) add(1u << (role - Spec5::T)); }   // column bit 3 does not select a bank group
+        else if (role < 2) add(z->c[role]);
+        else pending[numPending++] = role;
+    }
+    for (unsigned k = 0; k < numPending; k++)
+        for (unsigned v = 1; v < 8; v++)
+            if (!inSpan[v]) { z->c[pending[k]] = v; add(v); break; }
+    for (unsigned i = 2, v = 1; i < 5; i++)                          // rows outside the quarter-warp bits: any value
+        if (z->c[i] == 0) { z->c[i] = v; v = (v % 7) + 1; }
+}
+
+// t == 5, warp-specialised kernel (mover warps + compute warp pairs); same tile geometry as the one-warp kernel
+template <unsigned NIN, bool UNROLL_NB>
+int launchSpec5Impl(dfsa_state* s, uint64_t numTiles, const BitSpec& tileSpec, const BitSpec& localPos, const double2* devGate, const TileMap<5>& map, const Spec5Swz& swz) {
+    DfsaContext& ctx = dfsaCtx();
+    static bool configured = false;
+    if (!configured) {
+        DFSA_CUDA(cudaFuncSetAttribute(manyTarg5SpecKernel<NIN, UNROLL_NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Spec5::smemBytes(NIN)));
+        configured = true;
+    }
+    const uint64_t blocksNeeded = (numTiles + Spec5::PAIRS - 1) / Spec5::PAIRS;
+    const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs);
+    manyTarg5SpecKernel<NIN, UNROLL_NB><<<grid, Spec5::THREADS, Spec5::smemBytes(NIN), ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, devGate, map, swz);
+    DFSA_LAUNCH_CHECK();
+    return DFSA_OK;
+}
+
+int launchSpec5(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const double2* devGate) {
+    const unsigned L = s->logNumAmps;
+    BitSpec tileSpec, localPos;
+    DFSA_TRY(buildTile(targets, Spec5::T, L, targMask, Spec5::F, &tileSpec, &localPos));
+    Spec5Swz swz;
+    chooseSpec5Swizzle(localPos, &swz);
+    // When address bit 0 is a gate-row bit, the two amplitudes of a 32-byte sector go to different slab rows and the
+    // L1-bypassing cp.async.cg fetches the sector from L2 once per half (ncu: 2.5x the L2 read sectors, low targets);
+    // routed through L1 (.ca) the second half hits. Data is read once per kernel, so L1 residency costs nothing else.
+    swz.viaL1 = (localPos.pos[0] < Spec5::T) ? 1u : 0u;
+    if (const char* e = getenv("DFSA_SPEC5_CA")) swz.viaL1 = (unsigned)atoi(e);
+    // i part of element (lane | i << 5): shard byte offset and slab offset (row and swizzled column fields)
+    TileMap<5> map;
+    for (unsigned i = 0; i < 16; i++) {
+        uint64_t off = 0;
+        unsigned row = 0, n = 0;
+        for (unsigned b = 5; b < Spec5::T + Spec5::F; b++) {
+            const unsigned bit = (i >> (b - 5)) & 1u, role = localPos.pos[b];
+            off |= (uint64_t)bit << tileSpec.pos[b];
+            if (role < Spec5::T) row |= bit << role; else n |= bit << (role - Spec5::T);
+        }
+        map.gByte[i] = off << 4;
+        map.sByte[i] = spec5Offset(row, n, swz);
+    }
+    const uint64_t numTiles = s->numAmps >> (Spec5::T + Spec5::F);
+    const char* e = getenv("DFSA_SPEC5_NIN");
+    const char* u = getenv("DFSA_SPEC5_UNROLL");
+    const bool nin3 = e && atoi(e) == 3, unroll = !(u && atoi(u) == 0);
+    if (nin3) return unroll ? launchSpec5Impl<3, true>(s, numTiles, tileSpec, localPos, devGate, map, swz)
+                            : launchSpec5Impl<3, false>(s, numTiles, tileSpec, localPos, devGate, map, swz);
+    return unroll ? launchSpec5Impl<4, true>(s, numTiles, tileSpec, localPos, devGate, map, swz)
+                  : launchSpec5Impl<4, false>(s, numTiles, tileSpec, localPos, devGate, map, swz);
+}
+
 // DFSA_MANYTARG5=warp selects the one-warp-per-tile 4M kernel for t = 5 (kept for comparison runs); default is the pair kernel
-bool usePair5() {
+int variant5() {                                                     // 0 = pair (default), 1 = warp, 2 = spec
     const char* e = getenv("DFSA_MANYTARG5");
-    return !(e && strcmp(e, "warp") == 0);
+    if (e && strcmp(e, "warp") == 0) return 1;
+    if (e && strcmp(e, "spec") == 0) return 2;
+    return 0;
 }
 
 }  // namespace
@@ -675,7 +922,12 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         switch (t) {
             case 3:  return launchDmmaKernel<3>(s, targets, targMask, dev);
             case 4:  return launchDmmaKernel<4>(s, targets, targMask, dev);
-            default: return usePair5() ? launchPair5(s, targets, targMask, dev) : launchDmmaKernel<5>(s, targets, targMask, dev);
+            default:
+                switch (variant5()) {
+                    case 1:  return launchDmmaKernel<5>(s, targets, targMask, dev);
+                    case 2:  return launchSpec5(s, targets, targMask, dev);
+                    default: return launchPair5(s, targets, targMask, dev);
+                }
         }
     }
 

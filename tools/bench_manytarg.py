@@ -48,18 +48,22 @@ def main():
                           "TFLOPs_3M_count": round(flops_per_amp_issued * A / t / 1e9, 2),
                           "bound_ms": round(max(hbm_ms, fp_ms), 3), "roofline_frac": round(max(hbm_ms, fp_ms) / t, 3)}), flush=True)
 
-    for nt in (2, 3, 4, 5, 6):
+    only = [int(x) for x in os.environ.get("MT_ONLY", "2,3,4,5,6").split(",")]
+    for nt in only:
         d = 1 << nt
         g, _ = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
         placements = {"low": list(range(nt)), "top": list(range(nq - nt, nq)), "mid": [6 + 2 * i for i in range(nt)][::-1],
                       "mixed": [3, 0, 17, nq - 1, 9, 12][:nt]}
         for pname, targs in placements.items():
-            variants = [("pair3m", None), ("warp4m", "warp")] if nt == 5 else [("", None)]
+            variants = [("", None)]
+            if nt == 5:
+                variants = [("spec", {"DFSA_MANYTARG5": "spec"}), ("spec-nounroll", {"DFSA_MANYTARG5": "spec", "DFSA_SPEC5_UNROLL": "0"}),
+                            ("spec-cg", {"DFSA_MANYTARG5": "spec", "DFSA_SPEC5_CA": "0"}), ("spec-ca", {"DFSA_MANYTARG5": "spec", "DFSA_SPEC5_CA": "1"}),
+                            ("pair", {"DFSA_MANYTARG5": "pair"}), ("warp4m", {"DFSA_MANYTARG5": "warp"})]
             for vname, env in variants:
-                if env:
-                    os.environ["DFSA_MANYTARG5"] = env
-                else:
-                    os.environ.pop("DFSA_MANYTARG5", None)
+                for k in ("DFSA_MANYTARG5", "DFSA_SPEC5_NIN", "DFSA_SPEC5_UNROLL", "DFSA_SPEC5_CA"):
+                    os.environ.pop(k, None)
+                os.environ.update(env or {})
                 # the roofline counts FP64 work in the 3M form (6 * 2^t flop per amplitude) whichever form the kernel issues
                 timeit("manyTarg t=%d %s %s" % (nt, pname, vname), lambda: st.sv_manyTargGate(targs, g), 8 * d, 6 * d)
     os.environ.pop("DFSA_MANYTARG5", None)
