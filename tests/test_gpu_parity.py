@@ -116,19 +116,12 @@ def test_every_target_position_one_and_ctrl_gate(dfsa):
     compare.assert_close(st.get_amps(), o.get_amps(), tol=1e-11, what="target sweep")   # 28 chained non-unitary gates
 
 
-@pytest.mark.parametrize("nt,variant", [(1, ""), (2, ""), (3, ""), (3, "nobulk"), (4, ""), (4, "nobulk"), (5, ""), (5, "warp"), (5, "warp-nobulk"), (5, "spec"), (5, "spec-nin3"), (6, ""), (7, "")])
-def test_many_targ_gate_every_kernel_variant(dfsa, monkeypatch, nt, variant):
-    """manyTargGate (local_statevector.hpp:72-99) picks its kernel by target count and placement: tensor-core tiles with
-    bulk row copies (targets above the tile's free bits), the gather form (targets among the low bits), the generic kernel
-    on shards too small for a tile. Every variant against the oracle, targets in caller order (not sorted)."""
-    if "warp" in variant:
-        monkeypatch.setenv("DFSA_MANYTARG5", "warp")          # the one-warp-per-tile 4M kernel instead of the warp-pair 3M kernel
-    if "spec" in variant:
-        monkeypatch.setenv("DFSA_MANYTARG5", "spec")          # the warp-specialised (mover + compute warps) 3M kernel
-    if "nin3" in variant:
-        monkeypatch.setenv("DFSA_SPEC5_NIN", "3")             # three input slabs per pair instead of four
-    if "nobulk" in variant:
-        monkeypatch.setenv("DFSA_MANYTARG_NO_BULK", "1")      # gather form even where bulk row copies apply
+@pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 6, 7])
+def test_many_targ_gate_every_kernel_and_placement(dfsa, nt):
+    """manyTargGate (local_statevector.hpp:72-99) picks its kernel by target count (pair stream, quad stream, tensor-core
+    tiles for t = 3..5, DFMA tile for t = 6, generic above and on shards smaller than a tile), and the tensor-core kernel's
+    tile layout and shared-memory swizzle depend on where the targets sit. Every kernel, targets low / high / scattered /
+    just above the free bits, in caller order (not sorted), against the oracle."""
     rng = np.random.default_rng(100 + nt)
     for nq in (nt, nt + 2, 13, 16):
         if nq < nt:

@@ -31,14 +31,14 @@ for step in $STEPS; do
       tail -n 3 $OUT/${TAG}_ncu.log ;;
     mt5)
       timeout 120 python -m pytest tests -m gpu -q -k many_targ > $OUT/${TAG}_pytest_mt.log 2>&1; tail -n 4 $OUT/${TAG}_pytest_mt.log
-      MT_ONLY=5 timeout 300 python tools/bench_manytarg.py 30 > $OUT/${TAG}_manytarg5.jsonl 2> $OUT/${TAG}_manytarg5.err
-      cat $OUT/${TAG}_manytarg5.jsonl; tail -n 5 $OUT/${TAG}_manytarg5.err ;;
+      MT_ONLY=${MT_ONLY:-3,4,5} timeout 300 python tools/bench_manytarg.py 30 > $OUT/${TAG}_manytarg.jsonl 2> $OUT/${TAG}_manytarg.err
+      cat $OUT/${TAG}_manytarg.jsonl; tail -n 5 $OUT/${TAG}_manytarg.err ;;
     ncu5)
-      for v in ${NCU5_VARIANTS:-spec}; do for pl in ${NCU5_PLACEMENTS:-mid low}; do
-        DFSA_MANYTARG5=$v timeout 300 ncu --set full --clock-control none --import-source on -k regex:manyTarg -c 2 -f -o $OUT/${TAG}_mt5_${v}_${pl} \
-            python tools/prof_manytarg.py 26 5 $pl > $OUT/${TAG}_ncu5_${v}_${pl}.log 2>&1
-        ncu -i $OUT/${TAG}_mt5_${v}_${pl}.ncu-rep --page raw --csv > $OUT/${TAG}_mt5_${v}_${pl}_raw.csv 2>> $OUT/${TAG}_ncu5_${v}_${pl}.log
-        tail -n 2 $OUT/${TAG}_ncu5_${v}_${pl}.log
+      for t in ${NCU_T:-5}; do for pl in ${NCU_PLACEMENTS:-mid low}; do
+        timeout 300 ncu --set full --clock-control none --import-source on -k regex:manyTarg -c 2 -f -o $OUT/${TAG}_mt${t}_${pl} \
+            python tools/prof_manytarg.py 26 $t $pl > $OUT/${TAG}_ncu_mt${t}_${pl}.log 2>&1
+        ncu -i $OUT/${TAG}_mt${t}_${pl}.ncu-rep --page raw --csv > $OUT/${TAG}_mt${t}_${pl}_raw.csv 2>> $OUT/${TAG}_ncu_mt${t}_${pl}.log
+        tail -n 2 $OUT/${TAG}_ncu_mt${t}_${pl}.log
       done; done ;;
     launches)
       timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_n1_30q.csv \

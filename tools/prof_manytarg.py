@@ -1,6 +1,6 @@
 """ncu target: manyTargGate launches on one state vector.
 Usage: python tools/prof_manytarg.py [numQubits] [t,t,...] [placement: random|low|mid|top|mixed]
-(the t = 5 kernel form follows DFSA_MANYTARG5 = pair | spec | warp)."""
+"""
 import importlib, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
