@@ -95,8 +95,11 @@ def comm_synch():
 
 
 def _u32(xs):
-    xs = [int(x) for x in np.asarray(xs).reshape(-1)]
-    return (C.c_uint * max(len(xs), 1))(*xs), len(xs)
+    a = np.ascontiguousarray(np.asarray(xs).reshape(-1), dtype=np.uint32)
+    n = int(a.size)
+    if n == 0:
+        a = np.zeros(1, dtype=np.uint32)
+    return a.ctypes.data_as(C.POINTER(C.c_uint)), n        # the pointer object keeps `a` alive
 
 
 def _cplx(a):

@@ -573,6 +573,41 @@ extern "C" int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned mo
     return dfsa_k_unpack(s, &pos, 1, movingBit, half);
 }
 
+// oneQubitDepolarising on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141)
+extern "C" int dfsa_xk_depol1Prefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    const uint64_t half = s ? s->numAmps >> 1 : 0;
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, half, half, pairRank));
+    DFSA_REQUIRE(s->isDensity && qb < s->numQubits && qb >= s->numQubits - s->logNumNodes, "needs a prefix qubit of a density matrix");
+    if (fusedAvailable())
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedDepol1(s, remote, qb, bit, prob); });
+    const uint32_t pos = qb;
+    DFSA_TRY(dfsa_k_pack(s, &pos, 1, bit & 1u, 0));                        // the ket bit == bra bit half (reference :119-127)
+    DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, half, half, pairRank, true, true));
+    return dfsa_k_depol1Combine(s, qb, bit, prob);
+}
+
+// damping on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:284-317): population flows one way, from
+// the rank holding bra bit 1 to the rank holding bra bit 0
+extern "C" int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    const uint64_t half = s ? s->numAmps >> 1 : 0;
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, 0, half, pairRank, false));
+    DFSA_REQUIRE(s->isDensity && qb < s->numQubits && qb >= s->numQubits - s->logNumNodes, "needs a prefix qubit of a density matrix");
+    if (fusedAvailable())
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedDamping(s, remote, qb, bit, prob); });
+    if (bit & 1u) {
+        DFSA_TRY(dfsa_k_dampingPrefix(s, qb, bit, prob, 0));
+        DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, 0, half, pairRank, true, false));
+    }
+    DFSA_TRY(dfsa_k_dampingPrefix(s, qb, bit, prob, 1));
+    if (!(bit & 1u)) {
+        DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, 0, half, pairRank, false, true));
+        DFSA_TRY(dfsa_k_dampingPrefix(s, qb, bit, prob, 2));
+    }
+    return DFSA_OK;     // the reference needs a global barrier here to protect the sender's buffer; stream order does that job
+}
+
 extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
                                             const double f[2], const double g[2], int exact) {
     DFSA_TRY(dfsaEnsureDevice());

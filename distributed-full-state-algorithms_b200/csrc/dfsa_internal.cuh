@@ -82,6 +82,8 @@ int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, dou
 int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
                                 unsigned numY, double2 f, double2 h, bool exact);
 int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit);   // buffer = shard after swapping suffix qubit qb with this pair's prefix qubit
+int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);    // prefix oneQubitDepolarising, buffer = result
+int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);   // prefix damping, buffer = result
 int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registry slots are this state's amps / buffer now
 
 // transport hooks implemented in dfsa_comm.cu

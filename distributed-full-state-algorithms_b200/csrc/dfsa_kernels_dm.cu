@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <vector>
 
+#include <string.h>
 #include "dfsa_stream_kernels.cuh"
 
 namespace {
@@ -164,6 +165,54 @@ extern "C" int dfsa_k_depol1Combine(dfsa_state* s, unsigned qb, unsigned bit, do
         amps[j | same]  = make_double2(fma(c1, v.c.x, c2 * v.a.x), fma(c1, v.c.y, c2 * v.a.y));
     };
     return launchStream<1, Item>(half, ld, st);
+}
+
+// K19 fused with its exchange (distributed_densitymatrix.hpp:119-141 as ONE out-of-place pass over peer memory):
+//   buffer[j | same]  = c2 * amps[j | same] + c1 * partner_amps[j | other]      (same = ket bit == this rank's bra bit)
+//   buffer[j | other] = c3 * amps[j | other]
+// `partner_amps[j | other]` is exactly what the reference packs, sends and receives; the caller swaps amps <-> buffer.
+int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob) {
+    const double c1 = 2 * prob / 3, c2 = 1 - 2 * prob / 3, c3 = 1 - 4 * prob / 3;
+    const uint64_t same = (uint64_t)(bit & 1u) << qb, other = (uint64_t)(!(bit & 1u)) << qb;
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    using Item = Amp3;     // a = mine, b = other half, c = partner's
+    auto ld = [=] __device__(uint64_t k) {
+        uint64_t j = insertZeroBit(k, qb);
+        return Item{amps[j | same], amps[j | other], remote[j | other]};
+    };
+    auto st = [=] __device__(uint64_t k, const Item& v) {
+        uint64_t j = insertZeroBit(k, qb);
+        out[j | other] = cscale(c3, v.b);
+        out[j | same]  = make_double2(fma(c1, v.c.x, c2 * v.a.x), fma(c1, v.c.y, c2 * v.a.y));
+    };
+    return launchStream<1, Item>(s->numAmps >> 1, ld, st);
+}
+
+// K22 fused with its one-way transfer (distributed_densitymatrix.hpp:284-313), out of place:
+//   bra bit 1 ranks: buffer[ket 1] = (1-p) amps[ket 1],  buffer[ket 0] = sqrt(1-p) amps[ket 0]            (no remote read)
+//   bra bit 0 ranks: buffer[ket 0] = amps[ket 0] + p * partner_amps[ket 1],  buffer[ket 1] = sqrt(1-p) amps[ket 1]
+int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob) {
+    const double c1 = sqrt(1 - prob), c2 = 1 - prob;
+    const uint64_t one = 1ULL << qb;
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    if (bit & 1u) {
+        auto ld = [=] __device__(uint64_t k) { uint64_t j = insertZeroBit(k, qb); return Amp2{amps[j], amps[j | one]}; };
+        auto st = [=] __device__(uint64_t k, const Amp2& v) {
+            uint64_t j = insertZeroBit(k, qb);
+            out[j] = cscale(c1, v.a0);
+            out[j | one] = cscale(c2, v.a1);
+        };
+        return launchStream<1, Amp2>(s->numAmps >> 1, ld, st);
+    }
+    auto ld = [=] __device__(uint64_t k) { uint64_t j = insertZeroBit(k, qb); return Amp3{amps[j], amps[j | one], remote[j | one]}; };
+    auto st = [=] __device__(uint64_t k, const Amp3& v) {
+        uint64_t j = insertZeroBit(k, qb);
+        out[j] = make_double2(fma(prob, v.c.x, v.a.x), fma(prob, v.c.y, v.a.y));
+        out[j | one] = cscale(c1, v.b);
+    };
+    return launchStream<1, Amp3>(s->numAmps >> 1, ld, st);
 }
 
 // K20: distributed_densitymatrix.hpp:152-183 (qb1 suffix, qb2 prefix). q0 = qb1, q1 = qb2, q2 = qb1+N, bit = rank bit of qb2's bra.
@@ -375,6 +424,12 @@ __global__ void __launch_bounds__(256) expecScanKernel(const double2* __restrict
     blockReduceToPartials(re, im, partials);
 }
 
+__global__ void __launch_bounds__(256) sumPartialsKernel(const double2* __restrict__ partials, unsigned n, double2* out) {
+    double re = 0.0, im = 0.0;
+    for (unsigned i = threadIdx.x; i < n; i += 256) { re += partials[i].x; im += partials[i].y; }
+    blockReduceToPartials(re, im, out);
+}
+
 extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]) {
     DFSA_DM_ENTRY(s);
     DFSA_REQUIRE(coeffs && paulis && out && numTerms >= 1, "bad argument");
@@ -404,18 +459,28 @@ extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsi
     unsigned grid = dfsaGrid(items, 256, 1, 8);
     size_t termBytes = (sizeof(PauliTerm) * numTerms + 255) / 256 * 256;
     double2* scratch;
-    DFSA_TRY(dfsaScratch(termBytes + grid * sizeof(double2), &scratch));
+    DFSA_TRY(dfsaScratch(termBytes + (grid + 1) * sizeof(double2), &scratch));
     PauliTerm* dTerms = (PauliTerm*)scratch;
     double2* partials = (double2*)((char*)scratch + termBytes);
-    DFSA_CUDA(cudaMemcpyAsync(dTerms, terms.data(), sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+    // term table: through the pinned staging ring when it fits (asynchronous), else a blocking pageable copy
+    void* stage = nullptr; int slot = -1;
+    if (dfsaStagingAcquire(sizeof(PauliTerm) * numTerms, &stage, &slot) == DFSA_OK) {
+        memcpy(stage, terms.data(), sizeof(PauliTerm) * numTerms);
+        DFSA_CUDA(cudaMemcpyAsync(dTerms, stage, sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+        DFSA_TRY(dfsaStagingCommit(slot));
+    } else {
+        DFSA_CUDA(cudaMemcpyAsync(dTerms, terms.data(), sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+        DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    }
     if (scan) expecScanKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, s->numAmps, (uint64_t)s->rank << s->logNumAmps, partials);
     else expecGatherKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, logCols, (uint64_t)s->rank << logCols, partials);
     DFSA_LAUNCH_CHECK();
-    std::vector<double2> host(grid);
-    DFSA_CUDA(cudaMemcpyAsync(host.data(), partials, grid * sizeof(double2), cudaMemcpyDeviceToHost, c.compute));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));               // also covers the lifetime of `terms`
-    double re = 0.0, im = 0.0;
-    for (const double2& p : host) { re += p.x; im += p.y; }
+    // block partials -> one value on the device (fixed order: deterministic), 16 bytes back through pinned memory
+    sumPartialsKernel<<<1, 256, 0, c.compute>>>(partials, grid, partials + grid);
+    DFSA_LAUNCH_CHECK();
+    DFSA_CUDA(cudaMemcpyAsync(c.hostPinned, partials + grid, sizeof(double2), cudaMemcpyDeviceToHost, c.compute));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    const double re = c.hostPinned[0], im = c.hostPinned[1];
     out[0] = re; out[1] = im;
     return DFSA_OK;
 }

@@ -80,13 +80,10 @@ static inline void distributed_densitymatrix_twoQubitDephasing(DensityMatrix& rh
 static inline void distributed_densitymatrix_oneQubitDepolarising(DensityMatrix& rho, Nat qb, Real prob) {
     const Nat threshold = rho.numQubits - rho.logNumNodes;
     if (qb < threshold) { local_densitymatrix_oneQubitDepolarising(rho, qb, prob); return; }
-    // the bra bit is a rank bit: swap the ket-bit == rank-bit halves with the partner, then mix
+    // the bra bit is a rank bit: the ket-bit == rank-bit halves are traded with the partner and mixed (reference :110-141);
+    // one fused pass over peer memory where the ranks share a node, else pack / exchange / combine
     const Nat rankQb = qb - threshold, bit = getBit(rho.rank, rankQb);
-    const Nat pairRank = Nat(flipBit(rho.rank, rankQb));
-    const Index half = rho.numAmpsPerNode / 2;
-    DFSA_CHECK(dfsa_k_pack(rho.handle, &qb, 1, bit, 0));
-    comm_exchangeArrays(rho.buffer, 0, rho.buffer, half, half, pairRank);
-    DFSA_CHECK(dfsa_k_depol1Combine(rho.handle, qb, bit, prob));
+    DFSA_CHECK(dfsa_xk_depol1Prefix(rho.handle, qb, bit, prob, int(flipBit(rho.rank, rankQb))));
 }
 
 // As in the reference, the three branches apply the reference's own formulas (SURVEY F2 explains why they are not
@@ -120,20 +117,9 @@ static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix&
 static inline void distributed_densitymatrix_damping(DensityMatrix& rho, Nat qb, Real prob) {
     const Nat threshold = rho.numQubits - rho.logNumNodes;
     if (qb < threshold) { local_densitymatrix_damping(rho, qb, prob); return; }
-    // population flows one way, from the rank holding bra bit 1 to the rank holding bra bit 0
+    // population flows one way, from the rank holding bra bit 1 to the rank holding bra bit 0 (reference :284-317)
     const Nat rankQb = qb - threshold, bit = getBit(rho.rank, rankQb);
-    const Nat pairRank = Nat(flipBit(rho.rank, rankQb));
-    const Index half = rho.numAmpsPerNode / 2;
-    if (bit == 1) {
-        DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 0));
-        comm_asynchSendArray(rho.buffer, half, pairRank);
-    }
-    DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 1));
-    if (bit == 0) {
-        comm_receiveArray(rho.buffer, half, pairRank);
-        DFSA_CHECK(dfsa_k_dampingPrefix(rho.handle, qb, bit, prob, 2));
-    }
-    // the reference needs a global barrier here to protect the sender's buffer; stream order does that job
+    DFSA_CHECK(dfsa_xk_dampingPrefix(rho.handle, qb, bit, prob, int(flipBit(rho.rank, rankQb))));
 }
 
 static inline Amp distributed_densitymatrix_expecPauliString(DensityMatrix& rho, RealArray coeffs, NatArray allPaulis) {

@@ -116,6 +116,11 @@ int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], con
  * leaves this rank (= NOT this rank's bit of the prefix qubit). With peer-mapped shards the partner's packed half is
  * gathered straight over NVLink into place; otherwise pack + dfsa_x_exchange + unpack. */
 int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank);
+/* oneQubitDepolarising / damping on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141, :284-317):
+ * pack + half exchange (one-way for damping) + combine of the reference. `bit` = this rank's bit of that qubit. With
+ * peer-mapped shards: one out-of-place pass that reads the partner's half over NVLink, then amps <-> buffer. */
+int dfsa_xk_depol1Prefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank);
+int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank);
 int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
                                  const double f[2], const double g[2], int exact);
 
