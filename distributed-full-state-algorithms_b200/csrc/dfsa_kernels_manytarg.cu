@@ -6,16 +6,16 @@
 // Kernels:
 //   t == 1   the pair-stream kernel of K1 (same operator)
 //   t == 2   register-resident 4x4 matvec on the streaming skeleton (quad items, gate in kernel parameters); HBM-bound
-//   t = 3..5 manyTargSpecKernel<T>: FP64 tensor cores (mma.sync m16n8k16.f64 -> SASS DMMA.8x8x4), warp-specialised:
+//   t = 3..6 manyTargSpecKernel<T>: FP64 tensor cores (mma.sync m16n8k16.f64 -> SASS DMMA.8x8x4), warp-specialised:
 //            mover warps stream 512-amplitude tiles HBM -> shared memory -> HBM (cp.async + mbarriers), compute warps do
 //            nothing but LDS -> DMMA -> STS with the gate held as A-fragments in registers.
 //            History (profiles/r01*_ncu_manytarg*): the DFMA version of t=5 was issue-bound at 18 % FP64-pipe utilisation
 //            and 8 % of DRAM bandwidth, i.e. compute- not HBM-bound -- the case north_star reserves the tensor path for;
 //            one warp per tile with per-element address tables reached 54 %, then 81 % of the pipe in 4M form; the
 //            3M form with the rows split over a warp pair 70 %; this kernel 81 % in 3M form (25 % fewer flops).
-//   t == 6   manyTargTileKernel<8>   block tile, gate transposed in shared memory, DFMA
+//            t == 6 (krausMap / density-matrix gates on 3 qubits): same kernel, the 64x64 gate's A-fragments in shared memory.
 //   t >= 7   manyTargGenericKernel   one block per 2^t group, gate streamed from L2, warp-per-row reduction
-//            (also: t = 3..5 on shards smaller than one tile)
+//            (also: t = 3..6 on shards smaller than one tile)
 #include <algorithm>
 #include <vector>
 
@@ -86,12 +86,15 @@ __device__ __forceinline__ void stsAmp(unsigned addr, double re, double im) {
 // fragment patterns: B reads vary (row bit 0, row bit 1, col bit 0), result writes vary (col bit 1, col bit 2, row bit 0).
 template <int T> struct SpecGeom {
     static constexpr unsigned D = 1u << T, TILE_BITS = 9, F = TILE_BITS - T, COLS = 1u << F;
-    static constexpr unsigned STREAMS = 4, NIN = 4, NOUT = 2;
+    // t = 6: the 64x64 gate cannot live in registers; its A-fragments (three 3M matrices, 96 KiB) sit in shared memory,
+    // which leaves room for 2 + 1 slabs per stream -- enough, the tile is FP64-bound four times over
+    static constexpr unsigned STREAMS = 4, NIN = (T == 6) ? 2 : 4, NOUT = (T == 6) ? 1 : 2;
     static constexpr unsigned SLAB_BYTES = 16u << TILE_BITS;                   // 8 KiB
     static constexpr unsigned THREADS = 32 * (2 * STREAMS + STREAMS);          // 8 compute warps + 4 mover warps
-    static constexpr size_t smemBytes = (size_t)STREAMS * (NIN + NOUT) * SLAB_BYTES + SLAB_BYTES;   // + alignment slack = 200 KiB
+    static constexpr unsigned GATE_BYTES = (T == 6) ? 3u * 16u * 2048u : 0u;   // [matrix][mb][kb] fragments of 2 KiB
+    static constexpr size_t smemBytes = (size_t)STREAMS * (NIN + NOUT) * SLAB_BYTES + GATE_BYTES + SLAB_BYTES;   // + alignment slack = 200 KiB
 };
-struct SpecLayout { uint32_t rowBit[5], colBit[6]; };               // slab byte-offset contribution of gate-row bit i / vector bit j
+struct SpecLayout { uint32_t rowBit[6], colBit[6]; };               // slab byte-offset contribution of gate-row bit i / vector bit j
 // i part of tile element (lane | i << 5): byte offset in the shard and in the slab. Rides in the kernel parameters, so after
 // unrolling every entry is a constant-bank operand (the first tensor kernel read two shared-memory tables and spent ~15 ALU
 // instructions per 16-byte element: 1200 non-DMMA instructions per tile against 512 DMMA slots).
@@ -126,6 +129,22 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
         for (unsigned o = 0; o < NOUT; o++) { mbarInit(&done[threadIdx.x][o], 2); mbarInit(&drained[threadIdx.x][o], 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // t = 6: A-fragments of the three 3M matrices, [matrix m][mb][kb][chunk c][lane] as 16-byte (a[2c], a[2c+1]) pairs, so
+    // that a warp's LDS.128 of one chunk is 512 contiguous bytes
+    const unsigned gateS = ((smemAddr(smem) + SLAB_BYTES - 1u) & ~(SLAB_BYTES - 1u)) + STREAMS * ((NIN + NOUT) * SLAB_BYTES);
+    if constexpr (T == 6) {
+        for (unsigned idx = threadIdx.x; idx < 3u * 16u * 4u * 32u; idx += G::THREADS) {
+            const unsigned ln = idx & 31u, c = (idx >> 5) & 3u, kb = (idx >> 7) & 3u, mb = (idx >> 9) & 3u, m = idx >> 11;
+            double val[2];
+#pragma unroll
+            for (unsigned w = 0; w < 2; w++) {
+                const unsigned v = 2 * c + w;                        // a[v]: row g + 8(v&1), col q + 4(v>>1)
+                const double2 e = gate[(16 * mb + (ln >> 2) + 8 * (v & 1)) * D + 16 * kb + (ln & 3u) + 4 * (v >> 1)];
+                val[w] = m == 0 ? e.x : (m == 1 ? e.y - e.x : e.x + e.y);
+            }
+            stsAmp(gateS + idx * 16u, val[0], val[1]);
+        }
+    }
     __syncthreads();
 
     const uint64_t stride = (uint64_t)gridDim.x * STREAMS;
@@ -177,14 +196,14 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
     const unsigned g = lane >> 2, q = lane & 3u;
     // thread parts of the operand (row q, column g) and result (row g [+ 16h], column 2q) slab offsets
     const unsigned laneB = specOffset<T>(q, g, lay);
-    const unsigned laneC = specOffset<T>((T == 5 ? 16 * h : 0) + g, 2 * q, lay);
+    const unsigned laneC = specOffset<T>((T == 5 ? 16 * h : (T == 6 ? 32 * h : 0)) + g, 2 * q, lay);
     // the gate as A-fragments. 3M complex product (t = 4, 5): with k1 = G_re (X_re + X_im), k2 = (G_im - G_re) X_re,
     // k3 = (G_re + G_im) X_im:  Y_re = k1 - k3, Y_im = k1 + k2 -- three real MMAs where the 4M form needs four.
     // t = 3: the 8x8 complex gate as ONE real 16x16 matrix [[G_re, -G_im], [G_im, G_re]] acting on [X_re; X_im].
-    constexpr int KB = (T == 5) ? 2 : 1;                            // 16-column blocks of the gate
+    constexpr int KB = (T == 5) ? 2 : 1;                            // 16-column blocks of the gate (register-resident forms)
     double ar[KB][8], ad[KB][8], as[KB][8];
 #pragma unroll
-    for (int kb = 0; kb < KB; kb++)
+    for (int kb = 0; kb < (T == 6 ? 0 : KB); kb++)
 #pragma unroll
         for (int v = 0; v < 8; v++) {
             const unsigned row = g + 8 * (v & 1), col = q + 4 * (v >> 1);
@@ -200,8 +219,8 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
             }
         }
     // column blocks (8 vectors each) this warp works on: all of them for t = 5 (rows are split), half of them otherwise
-    constexpr unsigned NBW = (T == 5) ? G::COLS / 8 : G::COLS / 16;
-    const unsigned nb0 = (T == 5) ? 0u : h * NBW;
+    constexpr unsigned NBW = (T >= 5) ? G::COLS / 8 : G::COLS / 16;
+    const unsigned nb0 = (T >= 5) ? 0u : h * NBW;
 
     for (unsigned i = 0; i < numMine; i++) {
         const unsigned s = i % NIN, o = i % NOUT;
@@ -211,7 +230,41 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
 #pragma unroll
         for (unsigned nbi = 0; nbi < NBW; nbi++) {
             const unsigned nb = nb0 + nbi;
-            if constexpr (T == 3) {
+            if constexpr (T == 6) {
+                // this warp: gate rows 32h .. 32h+31 (two 16-row blocks), all four 16-column blocks, A-fragments from shared memory
+                double k1[2][4], k2[2][4], k3[2][4];
+#pragma unroll
+                for (int mbl = 0; mbl < 2; mbl++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) { k1[mbl][v] = 0.0; k2[mbl][v] = 0.0; k3[mbl][v] = 0.0; }
+                const unsigned laneA = gateS + (h * (2u * 4u * 4u * 32u) + lane) * 16u;      // + ((m*4 + mbl)*4 + kb)*4 + c) * 512
+#pragma unroll
+                for (unsigned kb = 0; kb < 4; kb++) {
+                    double xr[4], xi[4], xs[4];
+#pragma unroll
+                    for (unsigned v = 0; v < 4; v++) {
+                        ldsAmp(xr[v], xi[v], xB ^ specOffset<T>(16 * kb + 4 * v, nb * 8, lay));
+                        xs[v] = xr[v] + xi[v];
+                    }
+#pragma unroll
+                    for (unsigned mbl = 0; mbl < 2; mbl++) {
+                        double a[3][8];
+#pragma unroll
+                        for (unsigned m = 0; m < 3; m++)
+#pragma unroll
+                            for (unsigned c = 0; c < 4; c++)
+                                ldsAmp(a[m][2 * c], a[m][2 * c + 1], laneA + ((((m * 4 + mbl) * 4 + kb) * 4 + c) << 9));
+                        dmma16816(k2[mbl], a[1], xr);
+                        dmma16816(k3[mbl], a[2], xi);
+                        dmma16816(k1[mbl], a[0], xs);
+                    }
+                }
+#pragma unroll
+                for (unsigned mbl = 0; mbl < 2; mbl++)
+#pragma unroll
+                    for (unsigned v = 0; v < 4; v++)                    // c[v]: row 32h + 16mbl + g + 8(v>>1), column 2q + (v&1)
+                        stsAmp(yC ^ specOffset<T>(16 * mbl + 8 * (v >> 1), nb * 8 + (v & 1), lay), k1[mbl][v] - k3[mbl][v], k1[mbl][v] + k2[mbl][v]);
+            } else if constexpr (T == 3) {
                 // b[v]: k = q + 4v; k < 8 -> X_re row k, k >= 8 -> X_im row k - 8
                 double x0r, x0i, x1r, x1i;
                 ldsAmp(x0r, x0i, xB ^ specOffset<T>(0, nb * 8, lay));
@@ -248,67 +301,7 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// t == 6: 64 KiB of gate does not fit constant memory; block-wide tile with the gate transposed in shared memory,
-// thread = (8 consecutive rows, one lane).
-template <int R>
-__global__ void __launch_bounds__(256) manyTargTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec,
-                                                         unsigned t, unsigned f, const double2* __restrict__ gateT, BitSpec localPos) {
-    extern __shared__ double2 smem[];
-    const unsigned d = 1u << t, lanes = 1u << f, tileAmps = d << f;
-    double2* G = smem;                 // G^T[l][r], d*d
-    double2* X = smem + (size_t)d * d; // X[row][lane]
-    for (unsigned e = threadIdx.x; e < d * d; e += blockDim.x) G[e] = gateT[e];
-
-    uint64_t gOff[8];
-    unsigned xIdx[8];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        unsigned e = threadIdx.x + k * 256;
-        uint64_t g = 0;
-        unsigned row = 0, lane = 0;
-        for (unsigned b = 0; b < t + f; b++) {
-            unsigned bit = (e >> b) & 1u, role = localPos.pos[b];
-            g |= (uint64_t)bit << tileSpec.pos[b];
-            if (role < t) row |= bit << role; else lane |= bit << (role - t);
-        }
-        gOff[k] = g;
-        xIdx[k] = row * lanes + lane;
-    }
-    const unsigned myLane = threadIdx.x % lanes, r0 = (threadIdx.x / lanes) * R;
-    const bool active = r0 < d;
-
-    for (uint64_t tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-        const uint64_t base = insertZeroBits(tile, tileSpec);
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (threadIdx.x + k * 256 < tileAmps) X[xIdx[k]] = amps[base | gOff[k]];
-        __syncthreads();
-        double2 acc[R];
-#pragma unroll
-        for (int i = 0; i < R; i++) acc[i] = make_double2(0.0, 0.0);
-        if (active) {
-            for (unsigned l = 0; l < d; l++) {
-                const double2 x = X[l * lanes + myLane];
-                const double2* grow = G + (size_t)l * d + r0;
-#pragma unroll
-                for (int i = 0; i < R; i++) acc[i] = cfma(grow[i], x, acc[i]);
-            }
-        }
-        __syncthreads();
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < R; i++) X[(r0 + i) * lanes + myLane] = acc[i];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 8; k++)
-            if (threadIdx.x + k * 256 < tileAmps) amps[base | gOff[k]] = X[xIdx[k]];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// t >= 7 (krausMap superoperators): one block per 2^t-amplitude group staged in shared memory,
+// t >= 7 (krausMap superoperators) and small shards: one block per 2^t-amplitude group staged in shared memory,
 // gate rows streamed from global memory (L2-resident), a warp per output row, shuffle reduction over columns.
 __global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint64_t numGroups, BitSpec sortedTargs, BitSpec callerTargs,
                                                             unsigned t, const double2* __restrict__ gate, double2* __restrict__ outStage) {
@@ -377,7 +370,7 @@ int buildTile(const uint32_t* targets, unsigned t, unsigned L, uint64_t targMask
 template <int T>
 void chooseLayout(const BitSpec& localPos, SpecLayout* z, unsigned bitOff[9]) {
     constexpr unsigned NB = SpecGeom<T>::TILE_BITS;
-    unsigned posOfRow[5] = {0, 0, 0, 0, 0}, posOfCol[6] = {0, 0, 0, 0, 0, 0};
+    unsigned posOfRow[6] = {0, 0, 0, 0, 0, 0}, posOfCol[6] = {0, 0, 0, 0, 0, 0};
     for (unsigned p = 0; p < NB; p++) {
         const unsigned role = localPos.pos[p];
         if (role < (unsigned)T) posOfRow[role] = p; else posOfCol[role - T] = p;
@@ -395,7 +388,7 @@ void chooseLayout(const BitSpec& localPos, SpecLayout* z, unsigned bitOff[9]) {
         if (independent(vec(involved[0]), vec(involved[1]), vec(involved[2])) && independent(vec(involved[3]), vec(involved[4]), vec(involved[0]))) break;
     }
     for (unsigned p = 0; p < NB; p++) bitOff[p] = (16u << p) ^ ((p >= 3 ? m[p] : 0u) << 4);
-    for (unsigned i = 0; i < 5; i++) z->rowBit[i] = i < (unsigned)T ? bitOff[posOfRow[i]] : 0u;
+    for (unsigned i = 0; i < 6; i++) z->rowBit[i] = i < (unsigned)T ? bitOff[posOfRow[i]] : 0u;
     for (unsigned j = 0; j < 6; j++) z->colBit[j] = j < SpecGeom<T>::F ? bitOff[posOfCol[j]] : 0u;
 }
 
@@ -476,7 +469,7 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
     }
 
     // tensor-core tiles span 9 local bits; a smaller shard (< 512 amplitudes) goes to the generic kernel below
-    if (t >= 3 && t <= 5 && L >= SpecGeom<3>::TILE_BITS) {
+    if (t >= 3 && t <= 6 && L >= SpecGeom<3>::TILE_BITS) {
         void* stage; int slot;
         DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
         memcpy(stage, gate, gateBytes);
@@ -487,29 +480,9 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         switch (t) {
             case 3:  return launchSpecKernel<3>(s, targets, targMask, dev);
             case 4:  return launchSpecKernel<4>(s, targets, targMask, dev);
-            default: return launchSpecKernel<5>(s, targets, targMask, dev);
+            case 5:  return launchSpecKernel<5>(s, targets, targMask, dev);
+            default: return launchSpecKernel<6>(s, targets, targMask, dev);
         }
-    }
-
-    if (t == 6) {
-        void* stage; int slot;
-        DFSA_TRY(dfsaStagingAcquire(gateBytes, &stage, &slot));
-        double2* gt = (double2*)stage;                    // transposed: G^T[l][r]
-        for (uint64_t r = 0; r < d; r++) for (uint64_t l = 0; l < d; l++) gt[l * d + r] = hostAmp(gate + 2 * (r * d + l));
-        double2* dev;
-        DFSA_TRY(dfsaScratch(gateBytes, &dev));
-        DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
-        DFSA_TRY(dfsaStagingCommit(slot));
-        const unsigned f = std::min(5u, L - t);
-        BitSpec tileSpec, localPos;
-        DFSA_TRY(buildTile(targets, t, L, targMask, f, &tileSpec, &localPos));
-        const size_t smemBytes = (d * d + (d << f)) * sizeof(double2);
-        const uint64_t numTiles = s->numAmps >> (t + f);
-        const unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 2);
-        DFSA_CUDA(cudaFuncSetAttribute(manyTargTileKernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-        manyTargTileKernel<8><<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, t, f, dev, localPos);
-        DFSA_LAUNCH_CHECK();
-        return DFSA_OK;
     }
 
     DFSA_REQUIRE(d * sizeof(double2) <= 200 * 1024, "manyTargGate: 2^numTargets amplitudes must fit shared memory (numTargets <= 13)");
