@@ -91,8 +91,8 @@ template <int T> struct SpecGeom {
     static constexpr unsigned STREAMS = 4, NIN = (T == 6) ? 2 : 4, NOUT = (T == 6) ? 1 : 2;
     static constexpr unsigned SLAB_BYTES = 16u << TILE_BITS;                   // 8 KiB
     static constexpr unsigned THREADS = 32 * (2 * STREAMS + STREAMS);          // 8 compute warps + 4 mover warps
-    static constexpr unsigned GATE_BYTES = (T == 6) ? 3u * 16u * 2048u : 0u;   // [matrix][mb][kb] fragments of 2 KiB
-    static constexpr size_t smemBytes = (size_t)STREAMS * (NIN + NOUT) * SLAB_BYTES + GATE_BYTES + SLAB_BYTES;   // + alignment slack = 200 KiB
+    static constexpr unsigned GATE_BYTES = 3u * (D / 16) * (D / 16) * 2048u;   // [matrix][mb][kb] A-fragments of 2 KiB, when they live in shared memory
+    static constexpr size_t smemBytes(bool smemA) { return (size_t)STREAMS * (NIN + NOUT) * SLAB_BYTES + (smemA ? GATE_BYTES : 0u) + SLAB_BYTES; }   // + alignment slack
 };
 struct SpecLayout { uint32_t rowBit[6], colBit[6]; };               // slab byte-offset contribution of gate-row bit i / vector bit j
 // i part of tile element (lane | i << 5): byte offset in the shard and in the slab. Rides in the kernel parameters, so after
@@ -110,7 +110,7 @@ __host__ __device__ __forceinline__ unsigned specOffset(unsigned row, unsigned c
     return o;
 }
 
-template <int T>
+template <int T, bool SMEM_A>
 __global__ void __launch_bounds__(SpecGeom<T>::THREADS, 1)
 manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec localPos, const double2* __restrict__ gate, SpecMap map, SpecLayout lay) {
     using G = SpecGeom<T>;
@@ -129,12 +129,13 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
         for (unsigned o = 0; o < NOUT; o++) { mbarInit(&done[threadIdx.x][o], 2); mbarInit(&drained[threadIdx.x][o], 1); }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // t = 6: A-fragments of the three 3M matrices, [matrix m][mb][kb][chunk c][lane] as 16-byte (a[2c], a[2c+1]) pairs, so
+    // SMEM_A: A-fragments of the three 3M matrices, [matrix m][mb][kb][chunk c][lane] as 16-byte (a[2c], a[2c+1]) pairs, so
     // that a warp's LDS.128 of one chunk is 512 contiguous bytes
+    constexpr unsigned MBT = D / 16;                                  // 16-row / 16-column blocks of the gate
     const unsigned gateS = ((smemAddr(smem) + SLAB_BYTES - 1u) & ~(SLAB_BYTES - 1u)) + STREAMS * ((NIN + NOUT) * SLAB_BYTES);
-    if constexpr (T == 6) {
-        for (unsigned idx = threadIdx.x; idx < 3u * 16u * 4u * 32u; idx += G::THREADS) {
-            const unsigned ln = idx & 31u, c = (idx >> 5) & 3u, kb = (idx >> 7) & 3u, mb = (idx >> 9) & 3u, m = idx >> 11;
+    if constexpr (SMEM_A) {
+        for (unsigned idx = threadIdx.x; idx < 3u * MBT * MBT * 4u * 32u; idx += G::THREADS) {
+            const unsigned ln = idx & 31u, c = (idx >> 5) & 3u, blk = idx >> 7, kb = blk % MBT, mb = (blk / MBT) % MBT, m = blk / (MBT * MBT);
             double val[2];
 #pragma unroll
             for (unsigned w = 0; w < 2; w++) {
@@ -196,14 +197,14 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
     const unsigned g = lane >> 2, q = lane & 3u;
     // thread parts of the operand (row q, column g) and result (row g [+ 16h], column 2q) slab offsets
     const unsigned laneB = specOffset<T>(q, g, lay);
-    const unsigned laneC = specOffset<T>((T == 5 ? 16 * h : (T == 6 ? 32 * h : 0)) + g, 2 * q, lay);
+    const unsigned laneC = specOffset<T>((T >= 5 ? (D / 2) * h : 0) + g, 2 * q, lay);
     // the gate as A-fragments. 3M complex product (t = 4, 5): with k1 = G_re (X_re + X_im), k2 = (G_im - G_re) X_re,
     // k3 = (G_re + G_im) X_im:  Y_re = k1 - k3, Y_im = k1 + k2 -- three real MMAs where the 4M form needs four.
     // t = 3: the 8x8 complex gate as ONE real 16x16 matrix [[G_re, -G_im], [G_im, G_re]] acting on [X_re; X_im].
     constexpr int KB = (T == 5) ? 2 : 1;                            // 16-column blocks of the gate (register-resident forms)
     double ar[KB][8], ad[KB][8], as[KB][8];
 #pragma unroll
-    for (int kb = 0; kb < (T == 6 ? 0 : KB); kb++)
+    for (int kb = 0; kb < (SMEM_A ? 0 : KB); kb++)
 #pragma unroll
         for (int v = 0; v < 8; v++) {
             const unsigned row = g + 8 * (v & 1), col = q + 4 * (v >> 1);
@@ -219,7 +220,7 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
             }
         }
     // column blocks (8 vectors each) this warp works on: all of them for t = 5 (rows are split), half of them otherwise
-    constexpr unsigned NBW = (T >= 5) ? G::COLS / 8 : G::COLS / 16;
+    constexpr unsigned NBW = SMEM_A ? 1 : ((T >= 5) ? G::COLS / 8 : G::COLS / 16);
     const unsigned nb0 = (T >= 5) ? 0u : h * NBW;
 
     for (unsigned i = 0; i < numMine; i++) {
@@ -230,40 +231,55 @@ manyTargSpecKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, BitSpec l
 #pragma unroll
         for (unsigned nbi = 0; nbi < NBW; nbi++) {
             const unsigned nb = nb0 + nbi;
-            if constexpr (T == 6) {
-                // this warp: gate rows 32h .. 32h+31 (two 16-row blocks), all four 16-column blocks, A-fragments from shared memory
-                double k1[2][4], k2[2][4], k3[2][4];
+            if constexpr (SMEM_A) {
+                // this warp: gate rows (D/2)h .. (D/2)h + D/2 - 1 (MBW 16-row blocks), all MBT 16-column blocks, every column
+                // block of the tile at once (NBJ: one A-fragment load feeds NBJ MMAs); A-fragments from shared memory
+                constexpr unsigned MBW = MBT / 2, NBJ = G::COLS / 8;
+                double k1[NBJ][MBW][4], k2[NBJ][MBW][4], k3[NBJ][MBW][4];
 #pragma unroll
-                for (int mbl = 0; mbl < 2; mbl++)
+                for (unsigned j = 0; j < NBJ; j++)
 #pragma unroll
-                    for (int v = 0; v < 4; v++) { k1[mbl][v] = 0.0; k2[mbl][v] = 0.0; k3[mbl][v] = 0.0; }
-                const unsigned laneA = gateS + (h * (2u * 4u * 4u * 32u) + lane) * 16u;      // + ((m*4 + mbl)*4 + kb)*4 + c) * 512
+                    for (unsigned mbl = 0; mbl < MBW; mbl++)
 #pragma unroll
-                for (unsigned kb = 0; kb < 4; kb++) {
-                    double xr[4], xi[4], xs[4];
+                        for (int v = 0; v < 4; v++) { k1[j][mbl][v] = 0.0; k2[j][mbl][v] = 0.0; k3[j][mbl][v] = 0.0; }
+                const unsigned laneA = gateS + (h * (MBW * MBT * 4u * 32u) + lane) * 16u;   // + ((((m*MBT + mbl)*MBT + kb)*4 + c) << 9)
 #pragma unroll
-                    for (unsigned v = 0; v < 4; v++) {
-                        ldsAmp(xr[v], xi[v], xB ^ specOffset<T>(16 * kb + 4 * v, nb * 8, lay));
-                        xs[v] = xr[v] + xi[v];
-                    }
+                for (unsigned kb = 0; kb < MBT; kb++) {
+                    double xr[NBJ][4], xi[NBJ][4], xs[NBJ][4];
 #pragma unroll
-                    for (unsigned mbl = 0; mbl < 2; mbl++) {
-                        double a[3][8];
+                    for (unsigned j = 0; j < NBJ; j++)
 #pragma unroll
-                        for (unsigned m = 0; m < 3; m++)
+                        for (unsigned v = 0; v < 4; v++) {
+                            ldsAmp(xr[j][v], xi[j][v], xB ^ specOffset<T>(16 * kb + 4 * v, j * 8, lay));
+                            xs[j][v] = xr[j][v] + xi[j][v];
+                        }
+#pragma unroll
+                    for (unsigned mbl = 0; mbl < MBW; mbl++) {
+                        // matrix order 1, 2, 0: the product that needs the DADD results (x_re + x_im) goes last
+#pragma unroll
+                        for (unsigned mi = 0; mi < 3; mi++) {
+                            const unsigned m = (mi + 1) % 3;
+                            double a[8];
 #pragma unroll
                             for (unsigned c = 0; c < 4; c++)
-                                ldsAmp(a[m][2 * c], a[m][2 * c + 1], laneA + ((((m * 4 + mbl) * 4 + kb) * 4 + c) << 9));
-                        dmma16816(k2[mbl], a[1], xr);
-                        dmma16816(k3[mbl], a[2], xi);
-                        dmma16816(k1[mbl], a[0], xs);
+                                ldsAmp(a[2 * c], a[2 * c + 1], laneA + ((((m * MBT + mbl) * MBT + kb) * 4 + c) << 9));
+#pragma unroll
+                            for (unsigned j = 0; j < NBJ; j++) {
+                                if (m == 1) dmma16816(k2[j][mbl], a, xr[j]);
+                                else if (m == 2) dmma16816(k3[j][mbl], a, xi[j]);
+                                else dmma16816(k1[j][mbl], a, xs[j]);
+                            }
+                        }
                     }
                 }
 #pragma unroll
-                for (unsigned mbl = 0; mbl < 2; mbl++)
+                for (unsigned j = 0; j < NBJ; j++)
 #pragma unroll
-                    for (unsigned v = 0; v < 4; v++)                    // c[v]: row 32h + 16mbl + g + 8(v>>1), column 2q + (v&1)
-                        stsAmp(yC ^ specOffset<T>(16 * mbl + 8 * (v >> 1), nb * 8 + (v & 1), lay), k1[mbl][v] - k3[mbl][v], k1[mbl][v] + k2[mbl][v]);
+                    for (unsigned mbl = 0; mbl < MBW; mbl++)
+#pragma unroll
+                        for (unsigned v = 0; v < 4; v++)                // c[v]: row (D/2)h + 16mbl + g + 8(v>>1), column 8j + 2q + (v&1)
+                            stsAmp(yC ^ specOffset<T>(16 * mbl + 8 * (v >> 1), j * 8 + (v & 1), lay), k1[j][mbl][v] - k3[j][mbl][v], k1[j][mbl][v] + k2[j][mbl][v]);
+                (void)nb;
             } else if constexpr (T == 3) {
                 // b[v]: k = q + 4v; k < 8 -> X_re row k, k >= 8 -> X_im row k - 8
                 double x0r, x0i, x1r, x1i;
@@ -393,7 +409,7 @@ void chooseLayout(const BitSpec& localPos, SpecLayout* z, unsigned bitOff[9]) {
 }
 
 // full tiles only (9 local bits): shards too small for one are the caller's business
-template <int T>
+template <int T, bool SMEM_A>
 int launchSpecKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, const double2* devGate) {
     using G = SpecGeom<T>;
     DfsaContext& ctx = dfsaCtx();
@@ -413,13 +429,13 @@ int launchSpecKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, 
     }
     static bool configured = false;
     if (!configured) {
-        DFSA_CUDA(cudaFuncSetAttribute(manyTargSpecKernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smemBytes));
+        DFSA_CUDA(cudaFuncSetAttribute(manyTargSpecKernel<T, SMEM_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::smemBytes(SMEM_A)));
         configured = true;
     }
     const uint64_t numTiles = s->numAmps >> G::TILE_BITS;
     const uint64_t blocksNeeded = (numTiles + G::STREAMS - 1) / G::STREAMS;
     const unsigned grid = (unsigned)std::min<uint64_t>(blocksNeeded, (uint64_t)ctx.numSMs);
-    manyTargSpecKernel<T><<<grid, G::THREADS, G::smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, devGate, map, lay);
+    manyTargSpecKernel<T, SMEM_A><<<grid, G::THREADS, G::smemBytes(SMEM_A), ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, localPos, devGate, map, lay);
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
 }
@@ -478,10 +494,11 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
         DFSA_TRY(dfsaStagingCommit(slot));
         switch (t) {
-            case 3:  return launchSpecKernel<3>(s, targets, targMask, dev);
-            case 4:  return launchSpecKernel<4>(s, targets, targMask, dev);
-            case 5:  return launchSpecKernel<5>(s, targets, targMask, dev);
-            default: return launchSpecKernel<6>(s, targets, targMask, dev);
+            case 3:  return launchSpecKernel<3, false>(s, targets, targMask, dev);
+            case 4:  return launchSpecKernel<4, false>(s, targets, targMask, dev);
+            // t = 5 measured both ways at 30 qubits: A-fragments in registers 7.2 ms, in shared memory 7.5 ms
+            case 5:  return launchSpecKernel<5, false>(s, targets, targMask, dev);
+            default: return launchSpecKernel<6, true>(s, targets, targMask, dev);
         }
     }
 
