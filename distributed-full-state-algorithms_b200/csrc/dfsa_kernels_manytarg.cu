@@ -442,6 +442,29 @@ int launchSpecKernel(dfsa_state* s, const uint32_t* targets, uint64_t targMask, 
 
 }  // namespace
 
+// Host-only view of the tensor-core kernel's tile plan (no device needed): which 9 index bits form a tile, their roles
+// (< t: gate-row bit, else vector bit role - t) and the shared-memory slab layout chosen for this placement.
+extern "C" int dfsa_plan_manyTargLayout(const uint32_t* targets, unsigned numTargets, unsigned logNumAmps, uint32_t tileBits[9],
+                                        uint32_t roles[9], uint32_t bitOff[9], uint32_t rowBit[6], uint32_t colBit[6]) {
+    DFSA_REQUIRE(targets && tileBits && roles && bitOff && rowBit && colBit, "null argument");
+    DFSA_REQUIRE(numTargets >= 3 && numTargets <= 6 && logNumAmps >= SpecGeom<3>::TILE_BITS && logNumAmps <= DFSA_MAX_QUBITS,
+                 "the tile kernel serves 3..6 targets on shards of at least 512 amplitudes");
+    BitSpec sortedT, tileSpec, localPos; uint64_t targMask;
+    DFSA_TRY(sortedSpec(targets, numTargets, logNumAmps, &sortedT, &targMask));
+    DFSA_TRY(buildTile(targets, numTargets, logNumAmps, targMask, SpecGeom<3>::TILE_BITS - numTargets, &tileSpec, &localPos));
+    SpecLayout lay;
+    unsigned off[9];
+    switch (numTargets) {
+        case 3:  chooseLayout<3>(localPos, &lay, off); break;
+        case 4:  chooseLayout<4>(localPos, &lay, off); break;
+        case 5:  chooseLayout<5>(localPos, &lay, off); break;
+        default: chooseLayout<6>(localPos, &lay, off); break;
+    }
+    for (unsigned p = 0; p < 9; p++) { tileBits[p] = tileSpec.pos[p]; roles[p] = localPos.pos[p]; bitOff[p] = off[p]; }
+    for (unsigned i = 0; i < 6; i++) { rowBit[i] = lay.rowBit[i]; colBit[i] = lay.colBit[i]; }
+    return DFSA_OK;
+}
+
 extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && targets && gate, "null argument");

@@ -132,6 +132,13 @@ int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, 
 int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2);
 /* K4: dense 2^t x 2^t gate on suffix targets, gate bit i <-> targets[i]. local_statevector.hpp:72 */
 int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate);
+/* Host-only (no device needed): the tile plan of the tensor-core manyTarg kernel (3 <= numTargets <= 6, logNumAmps >= 9) --
+ * the 9 index bits of a tile (ascending), their roles (< numTargets: gate-row bit i = targets[i], else vector bit
+ * role - numTargets), the slab byte-offset contribution of each tile bit (address order, XOR-swizzled) and the same per
+ * gate-row bit / vector bit. tests/test_manytarg_layout.py checks on CPU that every fragment access pattern is
+ * shared-memory bank-conflict free for every target placement. */
+int dfsa_plan_manyTargLayout(const uint32_t* targets, unsigned numTargets, unsigned logNumAmps, uint32_t tileBits[9],
+                             uint32_t roles[9], uint32_t bitOff[9], uint32_t rowBit[6], uint32_t colBit[6]);
 /* K5: amps[j0] = f*amps[j0] + g*b(j1)*amps[j1], j1 = j0^maskXY, b = i^numY * (-1)^parity(global(j1) & maskYZ);
  * maskXY==0 is the diagonal case. `exact` selects the move/negate-only path (f=0,g=1: pauliTensor).
  * local_statevector.hpp:102 */
