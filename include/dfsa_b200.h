@@ -112,9 +112,10 @@ int dfsa_x_allreduce_amp(double reim[2]);                         /* comm_reduce
  * dfsa_x_exchange + dfsa_k_combine / dfsa_k_pauliCombine. */
 int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]);
 /* swapGate of a suffix qubit `qb1` with the prefix qubit whose rank bit distinguishes this rank from `pairRank`
- * (distributed_statevector.hpp:160-186: pack, exchange half, unpack). `movingBit` is the value of qb1 in the half that
- * leaves this rank (= NOT this rank's bit of the prefix qubit). With peer-mapped shards the partner's packed half is
- * gathered straight over NVLink into place; otherwise pack + dfsa_x_exchange + unpack. */
+ * (distributed_statevector.hpp:140-186). `movingBit` is the value of qb1 in the half that leaves this rank (= NOT this
+ * rank's bit of the prefix qubit). With peer-mapped shards: ONE out-of-place pass -- buffer[j] = amps[j] where bit qb1 of
+ * j stays, else the partner's amps[j ^ (1 << qb1)] read over NVLink -- then amps <-> buffer. Otherwise the reference's
+ * steps: contiguous half exchange + copy (qb1 top suffix qubit) or pack + dfsa_x_exchange + unpack. */
 int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank);
 /* oneQubitDepolarising / damping on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141, :284-317):
  * pack + half exchange (one-way for damping) + combine of the reference. `bit` = this rank's bit of that qubit. With
