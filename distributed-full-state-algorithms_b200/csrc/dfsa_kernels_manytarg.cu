@@ -62,17 +62,18 @@ __device__ __forceinline__ void stsAmp(unsigned addr, double re, double im) {
 // ---------------------------------------------------------------------------------------------------------
 // Geometry. A tile = the 512 amplitudes (8 KiB) spanned by the t target bits and the F = 9 - t lowest non-target bits;
 // it is staged as a slab X[row][col]: row = gate-ordered target bits, col = free bits (2^F vectors the same gate acts on).
-// A block runs 4 tile STREAMS; each stream has one mover warp and two compute warps, NIN input slabs and two output
-// slabs, handed over through mbarriers:
+// A block runs 4 tile STREAMS; each stream has one mover warp and two compute warps, NIN input slabs and NOUT output
+// slabs (4 + 2; t = 6: 2 + 1), handed over through mbarriers:
 //   full[s]    mover -> compute: tile landed in input slab s (cp.async.mbarrier.arrive.noinc of the 32 mover lanes)
 //   done[o]    compute -> mover: output slab o holds a tile's results and its input slab is free again (both warps arrive)
 //   drained[o] mover -> compute: output slab o has been read out, it may be overwritten
-// Tile i of a stream uses input slab i % NIN and output slab i % 2; the mover loads tile i + NIN as soon as tile i is done,
+// Tile i of a stream uses input slab i % NIN and output slab i % NOUT; the mover loads tile i + NIN as soon as tile i is done,
 // i.e. NIN - 1 tile-times ahead of its use. Why specialise: with load/store and DMMA phases in the same warps, the warps of
 // a scheduler share the tensor pipe fairly and drift into lock-step -- all computing, then all moving data with the pipe idle.
 //
-// The two compute warps of a stream split the tile: t = 5 by gate ROWS (16 each: the three A-matrices of the 3M product then
-// cost 96 registers), t = 3, 4 by COLUMNS (the whole gate fits: 16 / 48 registers).
+// The two compute warps of a stream split the tile: t = 5, 6 by gate ROWS (t = 5: 16 each, the three A-matrices of the 3M
+// product then cost 96 registers; t = 6: 32 each, A-fragments in shared memory), t = 3, 4 by COLUMNS (the whole gate fits:
+// 16 / 48 registers).
 //
 // Slab layout: a slab is the tile in ADDRESS order -- tile element e (bit p of e = p-th lowest tile bit of the shard index)
 // sits at byte offset XOR_p bit_p(e) * bitOff[p], bitOff[p] = (16 << p) ^ (m[p] << 4) with a 3-bit swizzle m[p] for p >= 3.
