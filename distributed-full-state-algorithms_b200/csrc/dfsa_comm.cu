@@ -573,6 +573,49 @@ extern "C" int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned mo
     return dfsa_k_unpack(s, &pos, 1, movingBit, half);
 }
 
+// Relocation of manyTargGate (distributed_statevector.hpp:193-223): swap suffix qubit suffixQubits[i] with prefix qubit
+// prefixQubits[i] for all i. COLLECTIVE over all ranks. One pair: the fused swap. Several pairs with peer-mapped shards: one
+// pass that gathers from the 2^k shards of this rank's group ((1 - 2^-k) 16A bytes over NVLink instead of k * 8A, one
+// pass over HBM instead of k). Otherwise the reference's sequence of swaps. Applying it twice restores the state.
+extern "C" int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, const uint32_t* prefixQubits, unsigned numPairs) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DfsaContext& c = dfsaCtx();
+    DFSA_REQUIRE(s && suffixQubits && prefixQubits && numPairs >= 1 && numPairs <= 4 && c.size > 1, "bad argument");
+    const unsigned L = s->logNumAmps;
+    for (unsigned i = 0; i < numPairs; i++) {
+        DFSA_REQUIRE(suffixQubits[i] < L && prefixQubits[i] >= L && prefixQubits[i] < L + s->logNumNodes, "pairs are (suffix qubit, prefix qubit)");
+        for (unsigned j = 0; j < i; j++)
+            DFSA_REQUIRE(suffixQubits[i] != suffixQubits[j] && prefixQubits[i] != prefixQubits[j], "qubits must be distinct");
+    }
+    if (numPairs == 1 || !fusedAvailable()) {
+        for (unsigned i = 0; i < numPairs; i++) {
+            const unsigned rankBit = prefixQubits[i] - L, mine = ((unsigned)c.rank >> rankBit) & 1u;
+            DFSA_TRY(dfsa_xk_swapSuffixPrefix(s, suffixQubits[i], mine ^ 1u, c.rank ^ (1 << rankBit)));
+        }
+        return DFSA_OK;
+    }
+    unsigned rho = 0;
+    for (unsigned i = 0; i < numPairs; i++) rho |= (((unsigned)c.rank >> (prefixQubits[i] - L)) & 1u) << i;
+    DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    DFSA_TRY(shmBarrier());                                          // every shard of the group is final
+    const double2* peers[16];
+    for (unsigned sigma = 0; sigma < (1u << numPairs); sigma++) {
+        int owner = c.rank;
+        for (unsigned i = 0; i < numPairs; i++) {
+            const unsigned rankBit = prefixQubits[i] - L;
+            owner = (owner & ~(1 << rankBit)) | (int)(((sigma >> i) & 1u) << rankBit);
+        }
+        double2* p = s->arr[DFSA_AMPS];
+        if (owner != c.rank) DFSA_TRY(peerArray(s, owner, DFSA_AMPS, &p));
+        peers[sigma] = p;
+    }
+    DFSA_TRY(dfsaLaunchRelocate(s, peers, suffixQubits, numPairs, rho));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    DFSA_TRY(shmBarrier());                                          // nobody still reads the shard this rank is about to retire
+    return dfsa_state_swap_arrays(s);
+}
+
 // oneQubitDepolarising on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141)
 extern "C" int dfsa_xk_depol1Prefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank) {
     DFSA_TRY(dfsaEnsureDevice());

@@ -84,6 +84,7 @@ int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRa
 int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit);   // buffer = shard after swapping suffix qubit qb with this pair's prefix qubit
 int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);    // prefix oneQubitDepolarising, buffer = result
 int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);   // prefix damping, buffer = result
+int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigned* suffixPos, unsigned k, unsigned rho);   // buffer = shard after swapping k suffix with k prefix qubits
 int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registry slots are this state's amps / buffer now
 
 // transport hooks implemented in dfsa_comm.cu

@@ -316,6 +316,30 @@ int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsig
     return launchStream<1, Amp2>(s->numAmps >> 1, ld, st);
 }
 
+// Single-shot relocation: swap k suffix qubits s_i with k prefix qubits in ONE out-of-place pass over the
+// 2^k peer shards of this rank's group, instead of k sequential suffix<->prefix swaps (distributed_statevector.hpp:213-223).
+//   buffer[j] = shard_of_rank(R with its swapped rank bits := the s-bits of j)[ j with its s-bits := R's swapped rank bits ]
+// `peers[sigma]` is that shard for s-bits sigma (this rank's own amps for sigma == rho). Pure moves: bit-exact.
+struct RelocPeers { const double2* shard[16]; };
+struct RelocBits { unsigned pos[4]; };
+
+int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigned* suffixPos, unsigned k, unsigned rho) {
+    RelocPeers table;
+    RelocBits bits;
+    uint64_t sMask = 0, rhoBits = 0;
+    for (unsigned i = 0; i < 4; i++) bits.pos[i] = i < k ? suffixPos[i] : 0u;
+    for (unsigned i = 0; i < k; i++) { sMask |= 1ULL << suffixPos[i]; rhoBits |= (uint64_t)((rho >> i) & 1u) << suffixPos[i]; }
+    for (unsigned g = 0; g < 16; g++) table.shard[g] = g < (1u << k) ? peers[g] : nullptr;
+    double2* out = s->arr[DFSA_BUFFER];
+    auto ld = [=] __device__(uint64_t j) {
+        unsigned sigma = 0;
+        for (unsigned i = 0; i < k; i++) sigma |= (unsigned)((j >> bits.pos[i]) & 1ULL) << i;
+        return Amp1{table.shard[sigma][(j & ~sMask) | rhoBits]};
+    };
+    auto st = [=] __device__(uint64_t j, const Amp1& v) { out[j] = v.a; };
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
+}
+
 // K9: distributed_statevector.hpp:133-135, 152-156
 extern "C" int dfsa_k_copyFromBuffer(dfsa_state* s, uint64_t dstStart, uint64_t srcStart, uint64_t num) {
     DFSA_TRY(dfsaEnsureDevice());

@@ -176,11 +176,15 @@ static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const 
 static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArray targets, AmpMatrix gate) {
     assert(targets.size() <= psi.logNumAmpsPerNode);
     const NatArray placed = dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets);
+    // the (suffix, prefix) qubit pairs the reference swaps one after the other before and after the local gate (:213-223);
+    // the pairs are disjoint, so they commute and go in one relocation step, which is its own inverse
+    NatArray landing, prefix;
     for (std::size_t i = 0; i < targets.size(); i++)
-        if (placed[i] != targets[i]) distributed_statevector_swapGate(psi, placed[i], targets[i]);
+        if (placed[i] != targets[i]) { landing.push_back(placed[i]); prefix.push_back(targets[i]); }
+    assert(landing.size() <= 4 && "at most 16 ranks");
+    if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
     local_statevector_manyTargGate(psi, placed, gate);
-    for (std::size_t i = 0; i < targets.size(); i++)
-        if (placed[i] != targets[i]) distributed_statevector_swapGate(psi, placed[i], targets[i]);
+    if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
 }
 
 static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi, const NatArray& targets, const NatArray& paulis, Amp thisAmpFac, Amp otherAmpFac) {

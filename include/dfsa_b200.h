@@ -117,6 +117,11 @@ int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], con
  * j stays, else the partner's amps[j ^ (1 << qb1)] read over NVLink -- then amps <-> buffer. Otherwise the reference's
  * steps: contiguous half exchange + copy (qb1 top suffix qubit) or pack + dfsa_x_exchange + unpack. */
 int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank);
+/* Relocation of manyTargGate's prefix targets (distributed_statevector.hpp:193-223): swap suffix qubit suffixQubits[i] with
+ * prefix qubit prefixQubits[i] for every i (numPairs <= 4). COLLECTIVE: every rank calls it. One pair = the fused swap above;
+ * several pairs with peer-mapped shards = one gather pass over the 2^numPairs shards of the rank's group; otherwise the
+ * reference's sequence of swaps. Its own inverse. */
+int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, const uint32_t* prefixQubits, unsigned numPairs);
 /* oneQubitDepolarising / damping on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141, :284-317):
  * pack + half exchange (one-way for damping) + combine of the reference. `bit` = this rank's bit of that qubit. With
  * peer-mapped shards: one out-of-place pass that reads the partner's half over NVLink, then amps <-> buffer. */

@@ -283,6 +283,33 @@ def test_multi_rank_circuit_matches_oracle(nodes):
         compare.assert_close(r["amps"], w, tol=1e-11, what="circuit np=%d (%s)" % (nodes, r["transport"]))
 
 
+@pytest.mark.parametrize("nodes", [4, 8])
+def test_relocation_of_several_prefix_targets_matches_oracle(nodes):
+    """manyTargGate with 2, 3 (and at 8 ranks all) rank bits among its targets: the single-shot relocation gathers from the
+    2^k shards of a rank's group in one pass (distributed_statevector.hpp:193-223 does k swaps); also through the staged
+    transport (DFSA_FUSED_EXCHANGE=0), which falls back to the sequence of swaps."""
+    rng = np.random.default_rng(900 + nodes)
+    k = nodes.bit_length() - 1
+    nq = 12
+    L = nq - k
+    jobs, wants = [], []
+    for npre in range(2, k + 1):
+        for trial in range(2):
+            prefix = [int(x) for x in rng.permutation(np.arange(L, nq))[:npre]]
+            suffix = [int(x) for x in rng.permutation(L)[: int(rng.integers(0, 3))]]
+            targets = [int(x) for x in rng.permutation(prefix + suffix)]
+            gate = cases.random_matrix(rng, 1 << len(targets)) / (1 << len(targets)) ** 0.5
+            amps = cases.random_state(rng, nq)
+            op = ("sv_manyTargGate", targets, gate)
+            o, _ = _oracle_run("sv", nq, nodes, amps, op)
+            jobs.append(dict(kind="sv", nq=nq, op=op, amps=amps))
+            wants.append(o.get_amps())
+    for env in (None, {"DFSA_FUSED_EXCHANGE": "0"}):
+        results = product.run_cases_multirank(jobs, nodes, extra_env=env)
+        for job, r, w in zip(jobs, results, wants):
+            compare.assert_close(r["amps"], w, what="relocation np=%d targets=%r (%s)" % (nodes, job["op"][1], r["transport"]))
+
+
 def test_chunk_pipelined_exchange_matches_oracle():
     """Forces the chunked exchange+combine pipeline (16 chunks even on small shards) on the NCCL transport; on a
     single-GPU box the ranks share the device, the IPC transport is used and the same results must come out."""
