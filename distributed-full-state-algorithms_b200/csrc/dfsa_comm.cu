@@ -573,6 +573,29 @@ extern "C" int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned mo
     return dfsa_k_unpack(s, &pos, 1, movingBit, half);
 }
 
+// Host-only part of the single-shot relocation: for this rank, rho = its bits of the swapped prefix qubits (bit i <-> pair i)
+// and, for every value sigma of the k landing suffix bits, the rank whose shard supplies the amplitudes that end up at
+// suffix bits sigma here: this rank with its swapped rank bits set to sigma. (After the swap, index bit s_i holds what
+// was rank bit r_i and vice versa.)
+extern "C" int dfsa_plan_relocate(int rank, unsigned logNumAmps, const uint32_t* prefixQubits, unsigned numPairs, int owners[16], unsigned* rhoOut) {
+    DFSA_REQUIRE(prefixQubits && owners && rhoOut && numPairs >= 1 && numPairs <= 4 && rank >= 0, "bad argument");
+    unsigned rho = 0;
+    for (unsigned i = 0; i < numPairs; i++) {
+        DFSA_REQUIRE(prefixQubits[i] >= logNumAmps, "not a prefix qubit");
+        rho |= (((unsigned)rank >> (prefixQubits[i] - logNumAmps)) & 1u) << i;
+    }
+    for (unsigned sigma = 0; sigma < 16; sigma++) {
+        int owner = rank;
+        for (unsigned i = 0; i < numPairs; i++) {
+            const unsigned rankBit = prefixQubits[i] - logNumAmps;
+            owner = (owner & ~(1 << rankBit)) | (int)(((sigma >> i) & 1u) << rankBit);
+        }
+        owners[sigma] = sigma < (1u << numPairs) ? owner : -1;
+    }
+    *rhoOut = rho;
+    return DFSA_OK;
+}
+
 // Relocation of manyTargGate (distributed_statevector.hpp:193-223): swap suffix qubit suffixQubits[i] with prefix qubit
 // prefixQubits[i] for all i. COLLECTIVE over all ranks. One pair: the fused swap. Several pairs with peer-mapped shards: one
 // pass that gathers from the 2^k shards of this rank's group ((1 - 2^-k) 16A bytes over NVLink instead of k * 8A, one
@@ -595,19 +618,15 @@ extern "C" int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, con
         return DFSA_OK;
     }
     unsigned rho = 0;
-    for (unsigned i = 0; i < numPairs; i++) rho |= (((unsigned)c.rank >> (prefixQubits[i] - L)) & 1u) << i;
+    int owners[16];
+    DFSA_TRY(dfsa_plan_relocate(c.rank, L, prefixQubits, numPairs, owners, &rho));
     DFSA_CUDA(cudaStreamSynchronize(c.comm));
     DFSA_CUDA(cudaStreamSynchronize(c.compute));
     DFSA_TRY(shmBarrier());                                          // every shard of the group is final
     const double2* peers[16];
     for (unsigned sigma = 0; sigma < (1u << numPairs); sigma++) {
-        int owner = c.rank;
-        for (unsigned i = 0; i < numPairs; i++) {
-            const unsigned rankBit = prefixQubits[i] - L;
-            owner = (owner & ~(1 << rankBit)) | (int)(((sigma >> i) & 1u) << rankBit);
-        }
         double2* p = s->arr[DFSA_AMPS];
-        if (owner != c.rank) DFSA_TRY(peerArray(s, owner, DFSA_AMPS, &p));
+        if (owners[sigma] != c.rank) DFSA_TRY(peerArray(s, owners[sigma], DFSA_AMPS, &p));
         peers[sigma] = p;
     }
     DFSA_TRY(dfsaLaunchRelocate(s, peers, suffixQubits, numPairs, rho));

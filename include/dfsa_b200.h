@@ -122,6 +122,10 @@ int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, in
  * several pairs with peer-mapped shards = one gather pass over the 2^numPairs shards of the rank's group; otherwise the
  * reference's sequence of swaps. Its own inverse. */
 int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, const uint32_t* prefixQubits, unsigned numPairs);
+/* Host-only (no device needed): who supplies what in the single-shot relocation -- owners[sigma] = the rank whose shard holds
+ * the amplitudes that land at suffix bits sigma (bit i of sigma <-> pair i) on `rank`, -1 beyond 2^numPairs; *rho = rank's
+ * own bits of the swapped prefix qubits. new[j] = shard(owners[sigma(j)])[j with its landing bits := rho]. */
+int dfsa_plan_relocate(int rank, unsigned logNumAmps, const uint32_t* prefixQubits, unsigned numPairs, int owners[16], unsigned* rho);
 /* oneQubitDepolarising / damping on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141, :284-317):
  * pack + half exchange (one-way for damping) + combine of the reference. `bit` = this rank's bit of that qubit. With
  * peer-mapped shards: one out-of-place pass that reads the partner's half over NVLink, then amps <-> buffer. */

@@ -2,6 +2,7 @@
 # One gpurun call's worth of checks on a 1-GPU box: parity suite, manyTarg kernel timings, configs 3-5, one ncu capture
 # of the manyTarg kernels, the contract bench line. Everything lands in gpurun_out/ (merged back by gpurun).
 # Usage: gpurun --timeout 1500 -- 'bash tools/gpu_session.sh [tag] [steps...]'   steps default: test mt configs ncu bench
+#        gpurun --gpus N ... 'NP=N bash tools/gpu_session.sh tag configs_mp bench_mp'   (torchrun, one rank per GPU)
 set -u
 TAG=${1:-s}
 shift || true
@@ -47,6 +48,14 @@ for step in $STEPS; do
     bench)
       timeout 900 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench.err
       cat $OUT/${TAG}_bench_n1.json; tail -n 5 $OUT/${TAG}_bench.err ;;
+    configs_mp)
+      timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NP:-2} --master-addr 127.0.0.1 --master-port 29531 \
+          tools/bench_configs.py --reps 2 > $OUT/${TAG}_configs_n${NP:-2}.jsonl 2> $OUT/${TAG}_configs_n${NP:-2}.err
+      cat $OUT/${TAG}_configs_n${NP:-2}.jsonl; tail -n 3 $OUT/${TAG}_configs_n${NP:-2}.err ;;
+    bench_mp)
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NP:-2} --master-addr 127.0.0.1 --master-port 29532 \
+          bench.py --gpus ${NP:-2} --steps 2 --warmup 3 > $OUT/${TAG}_bench_n${NP:-2}.json 2> $OUT/${TAG}_bench_n${NP:-2}.err
+      cat $OUT/${TAG}_bench_n${NP:-2}.json; tail -n 3 $OUT/${TAG}_bench_n${NP:-2}.err ;;
     smoke)
       timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1
       tail -n 3 $OUT/${TAG}_smoke.log ;;
