@@ -161,6 +161,31 @@ class DeviceState:
     def init_hash(self, seed):
         host_lib().dfsa_host_state_setHashAmps(self.p, C.c_ulonglong(seed))
 
+    def init_plus(self):
+        check(device_lib().dfsa_state_init_plus(self.handle))
+
+    def copy_from(self, other):
+        check(device_lib().dfsa_state_copy(self.handle, other.handle))
+
+    def set_local_amps(self, amps):
+        """This rank's shard only (no global array on the host)."""
+        a, ptr = _cplx(amps)
+        assert a.size == self.num_amps_per_node
+        check(device_lib().dfsa_state_upload(self.handle, 0, C.c_uint64(0), C.c_uint64(a.size), ptr))
+
+    def compare(self, other):
+        """On-device two-sided comparison with another state of the same shape (collective):
+        (max |delta component|, number of amplitudes that differ in value, max |component| of `other`)."""
+        d, ne, mr = C.c_double(), C.c_uint64(), C.c_double()
+        check(device_lib().dfsa_state_compare(self.handle, other.handle, C.byref(d), C.byref(ne), C.byref(mr)))
+        return d.value, int(ne.value), mr.value
+
+    def compare_hash(self, seed):
+        """The same against the state init_hash(seed) produces, regenerated on the fly."""
+        d, ne, mr = C.c_double(), C.c_uint64(), C.c_double()
+        check(device_lib().dfsa_state_compare_hash(self.handle, C.c_uint64(seed), C.byref(d), C.byref(ne), C.byref(mr)))
+        return d.value, int(ne.value), mr.value
+
     def norm2(self):
         return float(host_lib().dfsa_host_state_getNorm2(self.p))
 

@@ -41,7 +41,7 @@ struct Shm {
     volatile int      barrierCount, barrierSense;
     volatile int      idReady;
     char              ncclId[128];
-    double            reduce[MAXP][2];
+    double            reduce[MAXP][4];
     volatile uint64_t pairSeq[MAXP][MAXP];
     AllocSlot         alloc[MAXP][MAXALLOC];
     volatile int      curSlot[MAXP][MAXALLOC][2];   // [rank][state key][amps|buffer] -> registry slot currently playing that role
@@ -693,28 +693,42 @@ extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_
     });
 }
 
-extern "C" int dfsa_x_allreduce_amp(double reim[2]) {
+// Host values reduced over the ranks (n <= 4; sum in rank order -- deterministic, identical on every rank -- or max with
+// NaN propagation). Through the shared page; on the id-only NCCL bootstrap through ncclAllReduce.
+int dfsaAllreduceDoubles(double* v, int n, bool isMax) {
     DfsaContext& c = dfsaCtx();
-    DFSA_REQUIRE(reim, "null argument");
+    DFSA_REQUIRE(v && n >= 1 && n <= 4, "bad argument");
     if (c.size == 1) return DFSA_OK;
     if (g_comm.shm) {
-        // rank-ordered sum through the shared page: deterministic, identical on every rank
-        g_comm.shm->reduce[c.rank][0] = reim[0];
-        g_comm.shm->reduce[c.rank][1] = reim[1];
+        for (int i = 0; i < n; i++) g_comm.shm->reduce[c.rank][i] = v[i];
         DFSA_TRY(shmBarrier());
-        double re = 0.0, im = 0.0;
-        for (int r = 0; r < c.size; r++) { re += g_comm.shm->reduce[r][0]; im += g_comm.shm->reduce[r][1]; }
+        double acc[4];
+        for (int i = 0; i < n; i++) {
+            acc[i] = g_comm.shm->reduce[0][i];
+            for (int r = 1; r < c.size; r++) {
+                const double x = g_comm.shm->reduce[r][i];
+                if (!isMax) acc[i] += x;
+                else if (x != x || acc[i] != acc[i]) acc[i] = x != x ? x : acc[i];
+                else if (x > acc[i]) acc[i] = x;
+            }
+        }
         DFSA_TRY(shmBarrier());
-        reim[0] = re; reim[1] = im;
+        for (int i = 0; i < n; i++) v[i] = acc[i];
         return DFSA_OK;
     }
     double2* scratch;
     DFSA_TRY(dfsaScratch(64, &scratch));
-    DFSA_CUDA(cudaMemcpyAsync(scratch, reim, 16, cudaMemcpyHostToDevice, c.comm));
-    DFSA_NCCL(ncclAllReduce(scratch, scratch, 2, ncclDouble, ncclSum, g_comm.nccl, c.comm));
-    DFSA_CUDA(cudaMemcpyAsync(reim, scratch, 16, cudaMemcpyDeviceToHost, c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    DFSA_CUDA(cudaMemcpyAsync(scratch, v, n * sizeof(double), cudaMemcpyHostToDevice, c.comm));
+    DFSA_NCCL(ncclAllReduce(scratch, scratch, n, ncclDouble, isMax ? ncclMax : ncclSum, g_comm.nccl, c.comm));
+    DFSA_CUDA(cudaMemcpyAsync(v, scratch, n * sizeof(double), cudaMemcpyDeviceToHost, c.comm));
     DFSA_CUDA(cudaStreamSynchronize(c.comm));
     return DFSA_OK;
+}
+
+extern "C" int dfsa_x_allreduce_amp(double reim[2]) {
+    DFSA_REQUIRE(reim, "null argument");
+    return dfsaAllreduceDoubles(reim, 2, false);
 }
 
 // getAllVecAmps (tests/test_utilities.hpp:419-435): every rank ends up with the whole state in host memory

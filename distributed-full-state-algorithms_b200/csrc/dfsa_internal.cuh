@@ -91,6 +91,7 @@ int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registr
 int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc
 int dfsaUnregisterAllocation(int id);
 int dfsaHostBarrier();                                             // inter-rank barrier without touching streams
+int dfsaAllreduceDoubles(double* v, int n, bool isMax);            // n <= 4 host values: rank-ordered sum, or max (NaN propagates)
 
 // ------------------------------------------------------------------------------------------------ device helpers
 

@@ -2,6 +2,7 @@
 // Replaces the std::vector storage of the reference's StateVector/DensityMatrix (src/states.hpp:13-69):
 // each rank's amplitude shard and its equal-size exchange buffer are plain cudaMalloc regions in HBM.
 #include <stdarg.h>
+#include <math.h>
 #include <string.h>
 #include <vector>
 
@@ -296,6 +297,100 @@ extern "C" int dfsa_state_init_hash(dfsa_state* s, uint64_t seed) {
     auto ld = [=] __device__(uint64_t j) { return Amp1{make_double2(hashReal(seed, 2 * (first + j)), hashReal(seed, 2 * (first + j) + 1))}; };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { amps[j] = v.a; };
     return launchStream<2, Amp1>(s->numAmps, ld, st);
+}
+
+extern "C" int dfsa_state_init_plus(dfsa_state* s) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    double2* amps = s->arr[0];
+    // |+>^n: 2^(-n/2) everywhere; as a density matrix |+><+|^N: 2^(-N) everywhere (both exact powers of two for even n)
+    const double v = s->isDensity ? ldexp(1.0, -(int)s->numQubits) : pow(2.0, -0.5 * s->numQubits);
+    auto ld = [=] __device__(uint64_t) { return Amp1{make_double2(v, 0.0)}; };
+    auto st = [=] __device__(uint64_t j, const Amp1& a) { amps[j] = a.a; };
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
+}
+
+extern "C" int dfsa_state_copy(dfsa_state* dst, const dfsa_state* src) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(dst && src && dst->numAmps == src->numAmps && dst->isDensity == src->isDensity, "states must have the same shape");
+    DFSA_CUDA(cudaMemcpyAsync(dst->arr[0], src->arr[0], src->numAmps * sizeof(double2), cudaMemcpyDeviceToDevice, g_ctx.compute));
+    return DFSA_OK;
+}
+
+// On-device comparator (the reference's agreesWith gathers both states to every rank's host, test_utilities.hpp:470-487):
+// per block {max |delta component|, max |reference component|, number of unequal amplitudes, NaN seen}; the reference side is
+// either a second shard or the hash state regenerated on the fly.
+struct CmpPartial { double maxDiff, maxRef, unequal, nan; };
+
+template <bool HASH>
+__global__ void __launch_bounds__(256) compareKernel(const double2* __restrict__ a, const double2* __restrict__ b, uint64_t n, uint64_t seed,
+                                                    uint64_t first, CmpPartial* partials) {
+    double md = 0.0, mr = 0.0;
+    unsigned long long ne = 0;
+    unsigned nan = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 x = a[i];
+        double2 y;
+        if (HASH) y = make_double2(hashReal(seed, 2 * (first + i)), hashReal(seed, 2 * (first + i) + 1));
+        else y = b[i];
+        const double dx = fabs(x.x - y.x), dy = fabs(x.y - y.y);
+        nan |= (dx != dx) | (dy != dy);
+        md = fmax(md, fmax(dx, dy));
+        mr = fmax(mr, fmax(fabs(y.x), fabs(y.y)));
+        ne += (x.x != y.x) | (x.y != y.y);
+    }
+    __shared__ CmpPartial w[8];
+    double ned = (double)ne, nand = (double)nan;
+    for (int off = 16; off > 0; off >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, off));
+        mr = fmax(mr, __shfl_xor_sync(0xffffffffu, mr, off));
+        ned += __shfl_xor_sync(0xffffffffu, ned, off);
+        nand += __shfl_xor_sync(0xffffffffu, nand, off);
+    }
+    if ((threadIdx.x & 31) == 0) w[threadIdx.x >> 5] = CmpPartial{md, mr, ned, nand};
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        CmpPartial t = w[0];
+        for (int k = 1; k < 8; k++) { t.maxDiff = fmax(t.maxDiff, w[k].maxDiff); t.maxRef = fmax(t.maxRef, w[k].maxRef); t.unequal += w[k].unequal; t.nan += w[k].nan; }
+        partials[blockIdx.x] = t;
+    }
+}
+
+static int compareImpl(dfsa_state* a, const double2* b, bool hash, uint64_t seed, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef) {
+    DFSA_REQUIRE(maxAbsDiff && numUnequal, "null output");
+    const unsigned grid = dfsaGrid(a->numAmps, 256, 4, 8);
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(grid * sizeof(CmpPartial), &scratch));
+    CmpPartial* dev = (CmpPartial*)scratch;
+    const uint64_t first = (uint64_t)a->rank << a->logNumAmps;
+    if (hash) compareKernel<true><<<grid, 256, 0, g_ctx.compute>>>(a->arr[0], nullptr, a->numAmps, seed, first, dev);
+    else compareKernel<false><<<grid, 256, 0, g_ctx.compute>>>(a->arr[0], b, a->numAmps, 0, first, dev);
+    DFSA_LAUNCH_CHECK();
+    std::vector<CmpPartial> host(grid);
+    DFSA_CUDA(cudaMemcpyAsync(host.data(), dev, grid * sizeof(CmpPartial), cudaMemcpyDeviceToHost, g_ctx.compute));
+    DFSA_CUDA(cudaStreamSynchronize(g_ctx.compute));
+    double mx[2] = {0.0, 0.0}, sums[2] = {0.0, 0.0};
+    for (const CmpPartial& p : host) { mx[0] = fmax(mx[0], p.maxDiff); mx[1] = fmax(mx[1], p.maxRef); sums[0] += p.unequal; sums[1] += p.nan; }
+    if (g_ctx.size > 1) {
+        DFSA_TRY(dfsaAllreduceDoubles(mx, 2, true));
+        DFSA_TRY(dfsaAllreduceDoubles(sums, 2, false));
+    }
+    *maxAbsDiff = sums[1] > 0.0 ? nan("") : mx[0];
+    *numUnequal = (uint64_t)sums[0];
+    if (maxAbsRef) *maxAbsRef = mx[1];
+    return DFSA_OK;
+}
+
+extern "C" int dfsa_state_compare(dfsa_state* a, dfsa_state* b, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(a && b && a->numAmps == b->numAmps && a->isDensity == b->isDensity, "states must have the same shape");
+    return compareImpl(a, b->arr[0], false, 0, maxAbsDiff, numUnequal, maxAbsRef);
+}
+
+extern "C" int dfsa_state_compare_hash(dfsa_state* s, uint64_t seed, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s, "null state");
+    return compareImpl(s, nullptr, true, seed, maxAbsDiff, numUnequal, maxAbsRef);
 }
 
 // sum |amp|^2 : block partials -> host sum (deterministic order)

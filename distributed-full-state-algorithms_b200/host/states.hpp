@@ -89,6 +89,17 @@ public:
         return true;
     }
     Real getNorm2() { double n = 0; DFSA_CHECK(dfsa_state_norm2(handle, &n)); return n; }
+    // device-resident utilities: nothing is gathered to the host
+    void setPlusAmps() { DFSA_CHECK(dfsa_state_init_plus(handle)); }
+    void copyAmpsFrom(StateVector& other) { DFSA_CHECK(dfsa_state_copy(handle, other.handle)); }
+    // max over all amplitudes and ranks of |delta re|, |delta im| (NaN if any NaN); numUnequal counts == mismatches
+    Real getMaxDifference(StateVector& other, Index* numUnequal = nullptr) {
+        double d = 0; uint64_t ne = 0;
+        DFSA_CHECK(dfsa_state_compare(handle, other.handle, &d, &ne, nullptr));
+        if (numUnequal) *numUnequal = ne;
+        return d;
+    }
+    bool agreesWith(StateVector& other, Real tol = 1E-5) { Real d = getMaxDifference(other); return d <= tol; }
 
 protected:
     StateVector() = default;

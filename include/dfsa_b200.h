@@ -95,6 +95,16 @@ int dfsa_state_upload_all(dfsa_state* s, const double* hostAll);  /* each rank k
 int dfsa_state_init_zero(dfsa_state* s);
 int dfsa_state_init_hash(dfsa_state* s, uint64_t seed);           /* synthetic state, SURVEY 8(d) */
 int dfsa_state_norm2(dfsa_state* s, double* out);                 /* sum |amp|^2 over all ranks */
+/* Device-resident test utilities (the reference's are host loops over gathered copies,
+ * tests/test_utilities.hpp:419-524). All collective, results identical on every rank. */
+int dfsa_state_init_plus(dfsa_state* s);                          /* every amplitude = 2^(-n/2) (sv) or 2^(-N) (dm: |+><+|) */
+int dfsa_state_copy(dfsa_state* dst, const dfsa_state* src);      /* dst.amps = src.amps (same shape) */
+/* agreesWith (test_utilities.hpp:470-487) without leaving the device, two-sided: *maxAbsDiff = max over all amplitudes and
+ * ranks of max(|re a - re b|, |im a - im b|) (NaN anywhere -> NaN), *numUnequal = how many amplitudes differ in value
+ * (== on both doubles, so +0 == -0: the bit-exact criterion of SURVEY 8c), *maxAbsRef = max |component| of b. */
+int dfsa_state_compare(dfsa_state* a, dfsa_state* b, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef);
+/* the same against the synthetic state dfsa_state_init_hash(seed) would produce, regenerated on the fly (no second shard) */
+int dfsa_state_compare_hash(dfsa_state* s, uint64_t seed, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef);
 
 /* ---- pairwise exchange: src/communication.hpp:77-164 ---------------------------------------------------- */
 /* comm_exchangeArrays(toSend, sendStart, toReceive, recvStart, num, pairRank): both partners call it with the
