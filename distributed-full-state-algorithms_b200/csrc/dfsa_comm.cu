@@ -9,6 +9,7 @@
 //           tests run on a single-GPU box; it is also the groundwork for the fused remote-load kernels.
 // Host side channel: one POSIX shared-memory page set (barrier, NCCL id, IPC handle registry, reduce slots).
 #include <errno.h>
+#include <stddef.h>
 #include <fcntl.h>
 #include <map>
 #include <nccl.h>
@@ -45,6 +46,16 @@ struct Shm {
     volatile uint64_t pairSeq[MAXP][MAXP];
     AllocSlot         alloc[MAXP][MAXALLOC];
     volatile int      curSlot[MAXP][MAXALLOC][2];   // [rank][state key][amps|buffer] -> registry slot currently playing that role
+    // stream-ordered signalling between the ranks' compute streams (no host synchronisation around a fused exchange):
+    volatile uint64_t progress[MAXP];               // written BY THE DEVICE (stream memory op): rank r's compute stream has reached ticket progress[r]
+    volatile uint64_t ticket[MAXP][MAXP][2];        // written by the host: ticket[r][p][n & 1] = r's "ready" ticket of its n-th rendezvous with p
+    volatile int      ticketSlot[MAXP][MAXP][2];    // ... and the registry slot of the array r offers for reading in that rendezvous
+    volatile int      device[MAXP];                 // CUDA device of each rank
+    volatile int      peerOk[MAXP];                 // rank r can map every other rank's shards (peer access / same device)
+    volatile int      signalOk[MAXP];               // rank r has stream memory ops on the shared page
+    // expecPauliString: each rank's partial sum lands here straight from its reduction kernel, flag = sequence number
+    volatile double   expecVal[2][MAXP][2];
+    volatile uint64_t expecFlag[2][MAXP];
 };
 
 struct CommState {
@@ -59,6 +70,14 @@ struct CommState {
     void*       localPtr[MAXALLOC] = {};
     std::map<std::pair<int, int>, void*> peerMap;   // (rank, slot) -> mapped device pointer
     uint64_t    pairCount[MAXP] = {};
+    // stream-ordered signalling
+    bool        signals = false;                    // every rank can wait on / write to the shared page from its stream
+    bool        peersOk = false;                    // every rank can map every other rank's shards
+    int         fusedOverride = -1;                 // dfsa_comm_set_fused: -1 = environment decides
+    void*       shmDev = nullptr;                   // device address of the shared page (cudaHostRegister)
+    bool        shmRegistered = false;
+    uint64_t    myTicket = 0;                       // last ticket this rank posted on its compute stream
+    uint64_t    expecSeq = 0;
 };
 
 CommState g_comm;
@@ -131,8 +150,13 @@ int pairBarrier(int pair) {
     return DFSA_OK;
 }
 
+size_t shmBytes() {
+    const size_t page = (size_t)sysconf(_SC_PAGESIZE);
+    return (sizeof(Shm) + page - 1) / page * page;
+}
+
 int mapShm(const char* name, bool create, int size) {
-    size_t bytes = sizeof(Shm);
+    size_t bytes = shmBytes();
     int fd = -1;
     if (create) {
         shm_unlink(name);
@@ -165,6 +189,78 @@ int mapShm(const char* name, bool create, int size) {
             napBriefly();
             if (spins > 1200000) { dfsaSetError("shared segment %s never became ready", name); return DFSA_ERR_COMM; }
         }
+    }
+    return DFSA_OK;
+}
+
+// ---- stream memory operations (driver API through the runtime's entry-point lookup: no link dependency on libcuda)
+typedef int (*StreamValueFn)(cudaStream_t, unsigned long long /*CUdeviceptr*/, unsigned long long /*value*/, unsigned int /*flags*/);
+StreamValueFn g_streamWrite64 = nullptr, g_streamWait64 = nullptr;
+
+bool loadStreamMemOps() {
+    if (g_streamWrite64 && g_streamWait64) return true;
+    void *w = nullptr, *q = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &w, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return false;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &q, cudaEnableDefault, &st) != cudaSuccess || st != cudaDriverEntryPointSuccess) return false;
+    g_streamWrite64 = (StreamValueFn)w;
+    g_streamWait64 = (StreamValueFn)q;
+    return w && q;
+}
+
+inline unsigned long long progressDevAddr(int rank) {
+    return (unsigned long long)((char*)g_comm.shmDev + offsetof(Shm, progress) + sizeof(uint64_t) * (size_t)rank);
+}
+
+// "everything enqueued on my compute stream so far is done" becomes visible to the other ranks as progress[me] >= ticket
+int postTicket(uint64_t* ticketOut) {
+    DfsaContext& c = dfsaCtx();
+    const uint64_t t = ++g_comm.myTicket;
+    if (g_streamWrite64(c.compute, progressDevAddr(c.rank), t, 0 /*CU_STREAM_WRITE_VALUE_DEFAULT: fenced*/) != 0) {
+        dfsaSetError("cuStreamWriteValue64 failed");
+        return DFSA_ERR_CUDA;
+    }
+    *ticketOut = t;
+    return DFSA_OK;
+}
+
+// my compute stream goes no further until rank `peer`'s stream has reached `ticket`
+int awaitTicket(int peer, uint64_t ticket) {
+    if (g_streamWait64(dfsaCtx().compute, progressDevAddr(peer), ticket, 0 /*CU_STREAM_WAIT_VALUE_GEQ*/) != 0) {
+        dfsaSetError("cuStreamWaitValue64 failed");
+        return DFSA_ERR_CUDA;
+    }
+    return DFSA_OK;
+}
+
+// Host rendezvous with a set of peers (no stream is touched): publish my ticket to each, then collect theirs. Everybody posts
+// before anybody waits, so any set of mutually consistent groups is deadlock-free. Slots are double-buffered by the parity
+// of the pair's rendezvous count: a slot is rewritten two rendezvous later, which the peer only lets happen after reading it.
+int exchangeTickets(const int* peers, int n, uint64_t mine, int mySlot, uint64_t* theirs, int* theirSlots) {
+    Shm* m = g_comm.shm;
+    DfsaContext& c = dfsaCtx();
+    uint64_t count[MAXP];
+    for (int i = 0; i < n; i++) {
+        const int p = peers[i];
+        count[i] = ++g_comm.pairCount[p];
+        m->ticket[c.rank][p][count[i] & 1] = mine;
+        m->ticketSlot[c.rank][p][count[i] & 1] = mySlot;
+        __sync_synchronize();
+        m->pairSeq[c.rank][p] = count[i];
+    }
+    const double t0 = nowSeconds();
+    for (int i = 0; i < n; i++) {
+        const int p = peers[i];
+        uint64_t spins = 0;
+        while (m->pairSeq[p][c.rank] < count[i]) {
+            if (++spins > 2000) {
+                napBriefly();
+                if ((spins & 1023) == 0 && nowSeconds() - t0 > commTimeoutSeconds()) { dfsaSetError("rendezvous with rank %d timed out", p); return DFSA_ERR_COMM; }
+            }
+        }
+        __sync_synchronize();
+        theirs[i] = m->ticket[p][c.rank][count[i] & 1];
+        theirSlots[i] = m->ticketSlot[p][c.rank][count[i] & 1];
     }
     return DFSA_OK;
 }
@@ -209,6 +305,35 @@ int finishInit() {
     } else {
         c.transport = Transport::Ipc;
     }
+    // Capabilities every rank must have for the fused remote-load kernels, agreed collectively so that all ranks take the same
+    // path: (a) this rank can map every other rank's shards (same device, or peer access between the two GPUs), (b) stream
+    // memory operations on the shared page (stream-ordered signalling; without them the fused kernels are host-synchronised).
+    Shm* m = g_comm.shm;
+    m->device[c.rank] = c.device;
+    DFSA_TRY(shmBarrier());
+    int ok = 1;
+    for (int r = 0; r < c.size && ok; r++) {
+        if (r == c.rank || m->device[r] == c.device) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c.device, m->device[r]) != cudaSuccess || !can) ok = 0;
+    }
+    cudaGetLastError();
+    m->peerOk[c.rank] = ok;
+    int sig = 0;
+    const char* noSig = getenv("DFSA_STREAM_SIGNALS");
+    if (!(noSig && atoi(noSig) == 0) && loadStreamMemOps()) {
+        const size_t page = (size_t)sysconf(_SC_PAGESIZE), bytes = (sizeof(Shm) + page - 1) / page * page;
+        if (cudaHostRegister((void*)m, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess) {
+            g_comm.shmRegistered = true;
+            if (cudaHostGetDevicePointer(&g_comm.shmDev, (void*)m, 0) == cudaSuccess && g_comm.shmDev) sig = 1;
+        }
+        cudaGetLastError();
+    }
+    m->signalOk[c.rank] = sig;
+    DFSA_TRY(shmBarrier());
+    g_comm.peersOk = g_comm.signals = true;
+    for (int r = 0; r < c.size; r++) { g_comm.peersOk = g_comm.peersOk && m->peerOk[r]; g_comm.signals = g_comm.signals && m->signalOk[r]; }
+    g_comm.myTicket = 0;
     return shmBarrier();
 }
 
@@ -226,11 +351,28 @@ extern "C" int dfsa_comm_init(void) {
         c.size = atoi(ws);
         c.rank = atoi(rk);
         if (c.size > MAXP) { dfsaSetError("at most %d ranks", MAXP); return DFSA_ERR_ARG; }
+        // One node, at most MAXP ranks: the side channel is a POSIX shared-memory segment and the fused kernels read peer
+        // shards over NVLink. A launcher that spreads the job over several hosts is refused here instead of hanging.
+        const char* lws = getenv("LOCAL_WORLD_SIZE");
+        if (lws && atoi(lws) != c.size) {
+            dfsaSetError("WORLD_SIZE=%d but LOCAL_WORLD_SIZE=%s: libdfsa_b200 runs the ranks of ONE node (multi-node needs dfsa_comm_init_with_id and the staged NCCL transport)", c.size, lws);
+            return DFSA_ERR_COMM;
+        }
+        // Segment name: DFSA_JOB_ID if given, else the rendezvous the launcher already agreed on (MASTER_ADDR:MASTER_PORT) --
+        // identical on every rank whatever process spawned it (srun / mpirun wrappers give each rank its own parent).
         const char* job = getenv("DFSA_JOB_ID");
         const char* port = getenv("MASTER_PORT");
-        char name[128];
+        const char* addr = getenv("MASTER_ADDR");
+        char name[160];
         if (job) snprintf(name, sizeof(name), "/dfsa_%s", job);
-        else snprintf(name, sizeof(name), "/dfsa_%d_%s", (int)getppid(), port ? port : "0");
+        else if (port) {
+            unsigned h = 2166136261u;
+            for (const char* q = addr ? addr : ""; *q; q++) h = (h ^ (unsigned char)*q) * 16777619u;
+            snprintf(name, sizeof(name), "/dfsa_%08x_%s_u%d", h, port, (int)getuid());
+        } else {
+            dfsaSetError("RANK/WORLD_SIZE are set but neither DFSA_JOB_ID nor MASTER_PORT: the ranks cannot agree on a shared segment");
+            return DFSA_ERR_COMM;
+        }
         g_comm.shmName = name;
         g_comm.shmOwner = (c.rank == 0);
         DFSA_TRY(mapShm(name, c.rank == 0, c.size));
@@ -239,9 +381,9 @@ extern "C" int dfsa_comm_init(void) {
         if (c.compute) { dfsaSetError("dfsa_comm_init with DFSA_NP must be the first CUDA-touching call"); return DFSA_ERR_COMM; }
         c.size = atoi(np);
         if (c.size > MAXP) { dfsaSetError("at most %d ranks", MAXP); return DFSA_ERR_ARG; }
-        void* mem = mmap(nullptr, sizeof(Shm), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        void* mem = mmap(nullptr, shmBytes(), PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
         if (mem == MAP_FAILED) { dfsaSetError("mmap failed: %s", strerror(errno)); return DFSA_ERR_COMM; }
-        memset(mem, 0, sizeof(Shm));
+        memset(mem, 0, shmBytes());
         g_comm.shm = (Shm*)mem;
         g_comm.shm->size = c.size;
         g_comm.shm->magic = SHM_MAGIC;
@@ -318,13 +460,22 @@ extern "C" int dfsa_comm_finalize(void) {
     DFSA_TRY(dfsaPoolDrain());                                // recycled shards: unregister (collective) and free
     for (auto& kv : g_comm.peerMap) cudaIpcCloseMemHandle(kv.second);
     g_comm.peerMap.clear();
+    // nobody may free a shard (states destroyed after comm_end skip the collective unregister) while a slower rank still
+    // holds a mapping of it
+    DFSA_TRY(dfsaHostBarrier());
     if (g_comm.nccl) { ncclCommDestroy(g_comm.nccl); g_comm.nccl = nullptr; }
+    if (g_comm.shmRegistered) { cudaHostUnregister((void*)g_comm.shm); g_comm.shmRegistered = false; }
     if (g_comm.forked) {
         fflush(stdout);
         if (c.rank != 0) _exit(0);                            // children never run the caller's epilogue
         for (pid_t pid : g_comm.children) { int st; waitpid(pid, &st, 0); }
     }
-    if (g_comm.shm && g_comm.shmOwner) shm_unlink(g_comm.shmName.c_str());
+    if (g_comm.shm) {
+        if (g_comm.shmOwner) shm_unlink(g_comm.shmName.c_str());
+        munmap((void*)g_comm.shm, shmBytes());
+    }
+    // a later comm_init starts from a clean slate (fresh segment, fresh counters)
+    g_comm = CommState();
     c.initialised = false;
     c.size = 1; c.rank = 0; c.transport = Transport::Single;
     return DFSA_OK;
@@ -519,23 +670,71 @@ double2 dfsaPowIHost(unsigned k);
 // [kernel done] pair barrier [swap amps<->buffer]. The second barrier keeps a partner from overwriting the shard this
 // rank is still reading. DFSA_FUSED_EXCHANGE=0 falls back to the staged NCCL / copy-engine path.
 static bool fusedAvailable() {
-    static int on = -1;
-    if (on < 0) { const char* e = getenv("DFSA_FUSED_EXCHANGE"); on = (e && atoi(e) == 0) ? 0 : 1; }
-    return on == 1 && g_comm.shm != nullptr;
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("DFSA_FUSED_EXCHANGE"); env = (e && atoi(e) == 0) ? 0 : 1; }
+    const int on = g_comm.fusedOverride >= 0 ? g_comm.fusedOverride : env;
+    // the side channel exists (ranks share a node) AND every rank can map every other rank's shards; otherwise the staged
+    // NCCL / copy-engine path is used -- decided collectively at init, so all ranks agree
+    return on == 1 && g_comm.shm != nullptr && g_comm.peersOk;
+}
+
+// Collective: switch between the fused remote-load kernels (1), the staged pack / exchange / combine path (0), or back to
+// what DFSA_FUSED_EXCHANGE says (-1). bench.py's self-check runs the same circuit both ways.
+extern "C" int dfsa_comm_set_fused(int mode) {
+    DFSA_REQUIRE(mode >= -1 && mode <= 1, "mode is -1, 0 or 1");
+    DFSA_TRY(dfsa_comm_barrier());
+    g_comm.fusedOverride = mode;
+    return DFSA_OK;
+}
+extern "C" int dfsa_comm_fused_active(void) { return fusedAvailable() ? (g_comm.signals ? 2 : 1) : 0; }
+
+// One fused step with the ranks in `peers` (the partner of a pairwise op; the 2^k - 1 other members of a relocation or
+// quad-depolarising group): launch(remote[i] = peers[i]'s current amplitude array) must write this rank's `buffer`;
+// afterwards amps <-> buffer. Ordering, all on the compute streams (stream memory operations on the shared page):
+//   [my earlier kernels] -> post READY -> wait every peer's READY -> kernel -> post DONE -> wait every peer's DONE
+// so a peer's shard is final before it is read and is not overwritten (it becomes that peer's buffer) while it is being read.
+// The hosts only meet to trade ticket numbers and array slots (a few shared-memory words), never to drain a stream, so
+// consecutive gates pipeline. Without stream memory ops: the same steps with host synchronisation (round-1 protocol).
+static int peerPointer(int pair, int slot, double2** out);
+
+static int swapArraysAfter(dfsa_state* s) { return dfsa_state_swap_arrays(s); }
+
+template <class Launch, class After>
+static int fusedGroupExchange(dfsa_state* s, const int* peers, int n, Launch launch, After after) {
+    DfsaContext& c = dfsaCtx();
+    const double2* remote[MAXP];
+    if (g_comm.signals) {
+        // transfers of the staged path run on the comm stream; the compute stream is already ordered after them (transfer())
+        // (the array a peer offers travels with its ticket: by the time this rank looks, a faster peer may already have
+        // finished the step and swapped its arrays, so the registry's "current" slot would be the wrong one)
+        uint64_t ready = 0, theirs[MAXP];
+        int theirSlots[MAXP];
+        DFSA_TRY(postTicket(&ready));
+        DFSA_TRY(exchangeTickets(peers, n, ready, s->allocId[DFSA_AMPS], theirs, theirSlots));
+        for (int i = 0; i < n; i++) DFSA_TRY(awaitTicket(peers[i], theirs[i]));
+        for (int i = 0; i < n; i++) { double2* p; DFSA_TRY(peerPointer(peers[i], theirSlots[i], &p)); remote[i] = p; }
+        DFSA_TRY(launch(remote));
+        uint64_t done = 0;
+        DFSA_TRY(postTicket(&done));                               // == ready + 1 on every rank: nothing else posts in between
+        for (int i = 0; i < n; i++) DFSA_TRY(awaitTicket(peers[i], theirs[i] + 1));
+        return after(s);
+    }
+    DFSA_CUDA(cudaStreamSynchronize(c.comm));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    for (int i = 0; i < n; i++) DFSA_TRY(pairBarrier(peers[i]));
+    for (int i = 0; i < n; i++) { double2* p; DFSA_TRY(peerArray(s, peers[i], DFSA_AMPS, &p)); remote[i] = p; }
+    DFSA_TRY(launch(remote));
+    DFSA_CUDA(cudaStreamSynchronize(c.compute));
+    for (int i = 0; i < n; i++) DFSA_TRY(pairBarrier(peers[i]));
+    return after(s);
 }
 
 template <class Launch>
+static int fusedGroupExchange(dfsa_state* s, const int* peers, int n, Launch launch) { return fusedGroupExchange(s, peers, n, launch, swapArraysAfter); }
+
+template <class Launch>
 static int fusedExchange(dfsa_state* s, int pairRank, Launch launch) {
-    DfsaContext& c = dfsaCtx();
-    DFSA_CUDA(cudaStreamSynchronize(c.comm));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));
-    DFSA_TRY(pairBarrier(pairRank));
-    double2* remote;
-    DFSA_TRY(peerArray(s, pairRank, DFSA_AMPS, &remote));
-    DFSA_TRY(launch(remote));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));
-    DFSA_TRY(pairBarrier(pairRank));
-    return dfsa_state_swap_arrays(s);
+    return fusedGroupExchange(s, &pairRank, 1, [&](const double2* const* remote) { return launch(remote[0]); });
 }
 
 extern "C" int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], const double f1[2]) {
@@ -620,19 +819,16 @@ extern "C" int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, con
     unsigned rho = 0;
     int owners[16];
     DFSA_TRY(dfsa_plan_relocate(c.rank, L, prefixQubits, numPairs, owners, &rho));
-    DFSA_CUDA(cudaStreamSynchronize(c.comm));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));
-    DFSA_TRY(shmBarrier());                                          // every shard of the group is final
-    const double2* peers[16];
+    int peers[16], slotOf[16], n = 0;
     for (unsigned sigma = 0; sigma < (1u << numPairs); sigma++) {
-        double2* p = s->arr[DFSA_AMPS];
-        if (owners[sigma] != c.rank) DFSA_TRY(peerArray(s, owners[sigma], DFSA_AMPS, &p));
-        peers[sigma] = p;
+        slotOf[sigma] = -1;
+        if (owners[sigma] != c.rank) { slotOf[sigma] = n; peers[n++] = owners[sigma]; }
     }
-    DFSA_TRY(dfsaLaunchRelocate(s, peers, suffixQubits, numPairs, rho));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));
-    DFSA_TRY(shmBarrier());                                          // nobody still reads the shard this rank is about to retire
-    return dfsa_state_swap_arrays(s);
+    return fusedGroupExchange(s, peers, n, [&](const double2* const* remote) {
+        const double2* shards[16];
+        for (unsigned sigma = 0; sigma < (1u << numPairs); sigma++) shards[sigma] = slotOf[sigma] < 0 ? s->arr[DFSA_AMPS] : remote[slotOf[sigma]];
+        return dfsaLaunchRelocate(s, shards, suffixQubits, numPairs, rho);
+    });
 }
 
 // oneQubitDepolarising on a qubit whose bra bit is a rank bit (distributed_densitymatrix.hpp:110-141)
@@ -668,6 +864,64 @@ extern "C" int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, d
         DFSA_TRY(dfsa_k_dampingPrefix(s, qb, bit, prob, 2));
     }
     return DFSA_OK;     // the reference needs a global barrier here to protect the sender's buffer; stream order does that job
+}
+
+// manyCtrlOneTargGate, prefix target + suffix controls (distributed_statevector.hpp:43-78)
+extern "C" int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls, unsigned numCtrls, int pairRank, const double f0[2], const double f1[2]) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && suffixCtrls && f0 && f1 && numCtrls >= 1 && numCtrls <= s->logNumAmps, "bad argument");
+    const uint64_t m = s->numAmps >> numCtrls, allOnes = (1ULL << numCtrls) - 1ULL;
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, m, m, pairRank));
+    if (fusedAvailable()) {
+        BitSpec spec;
+        uint64_t ones;
+        for (unsigned q = 1; q < numCtrls; q++) DFSA_REQUIRE(suffixCtrls[q] > suffixCtrls[q - 1], "controls must be strictly increasing");
+        DFSA_TRY(sortedSpec(suffixCtrls, numCtrls, s->logNumAmps, &spec, &ones));
+        const double2 c0 = make_double2(f0[0], f0[1]), c1 = make_double2(f1[0], f1[1]);
+        return fusedGroupExchange(s, &pairRank, 1,
+            [&](const double2* const* remote) { return dfsaLaunchFusedCombineSub(s, remote[0], spec, ones, c0, c1); },
+            [&](dfsa_state* st) { return dfsa_k_unpack(st, suffixCtrls, numCtrls, allOnes, 0); });      // both ranks are done reading: results go home
+    }
+    DFSA_TRY(dfsa_k_pack(s, suffixCtrls, numCtrls, allOnes, 0));
+    DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, m, m, pairRank, true, true));
+    return dfsa_k_combineSub(s, suffixCtrls, numCtrls, allOnes, m, f0, f1);
+}
+
+// twoQubitDepolarising, qb1 suffix / qb2 prefix (distributed_densitymatrix.hpp:146-183)
+extern "C" int dfsa_xk_depol2Pair(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit, double prob, int corrected, int pairRank) {
+    DFSA_TRY(dfsaEnsureDevice());
+    const uint64_t eighth = s ? s->numAmps >> 3 : 0;
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, eighth, eighth, pairRank));
+    DFSA_REQUIRE(s->isDensity && qb1 < qb2 && qb2 < s->numQubits && qb2 >= s->numQubits - s->logNumNodes && qb1 < s->numQubits - s->logNumNodes,
+                 "needs a density matrix, qb1 suffix and qb2 prefix");
+    const unsigned N = s->numQubits;
+    if (fusedAvailable())
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedDepol2Pair(s, remote, qb1, qb2, qb1 + N, bit, prob, corrected != 0); });
+    const int flag = corrected ? DFSA_DEPOL2_CORRECTED : 0;
+    DFSA_TRY(dfsa_k_depol2Pair(s, qb1, qb2, qb1 + N, bit, prob, 0 | flag));
+    DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, eighth, eighth, pairRank, true, true));
+    return dfsa_k_depol2Pair(s, qb1, qb2, qb1 + N, bit, prob, 1 | flag);
+}
+
+// twoQubitDepolarising, both qubits prefix (distributed_densitymatrix.hpp:187-237): pairRank0 / pairRank1 differ from this rank
+// in the bra bit of qb1 / qb2
+extern "C" int dfsa_xk_depol2Quad(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit0, unsigned bit1, double prob, int corrected, int pairRank0, int pairRank1) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DfsaContext& c = dfsaCtx();
+    const uint64_t quarter = s ? s->numAmps >> 2 : 0;
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, quarter, quarter, pairRank0));
+    DFSA_TRY(checkXArgs(s, DFSA_BUFFER, 0, DFSA_BUFFER, quarter, quarter, pairRank1));
+    DFSA_REQUIRE(s->isDensity && qb1 < qb2 && qb2 < s->numQubits && qb1 >= s->numQubits - s->logNumNodes, "needs a density matrix and two prefix qubits");
+    if (fusedAvailable()) {
+        const int peers[3] = {pairRank0, pairRank1, pairRank0 ^ pairRank1 ^ c.rank};
+        return fusedGroupExchange(s, peers, 3, [&](const double2* const* remote) { return dfsaLaunchFusedDepol2Quad(s, remote, qb1, qb2, bit0, bit1, prob, corrected != 0); });
+    }
+    const int flag = corrected ? DFSA_DEPOL2_CORRECTED : 0;
+    DFSA_TRY(dfsa_k_depol2Quad(s, qb1, qb2, bit0, bit1, prob, 0 | flag));
+    DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, quarter, quarter, pairRank0, true, true));
+    DFSA_TRY(dfsa_k_depol2Quad(s, qb1, qb2, bit0, bit1, prob, 1 | flag));
+    DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, quarter, quarter, pairRank1, true, true));
+    return dfsa_k_depol2Quad(s, qb1, qb2, bit0, bit1, prob, 2 | flag);
 }
 
 extern "C" int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,

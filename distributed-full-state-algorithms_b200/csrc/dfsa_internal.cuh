@@ -84,6 +84,9 @@ int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRa
 int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit);   // buffer = shard after swapping suffix qubit qb with this pair's prefix qubit
 int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);    // prefix oneQubitDepolarising, buffer = result
 int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);   // prefix damping, buffer = result
+int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const struct BitSpec& spec, uint64_t fixed, double2 c0, double2 c1);   // buffer[j] = c0*amps[k(j)] + c1*remote[k(j)] on a control sub-cube
+int dfsaLaunchFusedDepol2Pair(dfsa_state* s, const double2* remote, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, bool corrected);
+int dfsaLaunchFusedDepol2Quad(dfsa_state* s, const double2* const* remote, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, bool corrected);
 int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigned* suffixPos, unsigned k, unsigned rho);   // buffer = shard after swapping k suffix with k prefix qubits
 int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registry slots are this state's amps / buffer now
 

@@ -113,6 +113,12 @@ extern "C" int dfsa_k_damping(dfsa_state* s, unsigned qb, double prob) {
 // Reference constants (distributed_densitymatrix.hpp:247-249): c1 = 1-4p/5, c2 = 4p/15, c3 = -16p/15 -- with
 // these the map is NOT the depolarising channel but it is what the reference computes; `corrected`
 // uses c1 = 1-16p/15, which is the channel (1-16p/15) rho + (4p/15) I (x) Tr_2 rho.
+// ONE pass (32*A bytes; the reference makes two, 40*A): an item is the 16 amplitudes spanned by the four bits
+// (q0, q1 ket; q2, q3 bra); the 12 off-"diagonal" ones are scaled, the 4 diagonal ones mixed. Each item is read whole
+// before it is written, and pass 1 never touches what pass 2 reads, so the arithmetic is the reference's, operation for
+// operation.
+struct Amp16 { static constexpr int kLoads = 16; double2 v[16]; };
+
 extern "C" int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned qb2, double prob, int corrected) {
     DFSA_DM_ENTRY(s);
     if (qb1 > qb2) std::swap(qb1, qb2);
@@ -121,28 +127,27 @@ extern "C" int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned
     const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
     const double offFac = 1. + c3;
     double2* amps = s->arr[DFSA_AMPS];
-    {
-        auto ld = [=] __device__(uint64_t j) { return Amp1{amps[j]}; };
-        auto st = [=] __device__(uint64_t j, const Amp1& v) {
-            unsigned differ = (unsigned)(((j >> q0) ^ (j >> q2)) | ((j >> q1) ^ (j >> q3))) & 1u;
-            if (differ) amps[j] = cscale(offFac, v.a);
-        };
-        DFSA_TRY((launchStream<2, Amp1>(s->numAmps, ld, st)));
-    }
-    const uint64_t b02 = (1ULL << q0) | (1ULL << q2), b13 = (1ULL << q1) | (1ULL << q3);
+    // group element e = (b3 b2 b1 b0): bit i of e sits at index bit q_i; diagonal <=> b0 == b2 and b1 == b3: e = 0, 5, 10, 15
+    auto index = [=] __device__(uint64_t k, unsigned e) {
+        uint64_t j = insertZeroBit(insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2), q3);
+        return j | ((uint64_t)(e & 1u) << q0) | ((uint64_t)((e >> 1) & 1u) << q1) | ((uint64_t)((e >> 2) & 1u) << q2) | ((uint64_t)((e >> 3) & 1u) << q3);
+    };
     auto ld = [=] __device__(uint64_t k) {
-        uint64_t j = insertZeroBit(insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2), q3);
-        return Amp4{amps[j], amps[j | b02], amps[j | b13], amps[j | b02 | b13]};
+        Amp16 it;
+#pragma unroll
+        for (unsigned e = 0; e < 16; e++) it.v[e] = amps[index(k, e)];
+        return it;
     };
-    auto st = [=] __device__(uint64_t k, const Amp4& v) {
-        uint64_t j = insertZeroBit(insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2), q3);
-        double tx = ((v.a00.x + v.a01.x) + v.a10.x) + v.a11.x, ty = ((v.a00.y + v.a01.y) + v.a10.y) + v.a11.y;
-        amps[j]             = make_double2(fma(c2, tx, c1 * v.a00.x), fma(c2, ty, c1 * v.a00.y));
-        amps[j | b02]       = make_double2(fma(c2, tx, c1 * v.a01.x), fma(c2, ty, c1 * v.a01.y));
-        amps[j | b13]       = make_double2(fma(c2, tx, c1 * v.a10.x), fma(c2, ty, c1 * v.a10.y));
-        amps[j | b02 | b13] = make_double2(fma(c2, tx, c1 * v.a11.x), fma(c2, ty, c1 * v.a11.y));
+    auto st = [=] __device__(uint64_t k, const Amp16& it) {
+        const double2 a00 = it.v[0], a01 = it.v[5], a10 = it.v[10], a11 = it.v[15];
+        const double tx = ((a00.x + a01.x) + a10.x) + a11.x, ty = ((a00.y + a01.y) + a10.y) + a11.y;
+#pragma unroll
+        for (unsigned e = 0; e < 16; e++) {
+            const bool diag = (e == 0 || e == 5 || e == 10 || e == 15);
+            amps[index(k, e)] = diag ? make_double2(fma(c2, tx, c1 * it.v[e].x), fma(c2, ty, c1 * it.v[e].y)) : cscale(offFac, it.v[e]);
+        }
     };
-    return launchStream<1, Amp4>(s->numAmps >> 4, ld, st);
+    return launchStream<1, Amp16>(s->numAmps >> 4, ld, st);
 }
 
 // K19: distributed_densitymatrix.hpp:130-141. After the half exchange (received half at buffer[A/2..)):
@@ -217,10 +222,14 @@ int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, un
 
 // K20: distributed_densitymatrix.hpp:152-183 (qb1 suffix, qb2 prefix). q0 = qb1, q1 = qb2, q2 = qb1+N, bit = rank bit of qb2's bra.
 // phase 0: scale + pack the pre-summed eighth into buffer[0..A/8); phase 1: combine with buffer[A/8..A/4).
+// `phase | DFSA_DEPOL2_CORRECTED` selects the true channel (1-16p/15) rho + (4p/15) I (x) Tr_2 rho instead of the reference's
+// formulas: new = c1' a + c2 ((a0b0 + a1b1) + received), with the OLD a0b0 in both lines (no read-after-write).
 extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, int phase) {
     DFSA_DM_ENTRY(s);
     DFSA_REQUIRE(q0 < q1 && q1 < q2 && q2 < s->logNumAmps && s->arr[DFSA_BUFFER], "bad qubits / no exchange buffer");
-    const double c1 = 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
+    const bool corrected = (phase & DFSA_DEPOL2_CORRECTED) != 0;
+    phase &= ~DFSA_DEPOL2_CORRECTED;
+    const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
     const uint64_t eighth = s->numAmps >> 3;
     const uint64_t b1 = (uint64_t)(bit & 1u) << q1, b02 = (1ULL << q0) | (1ULL << q2);
     double2* amps = s->arr[DFSA_AMPS];
@@ -248,9 +257,16 @@ extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsign
     };
     auto st = [=] __device__(uint64_t k, const Item& v) {
         uint64_t j0b0 = insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | b1;
-        // literal reference arithmetic, including the read-after-write of :181 -> :182
-        double2 n0 = make_double2(fma(c2, v.b.x + v.c.x, c1 * v.a.x), fma(c2, v.b.y + v.c.y, c1 * v.a.y));
-        double2 n1 = make_double2(fma(c2, n0.x + v.c.x, c1 * v.b.x), fma(c2, n0.y + v.c.y, c1 * v.b.y));
+        double2 n0, n1;
+        if (corrected) {
+            const double sx = (v.a.x + v.b.x) + v.c.x, sy = (v.a.y + v.b.y) + v.c.y;
+            n0 = make_double2(fma(c2, sx, c1 * v.a.x), fma(c2, sy, c1 * v.a.y));
+            n1 = make_double2(fma(c2, sx, c1 * v.b.x), fma(c2, sy, c1 * v.b.y));
+        } else {
+            // literal reference arithmetic, including the read-after-write of :181 -> :182
+            n0 = make_double2(fma(c2, v.b.x + v.c.x, c1 * v.a.x), fma(c2, v.b.y + v.c.y, c1 * v.a.y));
+            n1 = make_double2(fma(c2, n0.x + v.c.x, c1 * v.b.x), fma(c2, n0.y + v.c.y, c1 * v.b.y));
+        }
         amps[j0b0] = n0;
         amps[j0b0 | b02] = n1;
     };
@@ -259,10 +275,14 @@ extern "C" int dfsa_k_depol2Pair(dfsa_state* s, unsigned q0, unsigned q1, unsign
 
 // K21: distributed_densitymatrix.hpp:195-237 (both qubits prefix).
 // phase 0: scale + pack quarter; phase 1: a = c1*a + c2*recv, also repacked; phase 2: a = (c2/c1)*recv  (overwrite, as the reference)
+// `phase | DFSA_DEPOL2_CORRECTED`: the true channel -- phase 1 keeps amps and sends on t = a + received, phase 2 computes
+// a = c1' a + c2 (t + received) (t is still in buffer[0..A/4)).
 extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, int phase) {
     DFSA_DM_ENTRY(s);
     DFSA_REQUIRE(q0 < q1 && q1 < s->logNumAmps && s->arr[DFSA_BUFFER], "bad qubits / no exchange buffer");
-    const double c1 = 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
+    const bool corrected = (phase & DFSA_DEPOL2_CORRECTED) != 0;
+    phase &= ~DFSA_DEPOL2_CORRECTED;
+    const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, c3 = -16 * prob / 15;
     const uint64_t quarter = s->numAmps >> 2;
     const uint64_t fixed = ((uint64_t)(bit0 & 1u) << q0) | ((uint64_t)(bit1 & 1u) << q1);
     double2* amps = s->arr[DFSA_AMPS];
@@ -282,6 +302,7 @@ extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsign
     if (phase == 1) {
         auto ld = [=] __device__(uint64_t k) { return Amp2{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed], buf[k + quarter]}; };
         auto st = [=] __device__(uint64_t k, const Amp2& v) {
+            if (corrected) { buf[k] = cadd(v.a0, v.a1); return; }
             double2 n = make_double2(fma(c2, v.a1.x, c1 * v.a0.x), fma(c2, v.a1.y, c1 * v.a0.y));
             amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = n;
             buf[k] = n;
@@ -289,10 +310,102 @@ extern "C" int dfsa_k_depol2Quad(dfsa_state* s, unsigned q0, unsigned q1, unsign
         return launchStream<1, Amp2>(quarter, ld, st);
     }
     DFSA_REQUIRE(phase == 2, "phase must be 0, 1 or 2");
+    if (corrected) {
+        auto ld = [=] __device__(uint64_t k) { return Amp3{amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed], buf[k], buf[k + quarter]}; };
+        auto st = [=] __device__(uint64_t k, const Amp3& v) {
+            const double sx = v.b.x + v.c.x, sy = v.b.y + v.c.y;
+            amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = make_double2(fma(c2, sx, c1 * v.a.x), fma(c2, sy, c1 * v.a.y));
+        };
+        return launchStream<1, Amp3>(quarter, ld, st);
+    }
     const double c4 = c2 / c1;
     auto ld = [=] __device__(uint64_t k) { return Amp1{buf[k + quarter]}; };
     auto st = [=] __device__(uint64_t k, const Amp1& v) { amps[insertZeroBit(insertZeroBit(k, q0), q1) | fixed] = cscale(c4, v.a); };
     return launchStream<2, Amp1>(quarter, ld, st);
+}
+
+// K20 fused with its exchange (distributed_densitymatrix.hpp:152-183 as ONE out-of-place pass over peer memory). An item is
+// the 8 amplitudes spanned by (q0, q1 ket bits; q2 = bra bit of qb1); the two "diagonal" ones with q1 bit == this rank's
+// bra bit of qb2 (a0b0, a1b1) are mixed with the partner's pair, which the reference pre-sums, packs and sends -- here the
+// partner's two amplitudes are read over NVLink and summed in the same order; everything else is scaled. The partner's
+// diagonal amplitudes are untouched by its own scaling step, so reading its ORIGINAL shard gives the reference's values.
+struct Amp10 { static constexpr int kLoads = 10; double2 v[8]; double2 r0, r1; };
+
+int dfsaLaunchFusedDepol2Pair(dfsa_state* s, const double2* remote, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, bool corrected) {
+    const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, offFac = 1. + (-16 * prob / 15);
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    const unsigned mine = bit & 1u;
+    const uint64_t other1 = (uint64_t)(mine ^ 1u) << q1, b02 = (1ULL << q0) | (1ULL << q2);
+    auto index = [=] __device__(uint64_t k, unsigned e) {     // e = (z y x): x at q0, y at q1, z at q2
+        return insertZeroBit(insertZeroBit(insertZeroBit(k, q0), q1), q2) | ((uint64_t)(e & 1u) << q0) | ((uint64_t)((e >> 1) & 1u) << q1) | ((uint64_t)((e >> 2) & 1u) << q2);
+    };
+    auto ld = [=] __device__(uint64_t k) {
+        Amp10 it;
+#pragma unroll
+        for (unsigned e = 0; e < 8; e++) it.v[e] = amps[index(k, e)];
+        const uint64_t jz = index(k, 0) | other1;
+        it.r0 = remote[jz];
+        it.r1 = remote[jz | b02];
+        return it;
+    };
+    auto st = [=] __device__(uint64_t k, const Amp10& it) {
+        const unsigned eA = mine << 1, eB = eA | 5u;             // a0b0: x = z = 0, y = mine;  a1b1: x = z = 1
+        const double2 A = mine ? it.v[2] : it.v[0], B = mine ? it.v[7] : it.v[5], recv = cadd(it.r0, it.r1);
+        double2 n0, n1;
+        if (corrected) {
+            const double sx = (A.x + B.x) + recv.x, sy = (A.y + B.y) + recv.y;
+            n0 = make_double2(fma(c2, sx, c1 * A.x), fma(c2, sy, c1 * A.y));
+            n1 = make_double2(fma(c2, sx, c1 * B.x), fma(c2, sy, c1 * B.y));
+        } else {                                                 // the reference's lines :181-182, read-after-write included
+            n0 = make_double2(fma(c2, B.x + recv.x, c1 * A.x), fma(c2, B.y + recv.y, c1 * A.y));
+            n1 = make_double2(fma(c2, n0.x + recv.x, c1 * B.x), fma(c2, n0.y + recv.y, c1 * B.y));
+        }
+#pragma unroll
+        for (unsigned e = 0; e < 8; e++) out[index(k, e)] = (e == eA) ? n0 : ((e == eB) ? n1 : cscale(offFac, it.v[e]));
+    };
+    return launchStream<1, Amp10>(s->numAmps >> 3, ld, st);
+}
+
+// K21 fused with its two exchanges (distributed_densitymatrix.hpp:195-237), ONE out-of-place pass over the shards of the
+// four ranks that differ in the two bra bits. An item is the 4 amplitudes spanned by the ket bits (q0, q1); the one whose
+// ket bits equal this rank's bra bits is the "diagonal" one. The reference's net effect, literally: after the scaling step
+//   diagonal = (c2/c1) * (c1 * P1 + c2 * P01)     P1 = partner 1's original diagonal amplitude, P01 = its partner 0's
+// (the value of phase 1, c1 a + c2 P0, is overwritten by phase 2 at :236 -- SURVEY F2). Corrected: c1' a + c2 (((a + P0) + P1) + P01).
+struct Amp7 { static constexpr int kLoads = 7; double2 v[4]; double2 p0, p1, p01; };
+
+int dfsaLaunchFusedDepol2Quad(dfsa_state* s, const double2* const* remote /* P0, P1, P01 */, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, bool corrected) {
+    const double c1 = corrected ? 1 - 16 * prob / 15 : 1 - 4 * prob / 5, c2 = 4 * prob / 15, offFac = 1. + (-16 * prob / 15), c4 = c2 / c1;
+    const double2* amps = s->arr[DFSA_AMPS];
+    const double2 *r0 = remote[0], *r1 = remote[1], *r01 = remote[2];
+    double2* out = s->arr[DFSA_BUFFER];
+    const unsigned b0 = bit0 & 1u, b1 = bit1 & 1u, eMine = b0 | (b1 << 1);
+    const uint64_t f0 = ((uint64_t)(b0 ^ 1u) << q0) | ((uint64_t)b1 << q1), f1 = ((uint64_t)b0 << q0) | ((uint64_t)(b1 ^ 1u) << q1),
+                   f01 = ((uint64_t)(b0 ^ 1u) << q0) | ((uint64_t)(b1 ^ 1u) << q1);
+    auto ld = [=] __device__(uint64_t k) {
+        Amp7 it;
+        const uint64_t jz = insertZeroBit(insertZeroBit(k, q0), q1);
+#pragma unroll
+        for (unsigned e = 0; e < 4; e++) it.v[e] = amps[jz | ((uint64_t)(e & 1u) << q0) | ((uint64_t)(e >> 1) << q1)];
+        it.p0 = corrected ? r0[jz | f0] : make_double2(0.0, 0.0);
+        it.p1 = r1[jz | f1];
+        it.p01 = r01[jz | f01];
+        return it;
+    };
+    auto st = [=] __device__(uint64_t k, const Amp7& it) {
+        const uint64_t jz = insertZeroBit(insertZeroBit(k, q0), q1);
+        const double2 a = it.v[eMine];
+        double2 n;
+        if (corrected) {
+            const double sx = ((a.x + it.p0.x) + it.p1.x) + it.p01.x, sy = ((a.y + it.p0.y) + it.p1.y) + it.p01.y;
+            n = make_double2(fma(c2, sx, c1 * a.x), fma(c2, sy, c1 * a.y));
+        } else {
+            n = cscale(c4, make_double2(fma(c2, it.p01.x, c1 * it.p1.x), fma(c2, it.p01.y, c1 * it.p1.y)));
+        }
+#pragma unroll
+        for (unsigned e = 0; e < 4; e++) out[jz | ((uint64_t)(e & 1u) << q0) | ((uint64_t)(e >> 1) << q1)] = (e == eMine) ? n : cscale(offFac, it.v[e]);
+    };
+    return launchStream<1, Amp7>(s->numAmps >> 2, ld, st);
 }
 
 // K22: distributed_densitymatrix.hpp:284-313.

@@ -297,6 +297,19 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
     return launchStream<1, Amp2>(items, ld, st);
 }
 
+// X2+K8 over peer memory (distributed_statevector.hpp:43-78: a 2x2 gate on a prefix target with suffix controls): only the
+// sub-cube with every suffix control set is touched, so the result cannot go out of place without copying the whole shard.
+// Two small passes instead: buffer[j] = f0*amps[k(j)] + f1*partner_amps[k(j)] (partner read over NVLink), then -- once both
+// ranks have finished reading each other -- amps[k(j)] = buffer[j] (dfsa_k_unpack). 64 bytes of HBM traffic per touched
+// amplitude against the staged path's 112 (pack, send + receive staging, combine), NVLink 16 per direction either way.
+int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const BitSpec& spec, uint64_t fixed, double2 c0, double2 c1) {
+    const double2* amps = s->arr[DFSA_AMPS];
+    double2* out = s->arr[DFSA_BUFFER];
+    auto ld = [=] __device__(uint64_t j) { const uint64_t k = insertZeroBits(j, spec) | fixed; return Amp2{amps[k], remote[k]}; };
+    auto st = [=] __device__(uint64_t j, const Amp2& v) { out[j] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    return launchStream<1, Amp2>(s->numAmps >> spec.n, ld, st);
+}
+
 // unpack half a shard from an arbitrary (possibly peer-mapped) source: amps[insert(k, qb, bitValue)] = src[k]
 // Suffix<->prefix qubit swap (distributed_statevector.hpp:140-186) as ONE out-of-place pass over peer memory:
 //   buffer[j] = amps[j]                     where bit qb of j equals this rank's bit of the prefix qubit (stays)

@@ -86,32 +86,31 @@ static inline void distributed_densitymatrix_oneQubitDepolarising(DensityMatrix&
     DFSA_CHECK(dfsa_xk_depol1Prefix(rho.handle, qb, bit, prob, int(flipBit(rho.rank, rankQb))));
 }
 
-// As in the reference, the three branches apply the reference's own formulas (SURVEY F2 explains why they are not
-// the textbook channel); `corrected` is only available on the all-suffix branch.
-static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob, bool corrected = false) {
+// As in the reference, the three branches apply the reference's own formulas (SURVEY F2 explains why they are not the
+// textbook channel); corrected = true applies the true channel (1-16p/15) rho + (4p/15) I (x) Tr_2 rho on all three.
+// A build with -DDFSA_CORRECTED_DEPOL2_DEFAULT makes that the default (the repaired Catch2 case, tests/catch_dropin/).
+#ifdef DFSA_CORRECTED_DEPOL2_DEFAULT
+#define DFSA_DEPOL2_DEFAULT true
+#else
+#define DFSA_DEPOL2_DEFAULT false
+#endif
+static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob, bool corrected = DFSA_DEPOL2_DEFAULT) {
     if (qb1 > qb2) std::swap(qb1, qb2);
     const Nat N = rho.numQubits, threshold = N - rho.logNumNodes;
     if (qb2 < threshold) { local_densitymatrix_twoQubitDepolarising(rho, qb1, qb2, prob, corrected); return; }
-    assert(!corrected && "corrected twoQubitDepolarising is only implemented for suffix qubits");
 
     if (qb1 < threshold) {
-        // pair: one partner (the rank bit of qb2's bra), an eighth of the shard pre-summed and exchanged
+        // pair (reference :146-183): one partner (the rank bit of qb2's bra); the partner's two "diagonal" amplitudes per
+        // group are read over NVLink (fused) or pre-summed, packed and exchanged as an eighth of the shard (staged)
         const Nat rankQb = qb2 - threshold, bit = getBit(rho.rank, rankQb);
-        const Index eighth = rho.numAmpsPerNode / 8;
-        DFSA_CHECK(dfsa_k_depol2Pair(rho.handle, qb1, qb2, qb1 + N, bit, prob, 0));
-        comm_exchangeArrays(rho.buffer, 0, rho.buffer, eighth, eighth, Nat(flipBit(rho.rank, rankQb)));
-        DFSA_CHECK(dfsa_k_depol2Pair(rho.handle, qb1, qb2, qb1 + N, bit, prob, 1));
+        DFSA_CHECK(dfsa_xk_depol2Pair(rho.handle, qb1, qb2, bit, prob, corrected ? 1 : 0, int(flipBit(rho.rank, rankQb))));
         return;
     }
-    // quad: two sequential partners, a quarter of the shard each time
+    // quad (reference :187-237): the four ranks that differ in the two bra bits; one fused pass, or two sequential
+    // quarter-shard exchanges
     const Nat rankQb0 = qb1 - threshold, rankQb1 = qb2 - threshold;
     const Nat bit0 = getBit(rho.rank, rankQb0), bit1 = getBit(rho.rank, rankQb1);
-    const Index quarter = rho.numAmpsPerNode / 4;
-    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 0));
-    comm_exchangeArrays(rho.buffer, 0, rho.buffer, quarter, quarter, Nat(flipBit(rho.rank, rankQb0)));
-    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 1));
-    comm_exchangeArrays(rho.buffer, 0, rho.buffer, quarter, quarter, Nat(flipBit(rho.rank, rankQb1)));
-    DFSA_CHECK(dfsa_k_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, 2));
+    DFSA_CHECK(dfsa_xk_depol2Quad(rho.handle, qb1, qb2, bit0, bit1, prob, corrected ? 1 : 0, int(flipBit(rho.rank, rankQb0)), int(flipBit(rho.rank, rankQb1))));
 }
 
 static inline void distributed_densitymatrix_damping(DensityMatrix& rho, Nat qb, Real prob) {

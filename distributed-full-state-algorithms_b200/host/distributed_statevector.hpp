@@ -124,14 +124,12 @@ static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi,
         case dfsa_detail::ExchangePlan::FullShard: dfsa_prefixOneTarg(psi, target, gate); return;
         default: break;
     }
-    // prefix target, suffix controls: only the ctrl=1 sub-cube (A / 2^c amplitudes) travels
-    const Index allOnes = (Index(1) << suffixCtrls.size()) - 1;
-    DFSA_CHECK(dfsa_k_pack(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), allOnes, 0));
-    comm_exchangeArrays(psi.buffer, 0, psi.buffer, plan.numAmps, plan.numAmps, plan.pairRank);
+    // prefix target, suffix controls: only the ctrl=1 sub-cube (A / 2^c amplitudes) is exchanged and combined (reference
+    // :43-78). Fused over peer memory where the ranks share a node, else pack / exchange / combine as the reference does.
     double f0[2], f1[2];
     dfsa_detail::ampToArray(gate[plan.bit][plan.bit], f0);
     dfsa_detail::ampToArray(gate[plan.bit][!plan.bit], f1);
-    DFSA_CHECK(dfsa_k_combineSub(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), allOnes, plan.numAmps, f0, f1));
+    DFSA_CHECK(dfsa_xk_ctrlPrefixTarg(psi.handle, suffixCtrls.data(), Nat(suffixCtrls.size()), int(plan.pairRank), f0, f1));
 }
 
 static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, Nat qb2) {

@@ -4,14 +4,20 @@
 // reference declares here and defines in tests/test_utilities.hpp (:419-524) are implemented with device copies.
 #pragma once
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <utility>
 
 #include "bit_maths.hpp"
 #include "communication.hpp"
 #include "misc.hpp"
 #include "types.hpp"
+
+#ifndef DFSA_AGREES_TOL
+#define DFSA_AGREES_TOL 1E-5
+#endif
 
 class StateVector {
 public:
@@ -75,14 +81,22 @@ public:
             for (Index i = 0; i < all.size(); i++) std::printf("%llu: (%.17g, %.17g)\n", i, all[i].real(), all[i].imag());
         comm_synch();
     }
-    // two-sided (the reference's comparison is one-sided and NaN-blind)
-    bool agreesWith(const AmpArray& ref, Real tol = 1E-5) {
+    // two-sided and NaN-aware (the reference's comparison is one-sided and NaN-blind). Default tolerance
+    // as the reference's (1E-5 absolute); a test build may tighten it: -DDFSA_AGREES_TOL=1e-12 -DDFSA_AGREES_RELATIVE makes the
+    // bound tol * max(1, max |ref component|), the bar of BASELINE north_star.
+    bool agreesWith(const AmpArray& ref, Real tol = DFSA_AGREES_TOL) {
         AmpArray all = getAllVecAmps();
         if (ref.size() != all.size()) return false;
+        Real bound = tol;
+#ifdef DFSA_AGREES_RELATIVE
+        Real scale = 1;
+        for (const Amp& a : ref) scale = std::max(scale, std::max(std::abs(a.real()), std::abs(a.imag())));
+        bound = tol * scale;
+#endif
         for (Index i = 0; i < ref.size(); i++) {
             Amp dif = ref[i] - all[i];
-            if (!(std::abs(dif.real()) <= tol) || !(std::abs(dif.imag()) <= tol)) {
-                if (rank == 0) std::printf("disagreement of (%g) + i(%g) at %llu\n", dif.real(), dif.imag(), i);
+            if (!(std::abs(dif.real()) <= bound) || !(std::abs(dif.imag()) <= bound)) {
+                if (rank == 0) std::printf("disagreement of (%g) + i(%g) at %llu (bound %g)\n", dif.real(), dif.imag(), i, bound);
                 return false;
             }
         }
@@ -99,7 +113,7 @@ public:
         if (numUnequal) *numUnequal = ne;
         return d;
     }
-    bool agreesWith(StateVector& other, Real tol = 1E-5) { Real d = getMaxDifference(other); return d <= tol; }
+    bool agreesWith(StateVector& other, Real tol = DFSA_AGREES_TOL) { Real d = getMaxDifference(other); return d <= tol; }
 
 protected:
     StateVector() = default;
@@ -149,7 +163,7 @@ public:
         setAllVecAmps(vec);
     }
     using StateVector::agreesWith;
-    bool agreesWith(const AmpMatrix& ref, Real tol = 1E-5) {
+    bool agreesWith(const AmpMatrix& ref, Real tol = DFSA_AGREES_TOL) {
         const Index dim = powerOf2(numQubits);
         if (ref.size() != dim) return false;
         AmpArray vec(dim * dim);

@@ -42,6 +42,7 @@ enum dfsa_status {
 };
 
 enum { DFSA_AMPS = 0, DFSA_BUFFER = 1 };
+enum { DFSA_DEPOL2_CORRECTED = 16 };  /* OR-ed into the `phase` of dfsa_k_depol2Pair / dfsa_k_depol2Quad: the true channel, not the reference's formulas */
 enum { DFSA_MAX_QUBITS = 64 };
 
 const char* dfsa_last_error(void);
@@ -62,6 +63,11 @@ int dfsa_comm_size(void);                          /* comm_getNumNodes() */
 int dfsa_comm_barrier(void);                       /* comm_synch(): device sync + inter-rank barrier */
 int dfsa_device_sync(void);
 const char* dfsa_comm_transport(void);             /* "single", "nccl" or "ipc" */
+/* Collective. 1: exchanges fused into the kernels that consume them (peer shards read over NVLink), 0: the staged pack /
+ * exchange / combine path of the reference, -1: what DFSA_FUSED_EXCHANGE says (default fused where every rank can map every
+ * other rank's shards). dfsa_comm_fused_active(): 0 staged, 1 fused with host synchronisation, 2 fused and stream-ordered. */
+int dfsa_comm_set_fused(int mode);
+int dfsa_comm_fused_active(void);
 void* dfsa_stream_compute(void);                   /* cudaStream_t the kernels run on (for CUDA-event timing) */
 
 /* ---- measurement helpers (no counterpart in the reference, which times with std::chrono around comm_synch, main.cpp:28-35) */
@@ -141,6 +147,13 @@ int dfsa_plan_relocate(int rank, unsigned logNumAmps, const uint32_t* prefixQubi
  * peer-mapped shards: one out-of-place pass that reads the partner's half over NVLink, then amps <-> buffer. */
 int dfsa_xk_depol1Prefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank);
 int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank);
+/* manyCtrlOneTargGate with a prefix target and suffix controls (distributed_statevector.hpp:43-78): amps[k] = f0*amps[k] +
+ * f1*partner_amps[k] on the sub-cube where every control in suffixCtrls (strictly increasing) is 1. */
+int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls, unsigned numCtrls, int pairRank, const double f0[2], const double f1[2]);
+/* twoQubitDepolarising with one (pair, :146-183) or both (quad, :187-237) bra bits in the rank index; qb1 < qb2; bit / bit0 /
+ * bit1 = this rank's bits of those qubits. corrected = 0: the reference's formulas, literally. */
+int dfsa_xk_depol2Pair(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit, double prob, int corrected, int pairRank);
+int dfsa_xk_depol2Quad(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit0, unsigned bit1, double prob, int corrected, int pairRank0, int pairRank1);
 int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
                                  const double f[2], const double g[2], int exact);
 

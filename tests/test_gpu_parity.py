@@ -119,7 +119,7 @@ def test_every_target_position_one_and_ctrl_gate(dfsa):
 @pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 6, 7])
 def test_many_targ_gate_every_kernel_and_placement(dfsa, nt):
     """manyTargGate (local_statevector.hpp:72-99) picks its kernel by target count (pair stream, quad stream, tensor-core
-    tiles for t = 3..5, DFMA tile for t = 6, generic above and on shards smaller than a tile), and the tensor-core kernel's
+    tiles for t = 3..6, generic above and on shards smaller than a tile), and the tensor-core kernel's
     tile layout and shared-memory swizzle depend on where the targets sit. Every kernel, targets low / high / scattered /
     just above the free bits, in caller order (not sorted), against the oracle."""
     rng = np.random.default_rng(100 + nt)
@@ -229,11 +229,14 @@ def test_large_state_properties(dfsa):
             cases.apply(st, (name, op[1], -op[2]))
     product.pkg().api.check(dfsa.device_lib().dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(4096), head.ctypes.data_as(C.POINTER(C.c_double))))
     compare.assert_close(head, vals[0::2] + 1j * vals[1::2], tol=1e-13, what="U then U^dagger")
+    d_all, _, _ = st.compare_hash(2024)                       # ... and over ALL 2^28 amplitudes, on the device
+    assert d_all <= 1e-13, "U then U^dagger, full state: %.3e" % d_all
     st.sv_swapGate(3, 25)
     st.sv_swapGate(25, 3)
     tail = np.empty(4096, dtype=np.complex128)
     product.pkg().api.check(dfsa.device_lib().dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(4096), tail.ctypes.data_as(C.POINTER(C.c_double))))
     compare.assert_exact(tail, head, what="swap twice")
+    assert st.compare_hash(2024)[0] == d_all                  # swap twice moved nothing, anywhere
 
 
 # ---------------------------------------------------------------- multi-rank (NCCL with >= P GPUs, else IPC on one GPU)
@@ -242,11 +245,17 @@ def _golden_multirank(nodes):
     return [c for c in GOLDEN if c["nodes"] == nodes]
 
 
+# the three ways an exchange can run: fused into the consuming kernel with stream-ordered signalling between the ranks
+# (default), fused with host synchronisation (no stream memory ops), staged pack / exchange / combine like the reference
+EXCHANGE_MODES = {"fused": None, "fused-hostsync": {"DFSA_STREAM_SIGNALS": "0"}, "staged": {"DFSA_FUSED_EXCHANGE": "0"}}
+
+
+@pytest.mark.parametrize("mode", sorted(EXCHANGE_MODES))
 @pytest.mark.parametrize("nodes", [2, 4, 8])
-def test_multi_rank_matches_reference_golden(nodes):
+def test_multi_rank_matches_reference_golden(nodes, mode):
     todo = _golden_multirank(nodes)
     jobs = [dict(kind=c["kind"], nq=c["nq"], op=c["op"], amps=c["amps"]) for c in todo]
-    results = product.run_cases_multirank(jobs, nodes)
+    results = product.run_cases_multirank(jobs, nodes, extra_env=EXCHANGE_MODES[mode])
     for c, r in zip(todo, results):
         name = c["op"][0]
         if name == "dm_expecPauliString":
@@ -260,9 +269,11 @@ def test_multi_rank_matches_reference_golden(nodes):
             compare.assert_close(r["amps"], c["out"], what=golden_io.case_id(c))
 
 
-@pytest.mark.parametrize("nodes", [2, 4])
-def test_multi_rank_circuit_matches_oracle(nodes):
-    """Chained ops on one state (exercises buffer reuse between exchanges) at a larger size."""
+@pytest.mark.parametrize("mode", sorted(EXCHANGE_MODES))
+@pytest.mark.parametrize("nodes", [2, 4, 8])
+def test_multi_rank_circuit_matches_oracle(nodes, mode):
+    """Chained ops on one state (exercises buffer reuse between exchanges, and -- in the stream-ordered mode -- gates
+    queued behind each other with no host synchronisation in between) at a larger size."""
     rng = np.random.default_rng(40 + nodes)
     k = nodes.bit_length() - 1
     jobs, wants = [], []
@@ -278,9 +289,29 @@ def test_multi_rank_circuit_matches_oracle(nodes):
             cases.apply(o, op)
         jobs.append(dict(kind=kind, nq=nq, ops=ops, amps=amps))
         wants.append(o.get_amps())
-    results = product.run_cases_multirank(jobs, nodes)
+    results = product.run_cases_multirank(jobs, nodes, extra_env=EXCHANGE_MODES[mode])
     for r, w in zip(results, wants):
-        compare.assert_close(r["amps"], w, tol=1e-11, what="circuit np=%d (%s)" % (nodes, r["transport"]))
+        compare.assert_close(r["amps"], w, tol=1e-11, what="circuit np=%d (%s, %s)" % (nodes, r["transport"], mode))
+
+
+@pytest.mark.parametrize("mode", sorted(EXCHANGE_MODES))
+@pytest.mark.parametrize("nodes", [2, 4, 8])
+def test_corrected_two_qubit_depolarising_on_prefix_qubits(nodes, mode):
+    """corrected=True on the pair and quad branches (one / both bra bits in the rank index) is the true channel
+    (1-16p/15) rho + (4p/15) I (x) Tr_2 rho: against the dense Kraus map."""
+    rng = np.random.default_rng(700 + nodes)
+    k = nodes.bit_length() - 1
+    nq = 5
+    pairs = [(0, nq - 1), (nq - 1, 2)] + ([(nq - 1, nq - 2), (nq - k, nq - 1)] if k >= 2 else [])
+    jobs, wants = [], []
+    for (a, b) in pairs:
+        amps = cases.random_state(rng, 2 * nq)
+        p = float(rng.uniform(0, 0.75))
+        jobs.append(dict(kind="dm", nq=nq, op=("dm_twoQubitDepolarising", a, b, p, True), amps=amps))
+        wants.append(dense.apply_op("dm", nq, amps, ("dm_twoQubitDepolarising", a, b, p)))
+    results = product.run_cases_multirank(jobs, nodes, extra_env=EXCHANGE_MODES[mode])
+    for job, r, w in zip(jobs, results, wants):
+        compare.assert_close(r["amps"], w, what="corrected depol2 %r np=%d (%s)" % (job["op"][1:3], nodes, mode))
 
 
 @pytest.mark.parametrize("nodes", [4, 8])
