@@ -1,13 +1,24 @@
 #!/usr/bin/env python
 """bench.py -- the hot path measured on B200s (contract: the driver's `python bench.py --gpus N --steps K --warmup W`).
 
-Workload (BASELINE.json configs[1], the largest single-GPU configuration; weak scaling for N > 1):
+Headline workload (BASELINE.json configs[1], the largest single-GPU configuration; weak scaling for N > 1):
   a (32 + log2 N)-qubit state vector, 64 GiB shard per GPU; one STEP = one sweep over ALL target positions,
   each position getting a oneTargGate and a manyCtrlOneTargGate with 1-3 controls (64 + 2 log2 N gates).
   Prefix targets (the top log2 N qubits) exercise the NVLink pairwise exchange.
-Metric: "34-qubit-equivalent SV gates/s" = amplitude-updates per second / 2^34 (so that the number is a whole-job
-  throughput that adds up over GPUs under weak scaling; `gates_per_s_actual` is the plain rate at the actual size).
+Metric: "34-qubit-equivalent SV gates/s" = amplitude-updates per second / 2^34 (BASELINE's "34-qubit SV gates/s" made additive
+  over GPUs under weak scaling -- a 34-qubit state does not fit one GPU); `gates_per_s_actual` is the plain rate at the actual
+  size and `amp_updates_per_s` the un-normalised throughput.
 Timing: CUDA events on the library's compute stream, barrier + device sync on both sides, max over ranks.
+
+The same JSON line also carries
+  "parity"   : BEFORE any timing, a (24 + log2 N)-qubit sweep + config-3 mini-circuit and a 12-qubit noisy density-matrix layer
+               run through the SAME transports the timed region uses (fused remote-load kernels over NVLink, then again on the
+               staged NCCL path) and are compared with the C oracle amplitude by amplitude on the device; a failure exits 3.
+  "selfcheck": at the FULL size (33-35 qubits are beyond any oracle): the sweep, then its inverse, compared with the
+               regenerated initial state over all amplitudes.
+  "configs"  : BASELINE configs 3, 4, 5 (random 5-target dense gates / gadgets; noisy density-matrix layer at 14 and 16 qubits;
+               expecPauliString over 256 strings + partialTrace), per-op device times and fractions of the roofline
+               max(HBM bytes / measured HBM peak, NVLink bytes per direction / NVLink rate MEASURED in this run, flop / FP64 peak).
 `--impl reference` times the reference's own CPU implementation (oracle/_ref/ref_driver: unmodified reference +
 setBit patch + fork/shm MPI stand-in) on the box's host cores on a bounded sample of the same sweep.
 """
@@ -29,15 +40,22 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 import numpy as np  # noqa: E402
 
 PKG = "distributed-full-state-algorithms_b200"
-REF_SAMPLE_QUBITS = 28          # bounded CPU sample of the sweep (4 GiB state)
+REF_SAMPLE_QUBITS = 30          # bounded CPU sample of the sweep (16 GiB state + 16 GiB buffer)
 SEED = 20261017
+FP64_PEAK_TFLOPS = 36.6         # measured on B200: profiles/r01_fp64_peak_b200.jsonl (DFMA 36.6, DMMA 37.0)
+NVLINK_FALLBACK_GBS = 770.0     # per direction, B200_PROFILING.md; replaced by the in-run measurement when N > 1
+PARITY_TOL = 1e-12
 
 
-# ------------------------------------------------------------------------------------------------ workload
+# ------------------------------------------------------------------------------------------------ workloads
+
+def haar(rng, d):
+    q, r = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
 
 def haar_2x2(rng):
-    q, r = np.linalg.qr(rng.standard_normal((2, 2)) + 1j * rng.standard_normal((2, 2)))
-    return q * (np.diag(r) / np.abs(np.diag(r)))
+    return haar(rng, 2)
 
 
 def make_sweep(num_qubits, seed=SEED):
@@ -52,21 +70,134 @@ def make_sweep(num_qubits, seed=SEED):
     return ops
 
 
-def op_algorithmic_bytes(op, num_qubits, log_ranks):
-    """per-rank HBM bytes of one gate (A = amps per rank); (hbm_bytes, nvlink_bytes_per_direction)."""
-    L = num_qubits - log_ranks
-    A = 1 << L
-    if op[0] == "sv_oneTargGate":
-        return (32 * A, 0) if op[1] < L else (48 * A, 16 * A)
-    ctrls, t = op[1], op[2]
-    suffix = [c for c in ctrls if c < L]
-    # ranks failing a prefix control do nothing; count the work of a participating rank
-    if t < L:
-        return (32 * A >> len(suffix), 0)
-    if not suffix:
-        return (48 * A, 16 * A)
-    m = A >> len(suffix)
-    return (16 * m + 16 * m + 48 * m, 16 * m)       # pack (r+w), send/recv staging, combine
+def inverse_ops(ops):
+    """The op list that undoes `ops` (unitary gates only)."""
+    out = []
+    for op in reversed(ops):
+        name = op[0]
+        if name == "sv_oneTargGate":
+            out.append((name, op[1], op[2].conj().T))
+        elif name == "sv_manyCtrlOneTargGate":
+            out.append((name, op[1], op[2], op[3].conj().T))
+        elif name == "sv_manyTargGate":
+            out.append((name, op[1], op[2].conj().T))
+        elif name == "sv_pauliGadget":
+            out.append((name, op[1], op[2], -op[3]))
+        elif name == "sv_phaseGadget":
+            out.append((name, op[1], -op[2]))
+        elif name in ("sv_swapGate", "sv_pauliTensor"):
+            out.append(op)
+        else:
+            raise ValueError(name)
+    return out
+
+
+def config_workload(name, world, seed=7, dm_qubits=None):
+    """BASELINE configs 3-5."""
+    rng = np.random.default_rng(seed)
+    if name == "circuit":
+        nq = {1: 32, 2: 33, 4: 34, 8: 34}[world]
+        ops = []
+        for _ in range(8):
+            ops.append(("sv_manyTargGate", [int(x) for x in rng.permutation(nq)[:5]], haar(rng, 32)))
+            nt = int(rng.integers(3, 7))
+            paulis = [int(x) for x in rng.integers(1, 4, size=nt)]
+            if all(p == 3 for p in paulis):
+                paulis[0] = 1
+            ops.append(("sv_pauliGadget", [int(x) for x in rng.permutation(nq)[:nt]], paulis, float(rng.uniform(-np.pi, np.pi))))
+            ops.append(("sv_phaseGadget", [int(x) for x in rng.permutation(nq)[:int(rng.integers(1, 8))]], float(rng.uniform(-np.pi, np.pi))))
+        return "sv", nq, ops, "config 3: random circuit of manyTargGate(5 targets) / pauliGadget / phaseGadget, random targets"
+    if name == "dm":
+        N = dm_qubits or (14 if world == 1 else 16)
+        ops = []
+        for q in range(N):
+            ops.append(("dm_manyTargGate", [q, (q + 1) % N], haar(rng, 4)))
+            ops.append(("dm_oneQubitDepolarising", q, float(rng.uniform(0, 0.5))))
+            ops.append(("dm_twoQubitDephasing", q, (q + 1) % N, float(rng.uniform(0, 0.5))))
+            ops.append(("dm_damping", q, float(rng.uniform(0, 0.5))))
+        return "dm", N, ops, "config 4: noisy layer (manyTargGate t=2, oneQubitDepolarising, twoQubitDephasing, damping) on every qubit"
+    if name == "expec":
+        N = dm_qubits or (14 if world == 1 else 16)
+        coeffs = rng.uniform(-10, 10, 256)
+        paulis = rng.integers(0, 4, size=(256, N))
+        ops = [("dm_expecPauliString", coeffs, paulis)] * 4
+        ops.append(("dm_partialTrace", [0, 3, 5, 8]))                       # all-suffix: local gather-sum
+        ops.append(("dm_partialTrace", [N - 4, N - 3, N - 2, N - 1]))      # top qubits: bra bits are rank bits -> relocation
+        return "dm", N, ops, "config 5: expecPauliString over 256 random Pauli strings (x4) + partialTrace of 4 qubits (local / relocating)"
+    raise ValueError(name)
+
+
+def op_cost(op, kind, nq, k, lazy_relocation=False):
+    """(hbm_bytes, nvlink_bytes_per_direction, flops) per rank for one API call -- the ALGORITHMIC work, not what a
+    particular implementation moves. nq = n (sv) or N (dm); A = amplitudes per rank."""
+    name = op[0]
+    bits = nq if kind == "sv" else 2 * nq
+    L = bits - k
+    A = float(1 << L)
+
+    def relocation(npre):
+        # npre (suffix, prefix) qubit pairs swapped in one step: every rank keeps 2^-npre of its shard and pulls the rest
+        # from the other members of its group; one read + one write of the shard in HBM
+        return (32 * A, (1.0 - 0.5 ** npre) * 16 * A) if npre else (0.0, 0.0)
+
+    def many_targ(targets):
+        npre = sum(1 for t in targets if t >= L)
+        r = relocation(npre)
+        # FP64 work in the cheapest known form of the complex product (3M: 6 * 2^t flop per amplitude; the 4M form is 8 * 2^t).
+        # The reference relocates before AND after the gate (distributed_statevector.hpp:213-223): two relocations.
+        return [(32 * A, 0.0, 6.0 * (1 << len(targets)) * A)] + [(r[0], r[1], 0.0)] * (2 if npre else 0)
+
+    if name == "sv_manyTargGate":
+        return many_targ(op[1])
+    if name == "sv_oneTargGate":
+        return [(32 * A, 0, 0)] if op[1] < L else [(48 * A, 16 * A, 0)]
+    if name == "sv_manyCtrlOneTargGate":
+        ctrls, t = op[1], op[2]
+        m = A / (1 << len([c for c in ctrls if c < L]))
+        # ranks failing a prefix control do nothing; the work of a participating rank is counted
+        return [(32 * m, 0, 0)] if t < L else [(48 * m, 16 * m, 0)]
+    if name in ("sv_pauliGadget", "sv_pauliTensor"):
+        prefix_xy = any(t >= L and p in (1, 2) for t, p in zip(op[1], op[2]))
+        return [(48 * A, 16 * A, 0)] if prefix_xy else [(32 * A, 0, 0)]
+    if name == "sv_phaseGadget":
+        return [(32 * A, 0, 0)]
+    if name == "sv_swapGate":
+        a, b = sorted(op[1:3])
+        if b < L:
+            return [(16 * A, 0, 0)]
+        return [(24 * A, 8 * A, 0)] if a < L else [(32 * A, 16 * A, 0)]
+    if name == "dm_manyTargGate":
+        t = len(op[1])
+        if t <= 2:
+            # U (x) conj(U) on the 2t bits {targets, targets + N} is ONE pass over the shard
+            return many_targ(list(op[1]) + [q + nq for q in op[1]])
+        return many_targ(op[1]) + many_targ([q + nq for q in op[1]])
+    thr = nq - k
+    if name == "dm_oneQubitDepolarising":
+        return [(32 * A, 0, 0)] if op[1] < thr else [(48 * A, 8 * A, 0)]
+    if name == "dm_twoQubitDephasing":
+        return [(28 * A, 0, 0)]            # every amplitude read, the 3/4 that change written
+    if name == "dm_oneQubitDephasing":
+        return [(16 * A, 0, 0)]
+    if name == "dm_twoQubitDepolarising":
+        a, b = sorted(op[1:3])
+        return [(32 * A, 0, 0)] if b < thr else ([(32 * A + 4 * A, 2 * A, 0)] if a < thr else [(32 * A + 8 * A, 8 * A, 0)])
+    if name == "dm_damping":
+        return [(32 * A, 0, 0)] if op[1] < thr else [(40 * A, 8 * A, 0)]
+    if name == "dm_expecPauliString":
+        T = len(op[1])
+        return [(min(16 * A, 32.0 * T * (1 << nq) / (1 << k)), 0, 0)]
+    if name == "dm_partialTrace":
+        t = len(op[1])
+        npre = sum(1 for q in op[1] if q + nq >= L)
+        r = relocation(npre)
+        return [(16 * A / (1 << t) + 16 * A / (1 << (2 * t)), 0, 0)] + ([(r[0], r[1], 0.0)] if npre else [])
+    raise ValueError(name)
+
+
+def bound_ms(cost, peaks):
+    """sum over the phases of one call of max(HBM time, NVLink time, FP64 time)."""
+    return sum(max(c[0] / (peaks["hbm_GBs"] * 1e9), c[1] / (peaks["nvlink_GBs_per_dir"] * 1e9), c[2] / (peaks["fp64_TFLOPs"] * 1e12)) for c in cost) * 1e3
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -132,15 +263,14 @@ def gates_equiv(num_gates, num_qubits, seconds):
 # ------------------------------------------------------------------------------------------------ reference arm
 
 def run_reference(args, world, rank):
-    """The reference's own CPU code path (real reference build when present, else unavailable) on a bounded sample."""
+    """The reference's own CPU code path (real reference build when present, else unavailable) on a bounded sample: the SAME
+    sweep on a 30-qubit state (smaller only if host RAM or the time budget forces it -- never a single pass scaled up),
+    np = N ranks x (cores / N) OpenMP threads, reported in the product arm's metric (per-amplitude normalised)."""
     if rank != 0:
         return
     from oracle import refrun
     nodes = max(1, args.gpus)
     k = nodes.bit_length() - 1
-    nq = REF_SAMPLE_QUBITS + k
-    while (16 << nq) * 2 > 0.5 * os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES"):
-        nq -= 1
     config = {"workload": "oneTargGate + manyCtrlOneTargGate sweep over all target positions (BASELINE configs[1])",
               "qubits": 32 + k, "gates_per_step": 2 * (32 + k), "parallelism": "%d-way state sharding" % nodes, "l2": "inputs >> L2"}
     line = {"impl": "reference", "metric": "34-qubit-equivalent SV gates/s", "unit": "gates/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -150,34 +280,45 @@ def run_reference(args, world, rank):
         line["unavailable"] = "oracle/_ref/ref_driver not built (needs /root/reference at build time)"
         print(json.dumps(line), flush=True)
         return
-    ops = make_sweep(nq)
     cores = os.cpu_count() or 1
     threads = max(1, cores // nodes)
+    budget_s = 200.0
+    ram = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    nq = REF_SAMPLE_QUBITS
+    while (16 << nq) * 2 > 0.5 * ram:
+        nq -= 1
+    # a short probe (same sweep, 24 qubits) gives the per-amplitude cost; the sample is the largest size <= 30 qubits at which
+    # one untimed + at least two timed passes fit the budget
+    probe_q = 24
+    probe = refrun.run("sv", probe_q, make_sweep(probe_q), num_nodes=nodes, init_seed=SEED, threads=threads, want_state=False, timed=True, timeout=600)
+    per_gate_amp = probe["seconds"] / (2 * probe_q * (1 << probe_q))
+    timed_passes = max(2, min(args.steps, 3))
+    while nq > 26 and (1 + timed_passes) * per_gate_amp * 2 * nq * (1 << nq) * 1.15 > budget_s:
+        nq -= 1
+    ops = make_sweep(nq)
     times = []
-    for i in range(args.warmup + args.steps):
-        if i >= 1 and (time.time() - t_start) > 240:      # keep the whole arm within a few minutes
-            break
-        if i == 0:
-            t_start = time.time()
+    for i in range(1 + timed_passes):
         r = refrun.run("sv", nq, ops, num_nodes=nodes, init_seed=SEED, threads=threads, want_state=False, timed=True, timeout=1800)
-        if i >= min(args.warmup, 1):
+        if i >= 1:
             times.append(r["seconds"])
     sec = float(np.mean(times))
     val = gates_equiv(len(ops), nq, sec)
-    sample = "%d-qubit sweep (%d gates), %d rank(s) x %d OpenMP threads, %d timed pass(es); %s" % (
-        nq, len(ops), nodes, threads, len(times), os.path.basename(refrun.driver_path()))
+    sample = "%d-qubit sweep (%d gates), %d rank(s) x %d OpenMP threads, 1 untimed + %d timed passes (%s s); %s" % (
+        nq, len(ops), nodes, threads, len(times), ", ".join("%.2f" % t for t in times), os.path.basename(refrun.driver_path()))
     line.update({"value": val, "ms_per_step": sec * 1e3, "sample_qubits": nq, "gates_per_s_actual_at_sample": len(ops) / sec,
+                 "amp_updates_per_s": len(ops) * float(1 << nq) / sec,
                  "cpu_baseline": {"value": val, "unit": "gates/s", "cores": threads * nodes, "kind": "reference", "sample": sample},
                  "e2e": {"value": val, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0, "steps_timed": len(times)})
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline_sample(budget_s=25.0):
-    """Rank 0, N=1: the real reference (kind=reference) or the C port (kind=port) on a bounded sample of the sweep."""
+def cpu_baseline_sample():
+    """Rank 0, N=1: the real reference (kind=reference) or the C port (kind=port) on a bounded sample of the sweep (28 qubits:
+    about 10 s of CPU work on 16 cores; the reference ARM uses the 30-qubit sample)."""
     from oracle import refrun
     cores = os.cpu_count() or 1
-    nq = REF_SAMPLE_QUBITS
+    nq = 28
     ops = make_sweep(nq)
     if refrun.available():
         r = refrun.run("sv", nq, ops, num_nodes=1, init_seed=SEED, threads=cores, want_state=False, timed=True, timeout=1800)
@@ -198,25 +339,229 @@ def cpu_baseline_sample(budget_s=25.0):
 
 # ------------------------------------------------------------------------------------------------ product arm
 
+class Job:
+    """One rank of the product run: library handles + the torch.distributed plumbing (barrier, max over ranks)."""
+
+    def __init__(self, world, rank, local_rank):
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+        self.k = world.bit_length() - 1
+        self.torch = self.dist = None
+        if world > 1:
+            import torch                                  # load torch's NCCL before ours; torch.distributed = plumbing only
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+        self.dfsa = importlib.import_module(PKG)
+        self.lib = self.dfsa.device_lib()
+        self.check = self.dfsa.api.check
+        self.dfsa.comm_init()                             # RANK/WORLD_SIZE/LOCAL_RANK from the launcher
+        assert self.dfsa.comm_size() == world and self.dfsa.comm_rank() == rank
+        if world > 1:
+            self.torch.cuda.set_device(local_rank)
+            self.dist.init_process_group("nccl", device_id=self.torch.device("cuda", local_rank))
+        self.lib.dfsa_comm_fused_active.restype = C.c_int
+
+    def event(self):
+        e = C.c_void_p()
+        self.check(self.lib.dfsa_event_create(C.byref(e)))
+        return e
+
+    def record(self, e):
+        self.check(self.lib.dfsa_event_record(e))
+
+    def elapsed(self, e0, e1):
+        ms = C.c_double()
+        self.check(self.lib.dfsa_event_elapsed_ms(e0, e1, C.byref(ms)))
+        return ms.value
+
+    def barrier(self):
+        self.dfsa.comm_synch()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([float(v)], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(self, v):
+        return -self.max_over_ranks(-float(v))
+
+    def broadcast_obj(self, obj):
+        if self.world == 1:
+            return obj
+        box = [obj]
+        self.dist.broadcast_object_list(box, src=0)
+        return box[0]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.barrier()
+            self.dist.destroy_process_group()
+        self.dfsa.comm_end()
+
+
+def measure_nvlink(job, st):
+    """GB/s per direction with every pair of ranks (rank ^ 1) pulling each other's shard at once: remote loads from a kernel
+    (what the fused exchange kernels do) and the copy engine. None at N = 1."""
+    if job.world == 1 or job.lib.dfsa_comm_fused_active() == 0:
+        return None
+    out = {}
+    shard_bytes = 16.0 * st.num_amps_per_node
+    for mode, label in ((0, "kernel_remote_loads"), (1, "copy_engine")):
+        best = None
+        for rep in range(3):
+            ms = C.c_double()
+            job.check(job.lib.dfsa_xk_measure_link(st.handle, job.rank ^ 1, mode, C.byref(ms)))
+            t = job.max_over_ranks(ms.value)
+            if rep > 0:
+                best = t if best is None else min(best, t)
+        out[label + "_GBs_per_dir"] = shard_bytes / (best * 1e-3) / 1e9
+    out["how"] = "all %d pairs (rank ^ 1) pull each other's %d GiB shard simultaneously, both directions; best of 2 after warm-up, max over ranks" % (job.world // 2, int(shard_bytes) >> 30)
+    return out
+
+
+def parity_selfcheck(job):
+    """Small-size parity on the transports the timed region uses, against the C oracle (virtual ranks), compared on the device."""
+    import cases
+    from oracle import capi
+    k, world, rank = job.k, job.world, job.rank
+    rng = np.random.default_rng(SEED + 1)
+    nq = 24 + k
+    L = nq - k
+    sv_ops = make_sweep(nq, seed=SEED + 2)
+    top = list(range(nq - 1, nq - 1 - max(k, 1), -1))                 # the prefix qubits (or just the top qubit at N = 1)
+    for rep in range(2):
+        t5 = top[: min(len(top), 1 + rep)] + [int(x) for x in rng.permutation(L)[: 5 - min(len(top), 1 + rep)]]
+        sv_ops.append(("sv_manyTargGate", [int(x) for x in rng.permutation(t5)], haar(rng, 32)))
+        sv_ops.append(("sv_pauliGadget", [top[0], 3, 11, top[-1]] if len(top) > 1 else [top[0], 3, 11], [1, 3, 2, 2][: (4 if len(top) > 1 else 3)], float(rng.uniform(-3, 3))))
+        sv_ops.append(("sv_phaseGadget", [top[0], 0, 7], float(rng.uniform(-3, 3))))
+        sv_ops.append(("sv_swapGate", top[0], 5 + rep))
+        if k >= 2:
+            sv_ops.append(("sv_swapGate", top[0], top[1]))
+        sv_ops.append(("sv_pauliTensor", [top[-1], 2], [2, 1]))
+    N = 12
+    dm_ops = []
+    for q in (0, N - 1, N - 2, 5):
+        dm_ops.append(("dm_manyTargGate", [q, (q + 1) % N], haar(rng, 4)))
+        dm_ops.append(("dm_oneQubitDepolarising", q, float(rng.uniform(0, 0.5))))
+        dm_ops.append(("dm_twoQubitDephasing", q, (q + 1) % N, float(rng.uniform(0, 0.5))))
+        dm_ops.append(("dm_damping", q, float(rng.uniform(0, 0.5))))
+    dm_ops.append(("dm_twoQubitDepolarising", N - 1, 3, 0.21))
+    dm_ops.append(("dm_twoQubitDepolarising", N - 1, N - 2, 0.17))
+    dm_ops.append(("dm_oneQubitDephasing", N - 1, 0.1))
+    suites = [("sv", nq, sv_ops, "%d-qubit sweep (%d gates) + config-3 mini-circuit" % (nq, 2 * nq)), ("dm", N, dm_ops, "12-qubit noisy density-matrix layer (config 4's ops)")]
+
+    # the oracle's results: rank 0 computes, the others map the file
+    path = "/dev/shm/dfsa_parity_%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getuid())
+    t0 = time.time()
+    if rank == 0:
+        os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
+        for kind, n, ops, _ in suites:
+            o = capi.OracleState(kind, n, world)
+            o.init_hash(SEED)
+            for op in ops:
+                cases.apply(o, op)
+            np.save(path + "_" + kind + ".npy", o.get_amps())
+            del o
+    oracle_s = time.time() - t0
+    job.barrier()
+    if world > 1:
+        job.dist.barrier()
+    results, worst, ok = [], 0.0, True
+    modes = [("fused", 1), ("staged", 0)] if world > 1 else [("single", -1)]
+    for kind, n, ops, what in suites:
+        want = np.load(path + "_" + kind + ".npy", mmap_mode="r")
+        st = job.dfsa.DeviceState(kind, n)
+        ref = job.dfsa.DeviceState(kind, n)
+        A = st.num_amps_per_node
+        ref.set_local_amps(np.ascontiguousarray(want[rank * A:(rank + 1) * A]))
+        for label, mode in modes:
+            if world > 1:
+                job.check(job.lib.dfsa_comm_set_fused(mode))
+            active = job.lib.dfsa_comm_fused_active()
+            st.init_hash(SEED)
+            for op in ops:
+                cases.apply(st, op)
+            d, ne, mr = st.compare(ref)
+            good = bool(d <= PARITY_TOL * max(1.0, mr))
+            ok = ok and good
+            worst = max(worst, d if d == d else float("inf"))
+            results.append({"what": what, "exchange": label, "fused_active": active, "max_abs_diff": d, "max_abs_ref": mr, "ok": good})
+        st.close()
+        ref.close()
+    if world > 1:
+        job.check(job.lib.dfsa_comm_set_fused(-1))
+        job.dist.barrier()
+    if rank == 0:
+        for kind, _, _, _ in suites:
+            try:
+                os.unlink(path + "_" + kind + ".npy")
+            except OSError:
+                pass
+    return {"ok": ok, "max_abs_diff": worst, "tol": "%g * max(1, max|ref|)" % PARITY_TOL, "transport": job.lib.dfsa_comm_transport().decode(),
+            "checker": "oracle/dfsa_oracle.c with %d virtual rank(s) (%.1f s on rank 0), compared on the device (dfsa_state_compare)" % (world, oracle_s),
+            "cases": results}
+
+
+def run_config(job, name, peaks, reps, dm_qubits=None):
+    """One BASELINE config: per-op device times (max over ranks) and roofline fractions."""
+    import cases
+    kind, nq, ops, desc = config_workload(name, job.world, dm_qubits=dm_qubits)
+    k = job.k
+    st = job.dfsa.DeviceState(kind, nq)
+    st.init_hash(SEED)
+    per_type, total = {}, []
+    for rep in range(reps + 1):                              # rep 0 = warm-up
+        evs = [(job.event(), job.event()) for _ in ops]
+        job.barrier()
+        for (e0, e1), op in zip(evs, ops):
+            job.record(e0)
+            r = cases.apply(st, op)
+            job.record(e1)
+            if op[0] == "dm_partialTrace":
+                r.close()
+                st.close()                                   # partialTrace mutates its input: start from a fresh state
+                st = job.dfsa.DeviceState(kind, nq)
+                st.init_hash(SEED)
+        job.barrier()
+        if rep == 0:
+            continue
+        tot = 0.0
+        for (e0, e1), op in zip(evs, ops):
+            v = job.max_over_ranks(job.elapsed(e0, e1))
+            tot += v
+            label = op[0]
+            if op[0] == "dm_partialTrace":
+                label += " (relocating)" if max(op[1]) + nq >= (2 * nq - k) else " (local)"
+            cost = op_cost(op, kind, nq, k)
+            if any(c[1] > 0 for c in cost) and op[0] not in ("dm_partialTrace",):
+                label += " [exchange]"
+            d = per_type.setdefault(label, {"n": 0, "ms": 0.0, "bound_ms": 0.0})
+            d["n"] += 1
+            d["ms"] += v
+            d["bound_ms"] += bound_ms(cost, peaks)
+        total.append(tot)
+    st.close()
+    step_ms = float(np.mean(total))
+    bound_total = sum(d["bound_ms"] for d in per_type.values()) / reps
+    return {"what": desc, "qubits": nq, "kind": kind, "ops_per_pass": len(ops), "passes_timed": reps, "ms_per_pass": step_ms,
+            "gates_per_s": len(ops) / (step_ms * 1e-3), "roofline_ms_per_pass": bound_total, "roofline_frac": bound_total / step_ms,
+            "per_op": {lab: {"count_per_pass": d["n"] // reps, "mean_ms": d["ms"] / d["n"], "roofline_frac": d["bound_ms"] / d["ms"]} for lab, d in sorted(per_type.items())}}
+
+
 def run_product(args, world, rank, local_rank):
     import cases
     # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version there) go to stderr
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    if world > 1:
-        import torch                                  # load torch's NCCL before ours; torch.distributed = plumbing only
-        import torch.distributed as dist
-    dfsa = importlib.import_module(PKG)
-    lib = dfsa.device_lib()
-    check = dfsa.api.check
-    dfsa.comm_init()                                  # RANK/WORLD_SIZE/LOCAL_RANK from the launcher
-    assert dfsa.comm_size() == world and dfsa.comm_rank() == rank
-    if world > 1:
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    job = Job(world, rank, local_rank)
+    lib, check, dfsa = job.lib, job.check, job.dfsa
+    k = job.k
 
-    k = world.bit_length() - 1
+    # ---- parity first (small states, real transports)
+    parity = None if args.skip_parity else parity_selfcheck(job)
+
     nq = args.qubits if args.qubits else 32 + k
     ops = make_sweep(nq)
     L = nq - k
@@ -224,77 +569,83 @@ def run_product(args, world, rank, local_rank):
     st = dfsa.DeviceState("sv", nq)
     st.init_hash(SEED)
 
-    def event():
-        e = C.c_void_p()
-        check(lib.dfsa_event_create(C.byref(e)))
-        return e
+    hbm_peak, peak_src = measured_peak()
+    nvlink = measure_nvlink(job, st)
+    peaks = {"hbm_GBs": hbm_peak, "fp64_TFLOPs": FP64_PEAK_TFLOPS,
+             "nvlink_GBs_per_dir": nvlink["kernel_remote_loads_GBs_per_dir"] if nvlink else NVLINK_FALLBACK_GBS,
+             "nvlink_source": "measured in this run (kernel remote loads, all pairs at once)" if nvlink else "not used at 1 GPU (fallback %g)" % NVLINK_FALLBACK_GBS,
+             "hbm_source": peak_src, "fp64_source": "profiles/r01_fp64_peak_b200.jsonl (DFMA 36.6, DMMA 37.0 TFLOP/s)"}
 
-    def barrier():
-        dfsa.comm_synch()
-
-    def run_step(per_gate=None):
-        for i, op in enumerate(ops):
+    def run_step(per_gate=None, the_ops=ops):
+        for i, op in enumerate(the_ops):
             if per_gate is not None:
-                check(lib.dfsa_event_record(per_gate[i][0]))
+                job.record(per_gate[i][0])
             cases.apply(st, op)
             if per_gate is not None:
-                check(lib.dfsa_event_record(per_gate[i][1]))
+                job.record(per_gate[i][1])
 
+    # ---- full-size self-consistency (also the first warm-up passes): the sweep, then its inverse, against the initial state
+    selfcheck = None
+    if not args.skip_parity:
+        inv = inverse_ops(ops)
+        run_step()
+        run_step(the_ops=inv)
+        d, ne, mr = st.compare_hash(SEED)
+        selfcheck = {"what": "%d-qubit sweep then its inverse (%d gates) vs the regenerated initial state, all 2^%d amplitudes, on the device" % (nq, 2 * len(ops), nq),
+                     "max_abs_diff": d, "max_abs_ref": mr, "ok": bool(d <= 1e-12)}
+        st.init_hash(SEED)
     for _ in range(max(args.warmup, 3)):
         run_step()
-    barrier()
+    job.barrier()
 
     # ---- timed region: K steps, device-timed, per-gate events inside for the roofline of the dominant kernel
-    per_gate = [[(event(), event()) for _ in ops] for _ in range(args.steps)]
-    e0, e1 = event(), event()
+    per_gate = [[(job.event(), job.event()) for _ in ops] for _ in range(args.steps)]
+    e0, e1 = job.event(), job.event()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = lib.dfsa_launch_count()
-    barrier()
-    check(lib.dfsa_event_record(e0))
+    job.barrier()
+    job.record(e0)
     for s in range(args.steps):
         run_step(per_gate[s])
-    check(lib.dfsa_event_record(e1))
-    barrier()
+    job.record(e1)
+    job.barrier()
     launches = int(lib.dfsa_launch_count() - launches0)
     clocks = sampler.stop() if rank == 0 else None
-    ms = C.c_double()
-    check(lib.dfsa_event_elapsed_ms(e0, e1, C.byref(ms)))
-    total_ms = ms.value
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = job.max_over_ranks(job.elapsed(e0, e1))
 
     # dominant kernel: local oneTargGate (ctrlOneTarg kernel with no controls), 32*A bytes per launch
-    one_ms = []
-    for s in range(args.steps):
-        for i, op in enumerate(ops):
-            if op[0] == "sv_oneTargGate" and op[1] < L:
-                check(lib.dfsa_event_elapsed_ms(per_gate[s][i][0], per_gate[s][i][1], C.byref(ms)))
-                one_ms.append(ms.value)
+    one_ms = [job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(args.steps) for i, op in enumerate(ops) if op[0] == "sv_oneTargGate" and op[1] < L]
     one_avg_ms = float(np.mean(one_ms))
-    if args.per_gate and rank == 0:
-        for i, op in enumerate(ops):
-            acc = 0.0
-            for s_ in range(args.steps):
-                check(lib.dfsa_event_elapsed_ms(per_gate[s_][i][0], per_gate[s_][i][1], C.byref(ms)))
-                acc += ms.value
-            hb, nb = op_algorithmic_bytes(op, nq, k)
-            what = "%s t=%d%s" % (op[0][3:], op[1] if op[0] == "sv_oneTargGate" else op[2], "" if op[0] == "sv_oneTargGate" else " ctrls=%s" % (op[1],))
-            bound = max(hb / (measured_peak()[0] * 1e9), nb / 770e9) * 1e3
-            sys.stderr.write("gate %2d %-48s %9.3f ms  (roofline %8.3f ms, %5.1f%%)\n" % (i, what, acc / args.steps, bound, 100 * bound / (acc / args.steps)))
-    peak, peak_src = measured_peak()
+    gate_ms = [job.max_over_ranks(float(np.mean([job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(args.steps)]))) for i in range(len(ops))] if (args.per_gate or world > 1) else None
+    exchange_summary = None
+    if gate_ms is not None:
+        ex = [(i, op) for i, op in enumerate(ops) if any(c[1] > 0 for c in op_cost(op, "sv", nq, k))]
+        if ex:
+            t = sum(gate_ms[i] for i, _ in ex)
+            b = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for _, op in ex)
+            nvb = sum(sum(c[1] for c in op_cost(op, "sv", nq, k)) for _, op in ex)
+            exchange_summary = {"gates": len(ex), "ms": t, "bound_ms": b, "frac_of_measured_nvlink_line": b / t, "achieved_GBs_per_dir": nvb / (t * 1e-3) / 1e9}
+        if args.per_gate and rank == 0:
+            for i, op in enumerate(ops):
+                what = "%s t=%d%s" % (op[0][3:], op[1] if op[0] == "sv_oneTargGate" else op[2], "" if op[0] == "sv_oneTargGate" else " ctrls=%s" % (op[1],))
+                b = bound_ms(op_cost(op, "sv", nq, k), peaks)
+                sys.stderr.write("gate %2d %-48s %9.3f ms  (roofline %8.3f ms, %5.1f%%)\n" % (i, what, gate_ms[i], b, 100 * b / gate_ms[i]))
     achieved = 32.0 * shard_amps / (one_avg_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
-    # whole-step roofline: sum over gates of max(HBM bytes / HBM peak, NVLink bytes / 770 GB/s)
-    bound_ms = 0.0
-    for op in ops:
-        hb, nb = op_algorithmic_bytes(op, nq, k)
-        bound_ms += max(hb / (peak * 1e9), nb / 770e9) * 1e3
+    bound_step = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op in ops)
     step_ms = total_ms / args.steps
     value = gates_equiv(len(ops), nq, step_ms * 1e-3)
+
+    # ---- BASELINE config 3 (state-vector circuit; its own state -- the sweep state is needed again for e2e at the same size)
+    configs = {}
+    if not args.skip_configs:
+        st.close()
+        st = None
+        configs["config3_circuit"] = run_config(job, "circuit", peaks, reps=2)
+        st = dfsa.DeviceState("sv", nq)
+        st.init_hash(SEED)
 
     # ---- e2e: the same step through the host API with HOST buffers: pinned-host -> HBM upload of the shard,
     #      the sweep, HBM -> pinned-host download of the result, every step
@@ -310,11 +661,7 @@ def run_product(args, world, rank, local_rank):
                     mem_avail = int(ln.split()[1]) * 1024
     except OSError:
         pass
-    ram_ok = shard_bytes * world <= 0.6 * mem_avail
-    if world > 1:
-        t = torch.tensor([1.0 if ram_ok else 0.0], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        ram_ok = bool(t.item() > 0.5)
+    ram_ok = job.min_over_ranks(1.0 if shard_bytes * world <= 0.6 * mem_avail else 0.0) > 0.5
     if not ram_ok:
         e2e = {"value": None, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "skipped": "host RAM too small to pin %d x %d GiB (MemAvailable %d GiB)" % (world, shard_bytes >> 30, mem_avail >> 30)}
@@ -322,23 +669,26 @@ def run_product(args, world, rank, local_rank):
         hp = C.cast(host, C.POINTER(C.c_double))
         check(lib.dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))     # fill the host buffer (untimed)
         e2e_steps = max(1, min(args.steps, 2))
-        barrier()
+        job.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             check(lib.dfsa_state_upload(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))
             run_step()
             check(lib.dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        job.barrier()
+        e2e_s = job.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": gates_equiv(len(ops), nq, e2e_s), "unit": "gates/s", "h2d_bytes_per_step": shard_bytes * world,
                "d2h_bytes_per_step": shard_bytes * world, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                "what": "per step: upload of every rank's shard from pinned host memory, the sweep through the host C++ API, download of the result"}
         lib.dfsa_host_free_pinned(host)
     norm2 = st.norm2()
+    st.close()
+
+    # ---- BASELINE configs 4 and 5 (density matrices; the 64 GiB state-vector shard is released first)
+    if not args.skip_configs:
+        for N in ((14, 16) if world == 1 else (16,)):
+            configs["config4_noisy_dm_%dq" % N] = run_config(job, "dm", peaks, reps=2, dm_qubits=N)
+        configs["config5_expec_ptrace_16q"] = run_config(job, "expec", peaks, reps=2, dm_qubits=16)
 
     if rank == 0:
         line = {
@@ -348,24 +698,29 @@ def run_product(args, world, rank, local_rank):
             "config": {"workload": "oneTargGate + manyCtrlOneTargGate sweep over all target positions (BASELINE configs[1])",
                        "qubits": nq, "gates_per_step": len(ops), "shard_GiB_per_gpu": shard_bytes / 2 ** 30,
                        "parallelism": "%d-way state sharding (top %d qubits = rank)" % (world, k), "transport": lib.dfsa_comm_transport().decode(),
+                       "exchange": {0: "staged", 1: "fused, host-synchronised", 2: "fused, stream-ordered"}[lib.dfsa_comm_fused_active()] if world > 1 else "none",
                        "l2": "inputs >> L2 (every gate streams the whole %d GiB shard)" % (shard_bytes >> 30)},
             "gates_per_s_actual": len(ops) / (step_ms * 1e-3),
-            "step_roofline": {"bound_ms": bound_ms, "frac": bound_ms / step_ms, "how": "sum over gates of max(HBM bytes/peak, NVLink bytes per direction/770 GB/s)"},
-            "roofline": {"bound": "hbm", "kernel": "streamKernel<ctrlOneTarg> (local oneTargGate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
+            "amp_updates_per_s": len(ops) * float(1 << nq) / (step_ms * 1e-3),
+            "step_roofline": {"bound_ms": bound_step, "frac": bound_step / step_ms,
+                              "how": "sum over gates of max(HBM bytes / HBM peak, NVLink bytes per direction / measured NVLink rate)"},
+            "roofline": {"bound": "hbm", "kernel": "streamKernel<ctrlOneTarg> (local oneTargGate)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
                          "avg_launch_ms": one_avg_ms, "launches_timed": len(one_ms),
                          "traffic": (traffic["dram_over_algorithmic"] * 32 * shard_amps) if traffic else None,
-                         "traffic_note": (traffic or {}).get("note")},
+                         "traffic_note": ("NOT measured in this run: " + traffic.get("note", "")) if traffic else None},
+            "peaks": peaks, "nvlink": nvlink, "exchange_gates": exchange_summary,
+            "parity": parity, "selfcheck": selfcheck, "configs": configs,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "norm2_after": norm2,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
-    st.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
-    dfsa.comm_end()
+    job.close()
+    bad = (parity is not None and not parity["ok"]) or (selfcheck is not None and not selfcheck["ok"])
+    if bad:
+        sys.stderr.write("bench.py: PARITY FAILURE (see the parity / selfcheck blocks of the JSON line)\n")
+        sys.exit(3)
 
 
 def main():
@@ -376,6 +731,8 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--qubits", type=int, default=0, help="override the state size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-parity", action="store_true", help="no parity / self-consistency blocks (debugging only)")
+    ap.add_argument("--skip-configs", action="store_true", help="no BASELINE configs 3-5 block (debugging only)")
     ap.add_argument("--per-gate", action="store_true", help="print the mean device time of every gate of the step to stderr")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))

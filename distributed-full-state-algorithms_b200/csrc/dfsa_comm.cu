@@ -866,6 +866,40 @@ extern "C" int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, d
     return DFSA_OK;     // the reference needs a global barrier here to protect the sender's buffer; stream order does that job
 }
 
+// Link microbenchmark (the NVLink line of the roofline must be measured on the box, not assumed): every rank pulls
+// its partner's whole shard into its own exchange buffer, all pairs at once, both directions -- the traffic pattern of a
+// prefix gate without the arithmetic. mode 0: remote loads from a kernel (what the fused kernels do), mode 1: copy engine
+// (cudaMemcpyAsync from the peer mapping). *ms = device time of this rank's pull (CUDA events on the compute stream).
+int dfsaLaunchPull(dfsa_state* s, const double2* remote);
+extern "C" int dfsa_xk_measure_link(dfsa_state* s, int pairRank, int mode, double* ms) {
+    DFSA_TRY(dfsaEnsureDevice());
+    DFSA_REQUIRE(s && ms && (mode == 0 || mode == 1), "bad argument");
+    DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank));
+    DFSA_REQUIRE(fusedAvailable(), "peer shards are not mapped (staged transport)");
+    DfsaContext& c = dfsaCtx();
+    cudaEvent_t e0, e1;
+    DFSA_CUDA(cudaEventCreate(&e0));
+    DFSA_CUDA(cudaEventCreate(&e1));
+    const size_t bytes = s->numAmps * sizeof(double2);
+    int rc = fusedGroupExchange(s, &pairRank, 1,
+        [&](const double2* const* remote) -> int {
+            DFSA_CUDA(cudaEventRecord(e0, c.compute));
+            if (mode == 0) DFSA_TRY(dfsaLaunchPull(s, remote[0]));
+            else DFSA_CUDA(cudaMemcpyAsync(s->arr[DFSA_BUFFER], remote[0], bytes, cudaMemcpyDeviceToDevice, c.compute));
+            DFSA_CUDA(cudaEventRecord(e1, c.compute));
+            return (int)DFSA_OK;
+        },
+        [](dfsa_state*) { return (int)DFSA_OK; });                      // the pulled copy is discarded: no array swap
+    if (rc == DFSA_OK) {
+        float f = 0.f;
+        if (cudaEventSynchronize(e1) != cudaSuccess || cudaEventElapsedTime(&f, e0, e1) != cudaSuccess) { dfsaSetError("link timing failed"); rc = DFSA_ERR_CUDA; }
+        *ms = f;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
 // manyCtrlOneTargGate, prefix target + suffix controls (distributed_statevector.hpp:43-78)
 extern "C" int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls, unsigned numCtrls, int pairRank, const double f0[2], const double f1[2]) {
     DFSA_TRY(dfsaEnsureDevice());

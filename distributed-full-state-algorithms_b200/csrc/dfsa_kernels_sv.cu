@@ -233,6 +233,14 @@ int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRa
                  : launchFusedPauli<false>(s, remote, pairRank, maskXY, maskYZ, numY, f, h);
 }
 
+// buffer = remote (the link microbenchmark of dfsa_xk_measure_link: a prefix gate's traffic without its arithmetic)
+int dfsaLaunchPull(dfsa_state* s, const double2* remote) {
+    double2* out = s->arr[DFSA_BUFFER];
+    auto ld = [=] __device__(uint64_t i) { return Amp1{remote[i]}; };
+    auto st = [=] __device__(uint64_t i, const Amp1& v) { out[i] = v.a; };
+    return launchStream<2, Amp1>(s->numAmps, ld, st);
+}
+
 // K18: distributed_densitymatrix.hpp:44-49 (amp *= -1) generalised to a complex factor.
 extern "C" int dfsa_k_scaleAll(dfsa_state* s, const double factor[2]) {
     DFSA_TRY(dfsaEnsureDevice());

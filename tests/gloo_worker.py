@@ -122,8 +122,14 @@ def main():
     t = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     assert float(t.item()) == 10.0 + world - 1
-    hb, nb = bench.op_algorithmic_bytes(("sv_oneTargGate", 32, None), 33, 1)
-    assert nb == 16 * 2 ** 32 and hb == 48 * 2 ** 32
+    (hb, nb, fl), = bench.op_cost(("sv_oneTargGate", 32, None), "sv", 33, 1)
+    assert nb == 16 * 2 ** 32 and hb == 48 * 2 ** 32 and fl == 0
+    # a 5-target gate with 2 prefix targets at 4 ranks: the local pass + a relocation before and after, 3/4 of a shard each way
+    cost = bench.op_cost(("sv_manyTargGate", [33, 0, 32, 7, 9], None), "sv", 34, 2)
+    assert len(cost) == 3 and cost[0] == (32 * 2.0 ** 32, 0.0, 6.0 * 32 * 2.0 ** 32) and cost[1] == cost[2] == (32 * 2.0 ** 32, 0.75 * 16 * 2.0 ** 32, 0.0)
+    # the ops of one sweep followed by their inverses are the identity: same number of gates, reversed order
+    inv = bench.inverse_ops(sweep)
+    assert len(inv) == len(sweep) and inv[0][0] == sweep[-1][0]
     dist.barrier()
     dist.destroy_process_group()
     print("gloo worker %d/%d ok (%d symmetric exchanges checked)" % (rank, world, checked))
