@@ -127,13 +127,32 @@ def config_workload(name, world, seed=7, dm_qubits=None):
     raise ValueError(name)
 
 
-def op_cost(op, kind, nq, k, lazy_relocation=False):
-    """(hbm_bytes, nvlink_bytes_per_direction, flops) per rank for one API call -- the ALGORITHMIC work, not what a
-    particular implementation moves. nq = n (sv) or N (dm); A = amplitudes per rank."""
+def op_cost(op, kind, nq, k, where=None, lazy=False):
+    """[(hbm_bytes, nvlink_bytes_per_direction, flops), ...] per rank for the phases of one API call -- the ALGORITHMIC work
+    (SURVEY 8d), not what a particular implementation moves. nq = n (sv) or N (dm); A = amplitudes per rank.
+    `where` = the state's current qubit layout (index bit of every logical qubit, host/layout.hpp): whether a gate needs an
+    exchange depends on where its qubits sit NOW. lazy: a dense gate relocates its prefix targets once and leaves them
+    (the undo is a separate, deferred step: "layout restore"); otherwise twice, as the reference does."""
     name = op[0]
     bits = nq if kind == "sv" else 2 * nq
     L = bits - k
     A = float(1 << L)
+    if name == "layout_restore":
+        npre = op[1]
+        return [(32 * A, (1.0 - 0.5 ** npre) * 16 * A, 0.0)] if npre else []
+    if where is not None and name.startswith("sv_"):
+        m = lambda qs: [where[q] for q in qs]           # noqa: E731
+        if name == "sv_oneTargGate":
+            op = (name, where[op[1]]) + tuple(op[2:])
+        elif name == "sv_manyCtrlOneTargGate":
+            op = (name, m(op[1]), where[op[2]]) + tuple(op[3:])
+        elif name == "sv_swapGate":
+            op = (name, where[op[1]], where[op[2]])
+        else:
+            op = (name, m(op[1])) + tuple(op[2:])
+    elif where is not None and name in ("dm_manyTargGate",):
+        pass                                               # handled below through many_targ (ket and bra bits mapped there)
+    mapq = (lambda q: where[q]) if where is not None else (lambda q: q)
 
     def relocation(npre):
         # npre (suffix, prefix) qubit pairs swapped in one step: every rank keeps 2^-npre of its shard and pulls the rest
@@ -144,8 +163,9 @@ def op_cost(op, kind, nq, k, lazy_relocation=False):
         npre = sum(1 for t in targets if t >= L)
         r = relocation(npre)
         # FP64 work in the cheapest known form of the complex product (3M: 6 * 2^t flop per amplitude; the 4M form is 8 * 2^t).
-        # The reference relocates before AND after the gate (distributed_statevector.hpp:213-223): two relocations.
-        return [(32 * A, 0.0, 6.0 * (1 << len(targets)) * A)] + [(r[0], r[1], 0.0)] * (2 if npre else 0)
+        # The reference relocates before AND after the gate (distributed_statevector.hpp:213-223): two relocations; with the
+        # lazy layout one (the undo is deferred and accounted for as "layout_restore").
+        return [(32 * A, 0.0, 6.0 * (1 << len(targets)) * A)] + [(r[0], r[1], 0.0)] * ((1 if lazy else 2) if npre else 0)
 
     if name == "sv_manyTargGate":
         return many_targ(op[1])
@@ -165,13 +185,15 @@ def op_cost(op, kind, nq, k, lazy_relocation=False):
         a, b = sorted(op[1:3])
         if b < L:
             return [(16 * A, 0, 0)]
-        return [(24 * A, 8 * A, 0)] if a < L else [(32 * A, 16 * A, 0)]
+        if a >= L:
+            return [] if lazy else [(32 * A, 16 * A, 0)]         # both on rank bits: a relabelling under the lazy layout
+        return [(24 * A, 8 * A, 0)]
     if name == "dm_manyTargGate":
         t = len(op[1])
         if t <= 2:
             # U (x) conj(U) on the 2t bits {targets, targets + N} is ONE pass over the shard
-            return many_targ(list(op[1]) + [q + nq for q in op[1]])
-        return many_targ(op[1]) + many_targ([q + nq for q in op[1]])
+            return many_targ([mapq(q) for q in op[1]] + [mapq(q + nq) for q in op[1]])
+        return many_targ([mapq(q) for q in op[1]]) + many_targ([mapq(q + nq) for q in op[1]])
     thr = nq - k
     if name == "dm_oneQubitDepolarising":
         return [(32 * A, 0, 0)] if op[1] < thr else [(48 * A, 8 * A, 0)]
@@ -510,11 +532,14 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
     k = job.k
     st = job.dfsa.DeviceState(kind, nq)
     st.init_hash(SEED)
+    lazy = bool(job.dfsa.host_lib().dfsa_host_lazyLayoutEnabled())
     per_type, total = {}, []
     for rep in range(reps + 1):                              # rep 0 = warm-up
-        evs = [(job.event(), job.event()) for _ in ops]
+        evs = [(job.event(), job.event()) for _ in range(len(ops) + 1)]
+        costs = []
         job.barrier()
         for (e0, e1), op in zip(evs, ops):
+            costs.append(op_cost(op, kind, nq, k, where=st.layout(), lazy=lazy))     # what the gate needs given where its qubits sit now
             job.record(e0)
             r = cases.apply(st, op)
             job.record(e1)
@@ -523,18 +548,29 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
                 st.close()                                   # partialTrace mutates its input: start from a fresh state
                 st = job.dfsa.DeviceState(kind, nq)
                 st.init_hash(SEED)
+        # the deferred part of the pass: put the relocated qubits back (nothing to do unless a dense gate left some displaced)
+        L = (nq if kind == "sv" else 2 * nq) - k
+        displaced = sum(1 for q, w in enumerate(st.layout()) if q >= L and w < L)
+        restore_op = ("layout_restore", displaced)
+        costs.append(op_cost(restore_op, kind, nq, k))
+        job.record(evs[-1][0])
+        st.restore_layout()
+        job.record(evs[-1][1])
         job.barrier()
         if rep == 0:
             continue
         tot = 0.0
-        for (e0, e1), op in zip(evs, ops):
+        for (e0, e1), op, cost in zip(evs, list(ops) + [restore_op], costs):
             v = job.max_over_ranks(job.elapsed(e0, e1))
             tot += v
             label = op[0]
+            if label == "layout_restore":
+                if not displaced:
+                    continue
+                label = "layout restore (deferred undo of relocations)"
             if op[0] == "dm_partialTrace":
                 label += " (relocating)" if max(op[1]) + nq >= (2 * nq - k) else " (local)"
-            cost = op_cost(op, kind, nq, k)
-            if any(c[1] > 0 for c in cost) and op[0] not in ("dm_partialTrace",):
+            elif any(c[1] > 0 for c in cost) and op[0] != "layout_restore":
                 label += " [exchange]"
             d = per_type.setdefault(label, {"n": 0, "ms": 0.0, "bound_ms": 0.0})
             d["n"] += 1
@@ -544,7 +580,7 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
     st.close()
     step_ms = float(np.mean(total))
     bound_total = sum(d["bound_ms"] for d in per_type.values()) / reps
-    return {"what": desc, "qubits": nq, "kind": kind, "ops_per_pass": len(ops), "passes_timed": reps, "ms_per_pass": step_ms,
+    return {"what": desc, "qubits": nq, "kind": kind, "ops_per_pass": len(ops), "passes_timed": reps, "lazy_layout": lazy, "ms_per_pass": step_ms,
             "gates_per_s": len(ops) / (step_ms * 1e-3), "roofline_ms_per_pass": bound_total, "roofline_frac": bound_total / step_ms,
             "per_op": {lab: {"count_per_pass": d["n"] // reps, "mean_ms": d["ms"] / d["n"], "roofline_frac": d["bound_ms"] / d["ms"]} for lab, d in sorted(per_type.items())}}
 

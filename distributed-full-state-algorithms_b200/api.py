@@ -140,7 +140,19 @@ class DeviceState:
 
     @property
     def handle(self):
+        """The C-ABI state. The C-ABI addresses amplitudes by index bit, so a lazily relabelled layout (host/layout.hpp) is put
+        back first."""
+        host_lib().dfsa_host_state_restoreLayout(self.p)
         return C.c_void_p(host_lib().dfsa_host_state_handle(self.p))
+
+    def layout(self):
+        """where[q] = index bit currently holding logical qubit q."""
+        out = (C.c_uint * self.total_bits)()
+        host_lib().dfsa_host_state_layout(self.p, out)
+        return list(out)
+
+    def restore_layout(self):
+        host_lib().dfsa_host_state_restoreLayout(self.p)
 
     # ---- state I/O
     def set_amps(self, amps):
@@ -162,6 +174,7 @@ class DeviceState:
         host_lib().dfsa_host_state_setHashAmps(self.p, C.c_ulonglong(seed))
 
     def init_plus(self):
+        host_lib().dfsa_host_state_resetLayout(self.p)
         check(device_lib().dfsa_state_init_plus(self.handle))
 
     def copy_from(self, other):
@@ -171,6 +184,7 @@ class DeviceState:
         """This rank's shard only (no global array on the host)."""
         a, ptr = _cplx(amps)
         assert a.size == self.num_amps_per_node
+        host_lib().dfsa_host_state_resetLayout(self.p)
         check(device_lib().dfsa_state_upload(self.handle, 0, C.c_uint64(0), C.c_uint64(a.size), ptr))
 
     def compare(self, other):

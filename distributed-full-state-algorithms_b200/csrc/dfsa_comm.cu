@@ -1019,6 +1019,80 @@ extern "C" int dfsa_x_allreduce_amp(double reim[2]) {
     return dfsaAllreduceDoubles(reim, 2, false);
 }
 
+// ---- expecPauliString: where the reduction kernel publishes its result, and how the host collects it
+namespace {
+bool      g_expecLocalOnly = false;
+unsigned* g_expecTicket = nullptr;        // device: block ticket of the last-block reduction
+double*   g_expecPinnedDev = nullptr;     // device view of the context's pinned page
+uint64_t  g_expecLocalSeq = 0;
+bool      g_expecLastGlobal = false;
+}
+
+int dfsaExpecLocalOnly(bool on) { g_expecLocalOnly = on; return DFSA_OK; }
+
+int dfsaExpecTarget(double** value, unsigned long long** flag, unsigned long long* seq, unsigned** ticket, int* global) {
+    DfsaContext& c = dfsaCtx();
+    if (!g_expecTicket) {
+        DFSA_CUDA(cudaMalloc((void**)&g_expecTicket, 256));
+        DFSA_CUDA(cudaMemsetAsync(g_expecTicket, 0, 256, c.compute));
+        DFSA_CUDA(cudaHostGetDevicePointer((void**)&g_expecPinnedDev, c.hostPinned, 0));
+    }
+    *ticket = g_expecTicket;
+    if (c.size > 1 && g_comm.signals && !g_expecLocalOnly) {
+        const uint64_t q = ++g_comm.expecSeq;
+        char* base = (char*)g_comm.shmDev;
+        *value = (double*)(base + offsetof(Shm, expecVal) + sizeof(double) * 2 * ((q & 1) * MAXP + c.rank));
+        *flag = (unsigned long long*)(base + offsetof(Shm, expecFlag) + sizeof(uint64_t) * ((q & 1) * MAXP + c.rank));
+        *seq = q;
+        *global = 1;
+        g_expecLastGlobal = true;
+        return DFSA_OK;
+    }
+    const uint64_t q = ++g_expecLocalSeq;
+    *value = g_expecPinnedDev + 8;                              // doubles 8, 9 of the pinned page; flag in slot 10
+    *flag = (unsigned long long*)(g_expecPinnedDev + 10);
+    *seq = q;
+    *global = 0;
+    g_expecLastGlobal = false;
+    return DFSA_OK;
+}
+
+static int spinForFlag(volatile uint64_t* flag, uint64_t seq, const char* what) {
+    DfsaContext& c = dfsaCtx();
+    const double t0 = nowSeconds();
+    for (uint64_t spins = 0; *flag < seq; spins++) {
+        if ((spins & 0xFFF) == 0xFFF) {
+            cudaError_t e = cudaStreamQuery(c.compute);
+            if (e != cudaSuccess && e != cudaErrorNotReady) { dfsaSetError("expecPauliString kernel failed: %s", cudaGetErrorString(e)); return DFSA_ERR_CUDA; }
+            if (nowSeconds() - t0 > commTimeoutSeconds()) { dfsaSetError("timed out waiting for %s", what); return DFSA_ERR_COMM; }
+        }
+    }
+    __sync_synchronize();
+    return DFSA_OK;
+}
+
+int dfsaExpecCollect(unsigned long long seq, double out[2]) {
+    DfsaContext& c = dfsaCtx();
+    if (!g_expecLastGlobal) {
+        volatile uint64_t* flag = (volatile uint64_t*)(c.hostPinned + 10);
+        DFSA_TRY(spinForFlag(flag, seq, "the reduction kernel"));
+        out[0] = ((volatile double*)c.hostPinned)[8];
+        out[1] = ((volatile double*)c.hostPinned)[9];
+        return DFSA_OK;
+    }
+    // every rank reads every rank's slot and sums in rank order: deterministic and identical everywhere, no barrier. A slot is
+    // rewritten two calls later, which needs every rank to have posted the call in between, i.e. to have finished reading this one.
+    Shm* m = g_comm.shm;
+    double re = 0.0, im = 0.0;
+    for (int r = 0; r < c.size; r++) {
+        DFSA_TRY(spinForFlag(&m->expecFlag[seq & 1][r], seq, "a rank's expectation value"));
+        re += m->expecVal[seq & 1][r][0];
+        im += m->expecVal[seq & 1][r][1];
+    }
+    out[0] = re; out[1] = im;
+    return DFSA_OK;
+}
+
 // getAllVecAmps (tests/test_utilities.hpp:419-435): every rank ends up with the whole state in host memory
 extern "C" int dfsa_state_download_all(dfsa_state* s, double* hostAll) {
     DFSA_TRY(dfsaEnsureDevice());

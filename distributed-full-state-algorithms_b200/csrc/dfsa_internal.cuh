@@ -94,6 +94,10 @@ int dfsaPublishArrays(dfsa_state* s);            // tell the peers which registr
 int dfsaRegisterAllocation(void* ptr, size_t bytes, int* idOut);   // collective when transport == Ipc
 int dfsaUnregisterAllocation(int id);
 int dfsaHostBarrier();                                             // inter-rank barrier without touching streams
+// expecPauliString plumbing (dfsa_comm.cu): host-visible slot the reduction kernel publishes to, and the host-side collection
+int dfsaExpecLocalOnly(bool on);
+int dfsaExpecTarget(double** value, unsigned long long** flag, unsigned long long* seq, unsigned** ticket, int* global);
+int dfsaExpecCollect(unsigned long long seq, double out[2]);
 int dfsaAllreduceDoubles(double* v, int n, bool isMax);            // n <= 4 host values: rank-ordered sum, or max (NaN propagates)
 
 // ------------------------------------------------------------------------------------------------ device helpers

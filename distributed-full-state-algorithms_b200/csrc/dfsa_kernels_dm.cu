@@ -437,18 +437,22 @@ extern "C" int dfsa_k_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, do
 // ---------------------------------------------------------------------------------------------------------
 // K17: local_densitymatrix.hpp:134-164. out[l] = sum_{k ascending} in[base(l) | spread(k)]; pure additions in the
 // reference's order, so the result is bit-exact. Reads 16*A/2^t, writes 16*A/4^t bytes.
+// One thread per output amplitude; neighbouring threads own neighbouring outputs, so for every k a warp reads runs of
+// 2^(lowest traced bit) contiguous amplitudes. The 2^t terms of an output are LOADED eight at a time before they are added
+// (round 1 issued one dependent load per iteration: 0.30-0.35 of the roofline, latency-bound), and ADDED one by one in
+// ascending k, which keeps the sum bit-identical to the reference's loop (:152-158). spreadTab[k] = the k-th term's offset.
+template <int BATCH>
 __global__ void __launch_bounds__(256) partialTraceKernel(const double2* __restrict__ in, double2* __restrict__ out, uint64_t numOut,
-                                                         BitSpec allSorted, BitSpec targs, BitSpec pairs, unsigned t) {
+                                                         BitSpec allSorted, const uint64_t* __restrict__ spreadTab, unsigned numTerms) {
     for (uint64_t l = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; l < numOut; l += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t base = insertZeroBits(l, allSorted);
+        const double2* base = in + insertZeroBits(l, allSorted);
         double2 acc = make_double2(0.0, 0.0);
-        for (uint64_t k = 0; k < (1ULL << t); k++) {
-            uint64_t idx = base;
-            for (unsigned b = 0; b < t; b++) {
-                uint64_t bit = (k >> b) & 1ULL;
-                idx |= (bit << targs.pos[b]) | (bit << pairs.pos[b]);
-            }
-            acc = cadd(acc, in[idx]);
+        for (unsigned k0 = 0; k0 < numTerms; k0 += BATCH) {
+            double2 v[BATCH];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) v[u] = base[__ldg(&spreadTab[k0 + u])];
+#pragma unroll
+            for (int u = 0; u < BATCH; u++) acc = cadd(acc, v[u]);
         }
         out[l] = acc;
     }
@@ -469,8 +473,29 @@ extern "C" int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32
         all.pos[q] = (uint8_t)both[q];
     }
     for (unsigned q = 0; q < numTargets; q++) { tg.pos[q] = (uint8_t)targets[q]; pr.pos[q] = (uint8_t)pairTargets[q]; }
+    // offsets of the 2^t terms of one output: bit b of k goes to the ket bit and to the bra bit of target b (:155-156)
+    const unsigned numTerms = 1u << numTargets;
+    DFSA_REQUIRE(numTargets <= 13, "partialTrace of more than 13 qubits at once");
+    std::vector<uint64_t> spread(numTerms);
+    for (unsigned k = 0; k < numTerms; k++) {
+        uint64_t off = 0;
+        for (unsigned b = 0; b < numTargets; b++) if ((k >> b) & 1u) off |= (1ULL << tg.pos[b]) | (1ULL << pr.pos[b]);
+        spread[k] = off;
+    }
+    DfsaContext& c = dfsaCtx();
+    void* stage; int slot;
+    DFSA_TRY(dfsaStagingAcquire(numTerms * sizeof(uint64_t), &stage, &slot));
+    memcpy(stage, spread.data(), numTerms * sizeof(uint64_t));
+    double2* scratch;
+    DFSA_TRY(dfsaScratch(numTerms * sizeof(uint64_t), &scratch));
+    DFSA_CUDA(cudaMemcpyAsync(scratch, stage, numTerms * sizeof(uint64_t), cudaMemcpyHostToDevice, c.compute));
+    DFSA_TRY(dfsaStagingCommit(slot));
+    const uint64_t* tab = (const uint64_t*)scratch;
+    // enough threads to keep ~8 x 16-byte loads per thread x 2048 loads per SM in flight; outputs are few when t is large
     unsigned grid = dfsaGrid(out->numAmps, 256, 1, 8);
-    partialTraceKernel<<<grid, 256, 0, dfsaCtx().compute>>>(in->arr[DFSA_AMPS], out->arr[DFSA_AMPS], out->numAmps, all, tg, pr, numTargets);
+    if (numTerms >= 8) partialTraceKernel<8><<<grid, 256, 0, c.compute>>>(in->arr[DFSA_AMPS], out->arr[DFSA_AMPS], out->numAmps, all, tab, numTerms);
+    else if (numTerms == 4) partialTraceKernel<4><<<grid, 256, 0, c.compute>>>(in->arr[DFSA_AMPS], out->arr[DFSA_AMPS], out->numAmps, all, tab, numTerms);
+    else partialTraceKernel<2><<<grid, 256, 0, c.compute>>>(in->arr[DFSA_AMPS], out->arr[DFSA_AMPS], out->numAmps, all, tab, numTerms);
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
 }
@@ -483,39 +508,78 @@ extern "C" int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32
 // (32-byte sectors) instead of a 16*A-byte scan; used when that is the smaller traffic. SCAN form otherwise.
 struct PauliTerm { uint64_t xy, y, z; double2 coeff; /* coeff * i^{#Y} */ };
 
-__device__ __forceinline__ void blockReduceToPartials(double re, double im, double2* partials) {
+// Block partial -> partials[blockIdx.x]; the LAST block to finish (device-wide ticket) sums the partials in a fixed order
+// (deterministic for a given grid) and publishes this rank's value straight into host-visible memory -- the pinned page of
+// this process, or its slot of the job's shared page -- followed by a sequence flag. No second kernel, no device-to-host copy,
+// no stream synchronisation: the host just watches the flag (three launches + blocking sync + two host barriers).
+struct ExpecOut { double* value; unsigned long long* flag; unsigned long long seq; unsigned* ticket; };
+
+__device__ __forceinline__ void blockSum(double& re, double& im) {
     __shared__ double sre[8], sim[8];
     for (int off = 16; off > 0; off >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, off); im += __shfl_xor_sync(0xffffffffu, im, off); }
+    __syncthreads();                                     // the scratch may still be read from a previous call in this kernel
     if ((threadIdx.x & 31) == 0) { sre[threadIdx.x >> 5] = re; sim[threadIdx.x >> 5] = im; }
     __syncthreads();
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; w++) { a += sre[w]; b += sim[w]; }
+    re = a; im = b;
+}
+
+__device__ __forceinline__ void finishExpec(double re, double im, double2* partials, ExpecOut out) {
+    blockSum(re, im);
+    __shared__ bool last;
     if (threadIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int w = 0; w < 8; w++) { a += sre[w]; b += sim[w]; }
-        partials[blockIdx.x] = make_double2(a, b);
+        partials[blockIdx.x] = make_double2(re, im);
+        __threadfence();
+        last = (atomicAdd(out.ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double tr = 0.0, ti = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { const double2 p = __ldcg(&partials[i]); tr += p.x; ti += p.y; }
+    blockSum(tr, ti);
+    if (threadIdx.x == 0) {
+        *out.ticket = 0;                                 // ready for the next call
+        volatile double* v = out.value;
+        v[0] = tr; v[1] = ti;
+        __threadfence_system();
+        *(volatile unsigned long long*)out.flag = out.seq;
     }
 }
 
-__global__ void __launch_bounds__(256) expecGatherKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numTerms,
-                                                        unsigned N, unsigned logCols, uint64_t firstCol, double2* partials) {
+// Item = (column c, a batch of EXPEC_BATCH terms): the batch's amplitudes are LOADED before any of them is used (eight
+// independent scattered 16-byte reads in flight per thread), and neighbouring threads take neighbouring batches of the SAME
+// column, so a warp's reads stay inside one 16 * 2^N-byte column (same DRAM pages / TLB entries) instead of striding whole
+// columns apart. The term table is padded with zero-coefficient terms to a multiple of the batch.
+constexpr unsigned EXPEC_BATCH = 8;
+
+__global__ void __launch_bounds__(256) expecGatherKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numBatches,
+                                                        unsigned N, unsigned logCols, uint64_t firstCol, double2* partials, ExpecOut out) {
     double re = 0.0, im = 0.0;
-    const uint64_t items = (uint64_t)numTerms << logCols;
-    // term-major inside a column: the reads of neighbouring threads stay inside one 16 * 2^N-byte column (same DRAM
-    // pages / TLB entry) instead of striding a whole column apart
+    const uint64_t items = (uint64_t)numBatches << logCols;
     for (uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t c = w / numTerms;
-        const PauliTerm tm = terms[w - c * numTerms];
-        const uint64_t hi = firstCol + c, lo = hi ^ tm.xy;
-        const double2 a = amps[(c << N) | lo];
-        const unsigned neg = (unsigned)(__popcll(~hi & tm.y) + __popcll(hi & tm.z)) & 1u;
-        double2 v = cmul(tm.coeff, a);
-        re += neg ? -v.x : v.x;
-        im += neg ? -v.y : v.y;
+        const uint64_t c = w / numBatches;
+        const PauliTerm* tb = terms + (w - c * numBatches) * EXPEC_BATCH;
+        const uint64_t hi = firstCol + c;
+        const double2* col = amps + (c << N);
+        double2 a[EXPEC_BATCH];
+#pragma unroll
+        for (unsigned u = 0; u < EXPEC_BATCH; u++) a[u] = col[hi ^ __ldg(&tb[u].xy)];
+#pragma unroll
+        for (unsigned u = 0; u < EXPEC_BATCH; u++) {
+            const PauliTerm tm = tb[u];
+            const unsigned neg = (unsigned)(__popcll(~hi & tm.y) + __popcll(hi & tm.z)) & 1u;
+            const double2 v = cmul(tm.coeff, a[u]);
+            re += neg ? -v.x : v.x;
+            im += neg ? -v.y : v.y;
+        }
     }
-    blockReduceToPartials(re, im, partials);
+    finishExpec(re, im, partials, out);
 }
 
 __global__ void __launch_bounds__(256) expecScanKernel(const double2* __restrict__ amps, const PauliTerm* __restrict__ terms, unsigned numTerms,
-                                                      unsigned N, uint64_t numAmps, uint64_t rankShift, double2* partials) {
+                                                      unsigned N, uint64_t numAmps, uint64_t rankShift, double2* partials, ExpecOut out) {
     double re = 0.0, im = 0.0;
     const uint64_t loMask = (1ULL << N) - 1ULL;
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < numAmps; j += (uint64_t)gridDim.x * blockDim.x) {
@@ -534,20 +598,18 @@ __global__ void __launch_bounds__(256) expecScanKernel(const double2* __restrict
             re += v.x; im += v.y;
         }
     }
-    blockReduceToPartials(re, im, partials);
+    finishExpec(re, im, partials, out);
 }
 
-__global__ void __launch_bounds__(256) sumPartialsKernel(const double2* __restrict__ partials, unsigned n, double2* out) {
-    double re = 0.0, im = 0.0;
-    for (unsigned i = threadIdx.x; i < n; i += 256) { re += partials[i].x; im += partials[i].y; }
-    blockReduceToPartials(re, im, out);
-}
-
-extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]) {
+// K23 + X11: the expectation value summed over all ranks (distributed_densitymatrix.hpp:322-344 incl. comm_reduceAmp).
+// *outIsGlobal = 1: out[] is the global sum already (every rank read every rank's slot of the shared page, rank order);
+// 0: out[] is this rank's part, combine with dfsa_x_allreduce_amp.
+extern "C" int dfsa_kx_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2], int* outIsGlobal) {
     DFSA_DM_ENTRY(s);
     DFSA_REQUIRE(coeffs && paulis && out && numTerms >= 1, "bad argument");
     const unsigned N = s->numQubits;
-    std::vector<PauliTerm> terms(numTerms);
+    const unsigned numBatches = (numTerms + EXPEC_BATCH - 1) / EXPEC_BATCH, numPadded = numBatches * EXPEC_BATCH;
+    std::vector<PauliTerm> terms(numPadded, PauliTerm{0, 0, 0, make_double2(0.0, 0.0)});     // padding: coefficient 0
     for (unsigned t = 0; t < numTerms; t++) {
         PauliTerm tm{0, 0, 0, make_double2(coeffs[t], 0.0)};
         unsigned numY = 0;
@@ -568,32 +630,43 @@ extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsi
     if (getenv("DFSA_EXPEC_FORCE_GATHER")) gather = true;
     if (getenv("DFSA_EXPEC_FORCE_SCAN")) gather = false;
     const bool scan = !gather;
-    uint64_t items = scan ? s->numAmps : ((uint64_t)numTerms << logCols);
+    uint64_t items = scan ? s->numAmps : ((uint64_t)numBatches << logCols);
     unsigned grid = dfsaGrid(items, 256, 1, 8);
-    size_t termBytes = (sizeof(PauliTerm) * numTerms + 255) / 256 * 256;
+    size_t termBytes = (sizeof(PauliTerm) * numPadded + 255) / 256 * 256;
     double2* scratch;
     DFSA_TRY(dfsaScratch(termBytes + (grid + 1) * sizeof(double2), &scratch));
     PauliTerm* dTerms = (PauliTerm*)scratch;
     double2* partials = (double2*)((char*)scratch + termBytes);
     // term table: through the pinned staging ring when it fits (asynchronous), else a blocking pageable copy
     void* stage = nullptr; int slot = -1;
-    if (dfsaStagingAcquire(sizeof(PauliTerm) * numTerms, &stage, &slot) == DFSA_OK) {
-        memcpy(stage, terms.data(), sizeof(PauliTerm) * numTerms);
-        DFSA_CUDA(cudaMemcpyAsync(dTerms, stage, sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+    if (dfsaStagingAcquire(sizeof(PauliTerm) * numPadded, &stage, &slot) == DFSA_OK) {
+        memcpy(stage, terms.data(), sizeof(PauliTerm) * numPadded);
+        DFSA_CUDA(cudaMemcpyAsync(dTerms, stage, sizeof(PauliTerm) * numPadded, cudaMemcpyHostToDevice, c.compute));
         DFSA_TRY(dfsaStagingCommit(slot));
     } else {
-        DFSA_CUDA(cudaMemcpyAsync(dTerms, terms.data(), sizeof(PauliTerm) * numTerms, cudaMemcpyHostToDevice, c.compute));
+        DFSA_CUDA(cudaMemcpyAsync(dTerms, terms.data(), sizeof(PauliTerm) * numPadded, cudaMemcpyHostToDevice, c.compute));
         DFSA_CUDA(cudaStreamSynchronize(c.compute));
     }
-    if (scan) expecScanKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, s->numAmps, (uint64_t)s->rank << s->logNumAmps, partials);
-    else expecGatherKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, logCols, (uint64_t)s->rank << logCols, partials);
+    // where the last block publishes: this rank's slot of the job's shared page when the device can write there (the sum over
+    // ranks is then formed by every host reading all slots -- out[] is already the GLOBAL value and dfsa_x_allreduce_amp must
+    // not be applied again: *outIsGlobal), else this process's pinned page
+    ExpecOut eo;
+    int global = 0;
+    DFSA_TRY(dfsaExpecTarget(&eo.value, &eo.flag, &eo.seq, &eo.ticket, &global));
+    if (scan) expecScanKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numTerms, N, s->numAmps, (uint64_t)s->rank << s->logNumAmps, partials, eo);
+    else expecGatherKernel<<<grid, 256, 0, c.compute>>>(s->arr[DFSA_AMPS], dTerms, numBatches, N, logCols, (uint64_t)s->rank << logCols, partials, eo);
     DFSA_LAUNCH_CHECK();
-    // block partials -> one value on the device (fixed order: deterministic), 16 bytes back through pinned memory
-    sumPartialsKernel<<<1, 256, 0, c.compute>>>(partials, grid, partials + grid);
-    DFSA_LAUNCH_CHECK();
-    DFSA_CUDA(cudaMemcpyAsync(c.hostPinned, partials + grid, sizeof(double2), cudaMemcpyDeviceToHost, c.compute));
-    DFSA_CUDA(cudaStreamSynchronize(c.compute));
-    const double re = c.hostPinned[0], im = c.hostPinned[1];
-    out[0] = re; out[1] = im;
+    DFSA_TRY(dfsaExpecCollect(eo.seq, out));
+    if (outIsGlobal) *outIsGlobal = global;
+    else if (global) { dfsaSetError("internal: global expectation value needs the outIsGlobal form"); return DFSA_ERR_ARG; }
     return DFSA_OK;
+}
+
+extern "C" int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]) {
+    // local part only (the documented contract of this entry): keep the cross-rank sum out of it
+    int global = 0;
+    DFSA_TRY(dfsaExpecLocalOnly(true));
+    int rc = dfsa_kx_expecPauliString(s, coeffs, numTerms, paulis, out, &global);
+    dfsaExpecLocalOnly(false);
+    return rc;
 }

@@ -48,6 +48,11 @@ void dfsa_host_state_setAllVecAmps(void* h, const double* in) {
     s.setAllVecAmps(AmpArray(p, p + Index(s.numNodes) * s.numAmpsPerNode));
 }
 void dfsa_host_state_setHashAmps(void* h, unsigned long long seed) { sv(h).setHashAmps(seed); }
+// lazy layout (layout.hpp): out[q] = index bit holding logical qubit q; restore = put every qubit back on its own bit
+void dfsa_host_state_layout(void* h, unsigned* out) { for (std::size_t q = 0; q < sv(h).where.size(); q++) out[q] = sv(h).where[q]; }
+void dfsa_host_state_restoreLayout(void* h) { sv(h).restoreLayout(); }
+void dfsa_host_state_resetLayout(void* h) { sv(h).resetLayout(); }
+int dfsa_host_lazyLayoutEnabled() { return dfsa_detail::lazyLayoutEnabled() ? 1 : 0; }
 double dfsa_host_state_getNorm2(void* h) { return sv(h).getNorm2(); }
 
 // ---- state-vector API (distributed_statevector.hpp)

@@ -70,14 +70,17 @@ static inline void distributed_densitymatrix_krausMap(DensityMatrix& rho, Matrix
 }
 
 static inline void distributed_densitymatrix_oneQubitDephasing(DensityMatrix& rho, Nat qb, Real prob) {
+    rho.restoreLayout();             // the channel kernels pair ket bit q with bra bit q + N by position
     local_densitymatrix_oneQubitDephasing(rho, qb, prob);      // the kernel handles the prefix case via the rank bit
 }
 
 static inline void distributed_densitymatrix_twoQubitDephasing(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob) {
+    rho.restoreLayout();             // the channel kernels pair ket bit q with bra bit q + N by position
     local_densitymatrix_twoQubitDephasing(rho, qb1, qb2, prob);
 }
 
 static inline void distributed_densitymatrix_oneQubitDepolarising(DensityMatrix& rho, Nat qb, Real prob) {
+    rho.restoreLayout();             // the channel kernels pair ket bit q with bra bit q + N by position
     const Nat threshold = rho.numQubits - rho.logNumNodes;
     if (qb < threshold) { local_densitymatrix_oneQubitDepolarising(rho, qb, prob); return; }
     // the bra bit is a rank bit: the ket-bit == rank-bit halves are traded with the partner and mixed (reference :110-141);
@@ -95,6 +98,7 @@ static inline void distributed_densitymatrix_oneQubitDepolarising(DensityMatrix&
 #define DFSA_DEPOL2_DEFAULT false
 #endif
 static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix& rho, Nat qb1, Nat qb2, Real prob, bool corrected = DFSA_DEPOL2_DEFAULT) {
+    rho.restoreLayout();
     if (qb1 > qb2) std::swap(qb1, qb2);
     const Nat N = rho.numQubits, threshold = N - rho.logNumNodes;
     if (qb2 < threshold) { local_densitymatrix_twoQubitDepolarising(rho, qb1, qb2, prob, corrected); return; }
@@ -114,6 +118,7 @@ static inline void distributed_densitymatrix_twoQubitDepolarising(DensityMatrix&
 }
 
 static inline void distributed_densitymatrix_damping(DensityMatrix& rho, Nat qb, Real prob) {
+    rho.restoreLayout();             // the channel kernels pair ket bit q with bra bit q + N by position
     const Nat threshold = rho.numQubits - rho.logNumNodes;
     if (qb < threshold) { local_densitymatrix_damping(rho, qb, prob); return; }
     // population flows one way, from the rank holding bra bit 1 to the rank holding bra bit 0 (reference :284-317)
@@ -123,16 +128,21 @@ static inline void distributed_densitymatrix_damping(DensityMatrix& rho, Nat qb,
 
 static inline Amp distributed_densitymatrix_expecPauliString(DensityMatrix& rho, RealArray coeffs, NatArray allPaulis) {
     assert(allPaulis.size() == coeffs.size() * rho.numQubits);
-    double local[2] = {0.0, 0.0};
-    DFSA_CHECK(dfsa_k_expecPauliString(rho.handle, coeffs.data(), Nat(coeffs.size()), allPaulis.data(), local));
-    Amp value(local[0], local[1]);
-    comm_reduceAmp(value);
+    rho.restoreLayout();
+    // local sum (reference :327-340) and the all-reduce (:342): one kernel per rank publishing into the shared page, every
+    // host summing the slots in rank order; comm_reduceAmp only where the ranks have no shared page
+    double sum[2] = {0.0, 0.0};
+    int isGlobal = 0;
+    DFSA_CHECK(dfsa_kx_expecPauliString(rho.handle, coeffs.data(), Nat(coeffs.size()), allPaulis.data(), sum, &isGlobal));
+    Amp value(sum[0], sum[1]);
+    if (!isGlobal) comm_reduceAmp(value);
     return value;
 }
 
 static inline DensityMatrix distributed_densitymatrix_partialTrace(DensityMatrix& inRho, NatArray targets) {
     const Nat N = inRho.numQubits, L = Nat(inRho.logNumAmpsPerNode);
     assert(N - targets.size() >= inRho.logNumNodes);
+    inRho.restoreLayout();           // the reference's relocation plan (and the mutated input it leaves) start from index order
     std::sort(targets.begin(), targets.end());
     const NatArray braTargets = dfsa_detail::shifted(targets, N);
 
@@ -143,8 +153,14 @@ static inline DensityMatrix distributed_densitymatrix_partialTrace(DensityMatrix
     NatArray extended = targets;
     extended.insert(extended.end(), braTargets.begin(), braTargets.end());
     const NatArray reordered = getReorderedAllSuffixTargets(extended, L);
+    // The reference swaps the moved targets one after the other, last to first (:382-384). Each pair is (free suffix qubit,
+    // prefix qubit) and no qubit occurs twice, so the swaps commute: they go as ONE relocation step (a single gather pass over
+    // the 2^k shards of the rank's group) and leave inRho exactly as the reference's sequence does.
+    NatArray landing, prefix;
     for (std::size_t q = reordered.size(); q-- != 0;)
-        if (reordered[q] != extended[q]) distributed_statevector_swapGate(inRho, reordered[q], extended[q]);
+        if (reordered[q] != extended[q]) { landing.push_back(reordered[q]); prefix.push_back(extended[q]); }
+    assert(landing.size() <= 4 && "at most 16 ranks");
+    if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(inRho.handle, landing.data(), prefix.data(), Nat(landing.size())));
 
     const NatArray pairTargets(reordered.begin() + targets.size(), reordered.end());
     DensityMatrix outRho = local_densitymatrix_partialTrace(inRho, targets, pairTargets);
@@ -153,7 +169,7 @@ static inline DensityMatrix distributed_densitymatrix_partialTrace(DensityMatrix
     for (Nat q = Nat(remaining.size()); q-- != 0;) {
         if (remaining[q] == q) continue;
         const Nat p = Nat(std::find(remaining.begin(), remaining.end(), q) - remaining.begin());
-        distributed_statevector_swapGate(outRho, q, p);
+        dfsa_detail::swapIndexBits(outRho, q, p);               // data movement: outRho must END in index order
         std::swap(remaining[q], remaining[p]);
     }
     return outRho;

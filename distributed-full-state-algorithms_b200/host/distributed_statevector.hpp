@@ -22,13 +22,7 @@ inline void ampToArray(const Amp& a, double out[2]) { out[0] = a.real(); out[1] 
 // The entry points below act on exactly these plans; tests/test_gloo_host_plans.py checks on CPU, across ranks, that
 // every planned exchange is symmetric (my partner plans the same exchange with me, same size).
 
-struct ExchangePlan {
-    enum Kind { Local = 0, Skip = 1, FullShard = 2, SubCube = 3, HalfContiguous = 4, HalfPacked = 5 };
-    int kind = Local;
-    Nat pairRank = 0;
-    Index numAmps = 0;       // amplitudes that travel per direction
-    Nat bit = 0;             // this rank's bit of the prefix qubit involved (FullShard / SubCube), or the moving bit (Half*)
-};
+// (ExchangePlan and planSwap live in layout.hpp: restoring a lazy layout needs the same four swap cases)
 
 // oneTargGate / manyCtrlOneTargGate (reference :18-39, :81-106)
 inline ExchangePlan planCtrlOneTarg(Nat rank, Nat L, const NatArray& controls, Nat target, NatArray* suffixCtrlsOut = nullptr) {
@@ -49,28 +43,6 @@ inline ExchangePlan planCtrlOneTarg(Nat rank, Nat L, const NatArray& controls, N
     plan.bit = getBit(rank, target - L);
     plan.kind = suffixCtrls.empty() ? ExchangePlan::FullShard : ExchangePlan::SubCube;
     plan.numAmps = (Index(1) << L) >> suffixCtrls.size();
-    return plan;
-}
-
-// swapGate (reference :109-187)
-inline ExchangePlan planSwap(Nat rank, Nat L, Nat qb1, Nat qb2) {
-    ExchangePlan plan;
-    if (qb1 > qb2) std::swap(qb1, qb2);
-    const Index A = Index(1) << L;
-    if (qb2 < L) { plan.kind = ExchangePlan::Local; return plan; }
-    if (qb1 >= L) {
-        // both prefix: ranks whose two bits differ trade whole shards with the rank that has them exchanged
-        if (getBit(rank, qb1 - L) == getBit(rank, qb2 - L)) { plan.kind = ExchangePlan::Skip; return plan; }
-        plan.kind = ExchangePlan::FullShard;
-        plan.pairRank = Nat(flipBit(flipBit(rank, qb1 - L), qb2 - L));
-        plan.numAmps = A;
-        return plan;
-    }
-    // one suffix, one prefix qubit: the half of the shard whose qb1 bit differs from this rank's qb2 bit moves
-    plan.pairRank = Nat(flipBit(rank, qb2 - L));
-    plan.numAmps = A / 2;
-    plan.bit = !getBit(rank, qb2 - L);
-    plan.kind = (qb1 == L - 1) ? ExchangePlan::HalfContiguous : ExchangePlan::HalfPacked;
     return plan;
 }
 
@@ -110,12 +82,15 @@ static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMat
 }
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
+    target = psi.where[target];                               // the index bit that holds the qubit (layout.hpp)
     if (target < psi.logNumAmpsPerNode) local_statevector_oneTargGate(psi, target, gate);
     else dfsa_prefixOneTarg(psi, target, gate);
 }
 
 static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi, NatArray controls, Nat target, AmpMatrix gate) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
+    controls = psi.physical(controls);
+    target = psi.where[target];
     NatArray suffixCtrls;
     const dfsa_detail::ExchangePlan plan = dfsa_detail::planCtrlOneTarg(psi.rank, L, controls, target, &suffixCtrls);
     switch (plan.kind) {
@@ -133,22 +108,15 @@ static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi,
 }
 
 static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, Nat qb2) {
-    if (qb1 > qb2) std::swap(qb1, qb2);
-    const dfsa_detail::ExchangePlan plan = dfsa_detail::planSwap(psi.rank, Nat(psi.logNumAmpsPerNode), qb1, qb2);
-    switch (plan.kind) {
-        case dfsa_detail::ExchangePlan::Local: local_statevector_swapGate(psi, qb1, qb2); return;
-        case dfsa_detail::ExchangePlan::Skip: return;
-        case dfsa_detail::ExchangePlan::FullShard:
-            comm_exchangeArrays(psi.amps, psi.buffer, plan.pairRank);
-            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, 0, 0, psi.numAmpsPerNode));      // whole shard: becomes a pointer swap
-            return;
-        default:
-            // one suffix, one prefix qubit (reference :140-186): the half whose qb1 bit differs from this rank's qb2 bit
-            // trades places with the partner's. Fused over peer memory into a single pass where the ranks share a node;
-            // otherwise contiguous exchange (qb1 top suffix qubit) or pack / exchange / unpack, as the reference does.
-            DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, qb1, plan.bit, int(plan.pairRank)));
-            return;
+    const Nat L = Nat(psi.logNumAmpsPerNode);
+    const Nat p1 = psi.where[qb1], p2 = psi.where[qb2];
+    if (p1 >= L && p2 >= L && dfsa_detail::lazyLayoutEnabled()) {
+        // both qubits sit on rank bits (reference :120-137 ships whole shards between the ranks whose two bits differ): the
+        // swap only renames which rank holds which block, so it is recorded in the layout and no amplitude moves
+        std::swap(psi.where[qb1], psi.where[qb2]);
+        return;
     }
+    dfsa_detail::swapIndexBits(psi, p1, p2);                  // the reference's four cases, on index bits
 }
 
 // Relocation plan of manyTargGate: every prefix target (caller order) is swapped onto a free suffix qubit for the
@@ -173,8 +141,9 @@ static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const 
 
 static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArray targets, AmpMatrix gate) {
     assert(targets.size() <= psi.logNumAmpsPerNode);
+    targets = psi.physical(targets);
     const NatArray placed = dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets);
-    // the (suffix, prefix) qubit pairs the reference swaps one after the other before and after the local gate (:213-223);
+    // the (suffix, prefix) index-bit pairs the reference swaps one after the other before and after the local gate (:213-223);
     // the pairs are disjoint, so they commute and go in one relocation step, which is its own inverse
     NatArray landing, prefix;
     for (std::size_t i = 0; i < targets.size(); i++)
@@ -182,12 +151,19 @@ static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArr
     assert(landing.size() <= 4 && "at most 16 ranks");
     if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
     local_statevector_manyTargGate(psi, placed, gate);
-    if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
+    if (landing.empty()) return;
+    if (dfsa_detail::lazyLayoutEnabled()) {
+        // leave the targets where they are and remember it: the next gate on them is local, and the undo happens once,
+        // when somebody needs the amplitudes in index order (StateVector::restoreLayout)
+        for (std::size_t i = 0; i < landing.size(); i++) psi.noteSwapped(landing[i], prefix[i]);
+        return;
+    }
+    DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
 }
 
 static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi, const NatArray& targets, const NatArray& paulis, Amp thisAmpFac, Amp otherAmpFac) {
     assert(targets.size() == paulis.size());
-    const dfsa_detail::PauliPlan plan = dfsa_detail::planPauli(psi.rank, Nat(psi.logNumAmpsPerNode), targets, paulis);
+    const dfsa_detail::PauliPlan plan = dfsa_detail::planPauli(psi.rank, Nat(psi.logNumAmpsPerNode), psi.physical(targets), paulis);
     if (plan.pairRank == psi.rank) {
         local_statevector_pauliTensorOrGadget_subroutine(psi, plan.numY, plan.maskXY, plan.maskYZ, thisAmpFac, otherAmpFac);
         return;
@@ -209,5 +185,5 @@ static inline void distributed_statevector_pauliGadget(StateVector& psi, NatArra
 }
 
 static inline void distributed_statevector_phaseGadget(StateVector& psi, NatArray targets, Real theta) {
-    local_statevector_phaseGadget(psi, targets, theta);
+    local_statevector_phaseGadget(psi, psi.physical(targets), theta);
 }

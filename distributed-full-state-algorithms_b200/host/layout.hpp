@@ -1,0 +1,126 @@
+// layout.hpp -- lazy logical -> physical qubit layout of a device-resident state.
+//
+// The reference moves a gate's prefix targets into the shard with swaps, applies the gate, and swaps them straight back
+// (src/distributed_statevector.hpp:213-223); a prefix<->prefix swapGate ships whole shards between ranks (:120-137). Both
+// are only RELABELLINGS of which index bit holds which qubit. Here a state remembers that relabelling instead of undoing it:
+//     where[q] = the index bit ("physical" position) that currently holds logical qubit q      (identity after construction)
+// Every state-vector entry point translates its qubits through `where` and then runs the reference's decision logic
+// (local vs. exchange) on physical positions. manyTargGate relocates what it must and leaves it there; a swapGate of two
+// qubits that both sit on rank bits just exchanges their entries -- no data moves. The layout is put back (restoreLayout)
+// before anything that looks at amplitudes by index: downloads, comparisons, the density-matrix channels, expecPauliString,
+// partialTrace -- so results, including the mutated input of partialTrace, are what the reference produces.
+// DFSA_LAZY_LAYOUT=0 turns the laziness off (relocations are undone at once, as in the reference).
+//
+// Included at the bottom of states.hpp; uses only the C-ABI.
+#pragma once
+
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+
+namespace dfsa_detail {
+
+inline bool lazyLayoutEnabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = std::getenv("DFSA_LAZY_LAYOUT"); on = (e && std::atoi(e) == 0) ? 0 : 1; }
+    return on == 1;
+}
+
+// ---- the host-side decision of swapGate as a pure function of (rank, L = logNumAmpsPerNode, qubits): reference :109-187
+struct ExchangePlan {
+    enum Kind { Local = 0, Skip = 1, FullShard = 2, SubCube = 3, HalfContiguous = 4, HalfPacked = 5 };
+    int kind = Local;
+    Nat pairRank = 0;
+    Index numAmps = 0;       // amplitudes that travel per direction
+    Nat bit = 0;             // this rank's bit of the prefix qubit involved (FullShard / SubCube), or the moving bit (Half*)
+};
+
+inline ExchangePlan planSwap(Nat rank, Nat L, Nat qb1, Nat qb2) {
+    ExchangePlan plan;
+    if (qb1 > qb2) std::swap(qb1, qb2);
+    const Index A = Index(1) << L;
+    if (qb2 < L) { plan.kind = ExchangePlan::Local; return plan; }
+    if (qb1 >= L) {
+        // both prefix: ranks whose two bits differ trade whole shards with the rank that has them exchanged
+        if (getBit(rank, qb1 - L) == getBit(rank, qb2 - L)) { plan.kind = ExchangePlan::Skip; return plan; }
+        plan.kind = ExchangePlan::FullShard;
+        plan.pairRank = Nat(flipBit(flipBit(rank, qb1 - L), qb2 - L));
+        plan.numAmps = A;
+        return plan;
+    }
+    // one suffix, one prefix qubit: the half of the shard whose qb1 bit differs from this rank's qb2 bit moves
+    plan.pairRank = Nat(flipBit(rank, qb2 - L));
+    plan.numAmps = A / 2;
+    plan.bit = !getBit(rank, qb2 - L);
+    plan.kind = (qb1 == L - 1) ? ExchangePlan::HalfContiguous : ExchangePlan::HalfPacked;
+    return plan;
+}
+
+// swap two INDEX BITS of the distributed array (the data movement of swapGate, whatever qubits they hold)
+inline void swapIndexBits(StateVector& psi, Nat p1, Nat p2) {
+    if (p1 > p2) std::swap(p1, p2);
+    const ExchangePlan plan = planSwap(psi.rank, Nat(psi.logNumAmpsPerNode), p1, p2);
+    switch (plan.kind) {
+        case ExchangePlan::Local: DFSA_CHECK(dfsa_k_swap(psi.handle, p1, p2)); return;
+        case ExchangePlan::Skip: return;
+        case ExchangePlan::FullShard:
+            DFSA_CHECK(dfsa_x_exchange(psi.handle, DFSA_AMPS, 0, DFSA_BUFFER, 0, psi.numAmpsPerNode, int(plan.pairRank)));
+            DFSA_CHECK(dfsa_k_copyFromBuffer(psi.handle, 0, 0, psi.numAmpsPerNode));      // whole shard: becomes a pointer swap
+            return;
+        default:
+            // one suffix, one prefix bit (reference :140-186): fused over peer memory into a single pass where the ranks share
+            // a node; otherwise contiguous exchange (top suffix bit) or pack / exchange / unpack, as the reference does
+            DFSA_CHECK(dfsa_xk_swapSuffixPrefix(psi.handle, p1, plan.bit, int(plan.pairRank)));
+            return;
+    }
+}
+}  // namespace dfsa_detail
+
+inline bool StateVector::layoutIsIdentity() const {
+    for (Nat q = 0; q < Nat(where.size()); q++) if (where[q] != q) return false;
+    return true;
+}
+
+inline NatArray StateVector::physical(const NatArray& logical) const {
+    NatArray out(logical.size());
+    for (std::size_t i = 0; i < logical.size(); i++) out[i] = where[logical[i]];
+    return out;
+}
+
+// index bits posA and posB have just traded contents (or are declared to have, for a pure relabelling)
+inline void StateVector::noteSwapped(Nat posA, Nat posB) {
+    for (Nat& w : where) {
+        if (w == posA) w = posB;
+        else if (w == posB) w = posA;
+    }
+}
+
+inline Nat StateVector::numDisplacedAcrossShardBoundary() const {
+    Nat n = 0;
+    for (Nat q = 0; q < Nat(where.size()); q++) n += (q >= logNumAmpsPerNode && where[q] < logNumAmpsPerNode) ? 1 : 0;
+    return n;
+}
+
+// Put every logical qubit back on its own index bit. What manyTargGate leaves behind are 2-cycles (a prefix qubit sitting on
+// a suffix bit and vice versa): all of those go in ONE relocation step; anything else (longer cycles after several gates) is
+// sorted out with plain index-bit swaps.
+inline void StateVector::restoreLayout() {
+    if (layoutIsIdentity()) return;
+    const Nat L = Nat(logNumAmpsPerNode), n = Nat(where.size());
+    NatArray holder(n);                                            // holder[p] = logical qubit on index bit p
+    for (Nat q = 0; q < n; q++) holder[where[q]] = q;
+    NatArray suffixBits, prefixBits;
+    for (Nat q = L; q < n && suffixBits.size() < 4; q++) {
+        const Nat p = where[q];                                    // logical prefix qubit q sits on bit p ...
+        if (p < L && where[p] == q) { suffixBits.push_back(p); prefixBits.push_back(q); }   // ... and bit q holds logical qubit p
+    }
+    if (!suffixBits.empty()) {
+        DFSA_CHECK(dfsa_xk_relocate(handle, suffixBits.data(), prefixBits.data(), Nat(suffixBits.size())));
+        for (std::size_t i = 0; i < suffixBits.size(); i++) noteSwapped(suffixBits[i], prefixBits[i]);
+    }
+    for (Nat q = 0; q < n; q++) {
+        if (where[q] == q) continue;
+        dfsa_detail::swapIndexBits(*this, where[q], q);
+        noteSwapped(where[q], q);
+    }
+}

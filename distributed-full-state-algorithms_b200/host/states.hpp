@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <numeric>
 #include <utility>
 
 #include "bit_maths.hpp"
@@ -34,6 +35,15 @@ public:
 
     dfsa_state* handle = nullptr;
 
+    // lazy qubit layout (layout.hpp): where[q] = index bit currently holding logical qubit q; identity unless a gate left
+    // its relocated targets in place. Anything that addresses amplitudes by index calls restoreLayout() first.
+    NatArray where;
+    bool layoutIsIdentity() const;
+    NatArray physical(const NatArray& logical) const;
+    void noteSwapped(Nat posA, Nat posB);
+    Nat numDisplacedAcrossShardBoundary() const;
+    void restoreLayout();
+
     explicit StateVector(Nat numQubits) { create(false, numQubits); }
     virtual ~StateVector() { release(); }
     StateVector(const StateVector&) = delete;
@@ -43,22 +53,26 @@ public:
 
     // ---- host <-> device (the reference's test-utility members + plain setters)
     AmpArray getAllVecAmps() {                                   // whole state on every rank
+        restoreLayout();
         AmpArray all(Index(numNodes) * numAmpsPerNode);
         DFSA_CHECK(dfsa_state_download_all(handle, reinterpret_cast<double*>(all.data())));
         return all;
     }
     void setAllVecAmps(const AmpArray& all) {                    // each rank keeps its slice of the global array
         assert(all.size() == Index(numNodes) * numAmpsPerNode);
+        resetLayout();
         comm_synch();
         DFSA_CHECK(dfsa_state_upload_all(handle, reinterpret_cast<const double*>(all.data())));
     }
     AmpArray getLocalAmps() {
+        restoreLayout();
         AmpArray local(numAmpsPerNode);
         DFSA_CHECK(dfsa_state_download(handle, DFSA_AMPS, 0, numAmpsPerNode, reinterpret_cast<double*>(local.data())));
         return local;
     }
     void setLocalAmps(const AmpArray& local) {
         assert(local.size() == numAmpsPerNode);
+        resetLayout();
         DFSA_CHECK(dfsa_state_upload(handle, DFSA_AMPS, 0, numAmpsPerNode, reinterpret_cast<const double*>(local.data())));
     }
     // Box-Muller on rand(), every rank drawing every rank's amplitudes so the streams stay in lock-step
@@ -74,7 +88,8 @@ public:
             }
         setLocalAmps(mine);
     }
-    void setHashAmps(unsigned long long seed) { DFSA_CHECK(dfsa_state_init_hash(handle, seed)); }
+    void setHashAmps(unsigned long long seed) { resetLayout(); DFSA_CHECK(dfsa_state_init_hash(handle, seed)); }
+    void resetLayout() { std::iota(where.begin(), where.end(), Nat(0)); }      // the contents are about to be overwritten
     void printAmps() {
         AmpArray all = getAllVecAmps();
         if (rank == 0)
@@ -104,11 +119,13 @@ public:
     }
     Real getNorm2() { double n = 0; DFSA_CHECK(dfsa_state_norm2(handle, &n)); return n; }
     // device-resident utilities: nothing is gathered to the host
-    void setPlusAmps() { DFSA_CHECK(dfsa_state_init_plus(handle)); }
-    void copyAmpsFrom(StateVector& other) { DFSA_CHECK(dfsa_state_copy(handle, other.handle)); }
+    void setPlusAmps() { resetLayout(); DFSA_CHECK(dfsa_state_init_plus(handle)); }
+    void copyAmpsFrom(StateVector& other) { other.restoreLayout(); resetLayout(); DFSA_CHECK(dfsa_state_copy(handle, other.handle)); }
     // max over all amplitudes and ranks of |delta re|, |delta im| (NaN if any NaN); numUnequal counts == mismatches
     Real getMaxDifference(StateVector& other, Index* numUnequal = nullptr) {
         double d = 0; uint64_t ne = 0;
+        restoreLayout();
+        other.restoreLayout();
         DFSA_CHECK(dfsa_state_compare(handle, other.handle, &d, &ne, nullptr));
         if (numUnequal) *numUnequal = ne;
         return d;
@@ -127,6 +144,8 @@ protected:
         numAmpsPerNode = dfsa_state_num_amps_per_node(handle);
         amps = DeviceAmpArray{handle, DFSA_AMPS};
         buffer = DeviceAmpArray{handle, DFSA_BUFFER};
+        where.resize(isDensity ? 2 * qubits : qubits);
+        resetLayout();
     }
     void release() {
         if (handle) DFSA_CHECK(dfsa_state_destroy(handle));
@@ -135,7 +154,7 @@ protected:
     void adopt(StateVector& o) {
         rank = o.rank; numNodes = o.numNodes; logNumNodes = o.logNumNodes; numQubits = o.numQubits;
         numAmpsPerNode = o.numAmpsPerNode; logNumAmpsPerNode = o.logNumAmpsPerNode;
-        amps = o.amps; buffer = o.buffer; handle = o.handle;
+        amps = o.amps; buffer = o.buffer; handle = o.handle; where = std::move(o.where);
         o.handle = nullptr; o.amps = DeviceAmpArray(); o.buffer = DeviceAmpArray();
     }
 };
@@ -172,3 +191,5 @@ public:
         return StateVector::agreesWith(vec, tol);
     }
 };
+
+#include "layout.hpp"

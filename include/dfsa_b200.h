@@ -219,6 +219,10 @@ int dfsa_k_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, 
 /* K23: local part of sum_t coeff_t Tr(P_t rho); paulis is numTerms x N (codes 0..3, qubit q of term t at [t*N+q]).
  * Result (this rank's partial sum) is written to out[2]; combine with dfsa_x_allreduce_amp. :322 */
 int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]);
+/* K23 + X11 (comm_reduceAmp, src/communication.hpp:172) in one call: where the ranks share a node the reduction kernel of every
+ * rank publishes into the job's shared page and each host sums all slots in rank order -- *outIsGlobal = 1, out[] is the value
+ * of distributed_densitymatrix_expecPauliString on every rank. Otherwise *outIsGlobal = 0 and out[] is the local part. */
+int dfsa_kx_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2], int* outIsGlobal);
 
 #ifdef __cplusplus
 }

@@ -10,7 +10,8 @@
 # Three one-token edits are applied to the throw-away copies, each a defect of the TEST, not of the API:
 #   * trial counts  `= 5000;`  ->  `= dfsaCatchTrials(5000);`       (DFSA_CATCH_TRIALS overrides; default unchanged)
 #   * tests_densitymatrix.hpp:191 builds sqrt(1-16/15.) = NaN as the identity Kraus operator of twoQubitDepolarising; with
-#     the reference's one-sided comparator NaN passes, so the case is vacuous. Here: sqrt(1-16*prob/15.), the channel's K0.
+#     the reference's one-sided comparator NaN passes, so the case is vacuous. Here: sqrt(1-prob), the K0 of the two-qubit
+#     depolarising channel (1-p) rho + (p/15) sum_{P != II} P rho P whose other 15 operators the case already builds.
 # Comparator: host/states.hpp agreesWith, two-sided, DFSA_AGREES_TOL=1e-12 relative to max(1, max|ref|) (north_star's bar).
 # The build also defines DFSA_CORRECTED_DEPOL2_DEFAULT: distributed_densitymatrix_twoQubitDepolarising then applies the TRUE
 # channel (1-16p/15) rho + (4p/15) I (x) Tr_2 rho, which is what that (repaired) case tests; the reference's literal formulas
@@ -37,9 +38,9 @@ trap 'rm -rf "$tmp"' EXIT
 cp "$REF_DIR/tests/tests.cpp" "$REF_DIR/tests/tests_statevector.hpp" "$REF_DIR/tests/tests_densitymatrix.hpp" "$tmp/"
 cp "$here/test_utilities.hpp" "$tmp/"
 sed -i 's/= 5000;/= dfsaCatchTrials(5000);/' "$tmp/tests_statevector.hpp" "$tmp/tests_densitymatrix.hpp"
-sed -i 's|sqrt(1-16/15\.)|sqrt(1-16*prob/15.)|' "$tmp/tests_densitymatrix.hpp"
+sed -i 's|sqrt(1-16/15\.)|sqrt(1-prob)|' "$tmp/tests_densitymatrix.hpp"
 grep -q 'dfsaCatchTrials' "$tmp/tests_statevector.hpp" && grep -q 'dfsaCatchTrials' "$tmp/tests_densitymatrix.hpp" || { echo "catch_dropin: trial-count edit did not apply"; exit 1; }
-grep -q 'sqrt(1-16\*prob/15\.)' "$tmp/tests_densitymatrix.hpp" || { echo "catch_dropin: Kraus-operator edit did not apply"; exit 1; }
+grep -q 'krausOps\[0\] = sqrt(1-prob)' "$tmp/tests_densitymatrix.hpp" || { echo "catch_dropin: Kraus-operator edit did not apply"; exit 1; }
 
 unset CC CXX
 flags="-std=c++17 -O2 -DDFSA_AGREES_TOL=1e-12 -DDFSA_AGREES_RELATIVE=1 -DDFSA_CORRECTED_DEPOL2_DEFAULT=1"

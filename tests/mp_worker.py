@@ -37,7 +37,9 @@ def main():
             elif op[0] == "dm_partialTrace":
                 res["mutated"] = cur.get_amps()
                 cur = r
+        res["layout_before_readback"] = cur.layout()
         res["amps"] = cur.get_amps()
+        res["layout_after_readback"] = cur.layout()
         res["transport"] = dfsa.device_lib().dfsa_comm_transport().decode()
         results.append(res)
         if cur is not st:

@@ -341,6 +341,58 @@ def test_relocation_of_several_prefix_targets_matches_oracle(nodes):
             compare.assert_close(r["amps"], w, what="relocation np=%d targets=%r (%s)" % (nodes, job["op"][1], r["transport"]))
 
 
+@pytest.mark.parametrize("nodes", [2, 4, 8])
+def test_lazy_layout_defers_relocation_and_matches_oracle(nodes):
+    """host/layout.hpp: manyTargGate leaves its relocated targets on the suffix bits they landed on, prefix<->prefix swaps
+    only relabel ranks, every later gate is translated through the layout, and the read-back restores index order. Same
+    results as the oracle (and as DFSA_LAZY_LAYOUT=0, where every relocation is undone at once); with laziness on, the layout
+    just before the read-back must be non-trivial and just after it the identity."""
+    rng = np.random.default_rng(1200 + nodes)
+    k = nodes.bit_length() - 1
+    nq = 12
+    L = nq - k
+    ops = []
+    for rep in range(3):
+        pre = [int(x) for x in rng.permutation(np.arange(L, nq))[: 1 + rep % k if k > 1 else 1]]
+        suf = [int(x) for x in rng.permutation(L)[:2]]
+        targets = [int(x) for x in rng.permutation(pre + suf)]
+        ops.append(("sv_manyTargGate", targets, cases.random_matrix(rng, 1 << len(targets)) / (1 << len(targets)) ** 0.5))
+        ops.append(("sv_oneTargGate", int(rng.integers(0, nq)), cases.random_matrix(rng, 2) / 1.5))
+        ops.append(("sv_manyCtrlOneTargGate", [nq - 1, 2], int(rng.integers(3, nq - 1)), cases.random_matrix(rng, 2) / 1.5))
+        ops.append(("sv_pauliGadget", [nq - 1, 0, 5], [1, 3, 2], float(rng.uniform(-3, 3))))
+        ops.append(("sv_phaseGadget", [nq - 1, 1], float(rng.uniform(-3, 3))))
+        ops.append(("sv_swapGate", nq - 1, int(rng.integers(0, L))))
+        if k >= 2:
+            ops.append(("sv_swapGate", nq - 1, nq - 2))
+        ops.append(("sv_pauliTensor", [nq - 2, 3], [2, 1]))
+    ops.append(("sv_manyTargGate", [nq - 1, 4, 0], cases.random_matrix(rng, 8) / 8 ** 0.5))      # ends with displaced qubits
+    amps = cases.random_state(rng, nq)
+    o = capi.OracleState("sv", nq, nodes)
+    o.set_amps(amps)
+    for op in ops:
+        cases.apply(o, op)
+    want = o.get_amps()
+    # a density matrix: unitaries ride the lazy layout, the channels force a restore in between
+    N = 6
+    dm_ops = [("dm_manyTargGate", [N - 1, 0, 2], cases.random_matrix(rng, 8) / 8 ** 0.5), ("dm_pauliGadget", [N - 1, 1], [2, 3], 0.3),
+              ("dm_damping", N - 1, 0.2), ("dm_manyTargGate", [N - 1, N - 2], cases.random_matrix(rng, 4) / 2), ("dm_swapGate", N - 1, N - 2),
+              ("dm_oneQubitDepolarising", 1, 0.1), ("dm_krausMap", [N - 1], [cases.random_matrix(rng, 2) / 2 for _ in range(3)]),
+              ("dm_manyTargGate", [N - 1, 3, 1], cases.random_matrix(rng, 8) / 8 ** 0.5)]
+    dm_amps = cases.random_state(rng, 2 * N)
+    od = capi.OracleState("dm", N, nodes)
+    od.set_amps(dm_amps)
+    for op in dm_ops:
+        cases.apply(od, op)
+    jobs = [dict(kind="sv", nq=nq, ops=ops, amps=amps), dict(kind="dm", nq=N, ops=dm_ops, amps=dm_amps)]
+    for lazy in ("1", "0"):
+        res = product.run_cases_multirank(jobs, nodes, extra_env={"DFSA_LAZY_LAYOUT": lazy})
+        compare.assert_close(res[0]["amps"], want, tol=1e-11, what="lazy layout=%s np=%d" % (lazy, nodes))
+        compare.assert_close(res[1]["amps"], od.get_amps(), tol=1e-11, what="lazy layout=%s np=%d (dm)" % (lazy, nodes))
+        for r, bits in ((res[0], nq), (res[1], 2 * N)):
+            assert r["layout_after_readback"] == list(range(bits))
+            assert (r["layout_before_readback"] != list(range(bits))) == (lazy == "1"), (lazy, r["layout_before_readback"])
+
+
 def test_chunk_pipelined_exchange_matches_oracle():
     """Forces the chunked exchange+combine pipeline (16 chunks even on small shards) on the NCCL transport; on a
     single-GPU box the ranks share the device, the IPC transport is used and the same results must come out."""
