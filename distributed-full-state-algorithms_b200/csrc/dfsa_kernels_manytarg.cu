@@ -14,7 +14,8 @@
 //            one warp per tile with per-element address tables reached 54 %, then 81 % of the pipe in 4M form; the
 //            3M form with the rows split over a warp pair 70 %; this kernel 81 % in 3M form (25 % fewer flops).
 //            t == 6 (krausMap / density-matrix gates on 3 qubits): same kernel, the 64x64 gate's A-fragments in shared memory.
-//   t >= 7   manyTargGenericKernel   one block per 2^t group, gate streamed from L2, warp-per-row reduction
+//   t = 7..11 manyTargGemmKernel: tiled FP64 DMMA GEMM over the groups, gate streamed from L2 as A-fragments (krausMap on 4-5 qubits)
+//   t >= 12  manyTargGenericKernel   one block per 2^t group, gate streamed from L2, warp-per-row reduction
 //            (also: t = 3..6 on shards smaller than one tile)
 #include <algorithm>
 #include <vector>
@@ -356,6 +357,124 @@ __global__ void __launch_bounds__(256) manyTargGenericKernel(double2* amps, uint
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// t = 7 .. 11 (krausMap superoperators on 4-5 qubits): the gate no longer fits on chip, so the operation is
+// run as what it is -- a GEMM  Y[D x M] = G[D x D] X[D x M]  over the M = A / D groups of amplitudes -- on the FP64 tensor cores,
+// in the 3M form of the complex product, with the gate STREAMED: a prep kernel turns it into the three real matrices as
+// mma A-fragments (fragment-major, so a warp's load of one fragment is 4 x 512 contiguous bytes), which then come from L2
+// (<= 96 MiB, resident) straight into registers. Block tile = 128 gate rows (8 warps x 16) x 64 groups; K loop over 16-row
+// slices of X, double-buffered in shared memory with cp.async (XOR-swizzled so the B-fragment reads are conflict free);
+// accumulators (3 x 8 x 4 doubles per thread) stay in registers for the whole K loop. One A-fragment load feeds 8 MMAs:
+// 16 flop per byte from L2, ~2.3 TB/s of L2 traffic at the FP64 peak. Results go to a scratch slab [row][group] and are
+// copied back by a second pass (other blocks still need the old amplitudes of the same groups), chunk by chunk so the
+// scratch stays at 256 MiB whatever the shard size.
+constexpr unsigned GEMM_BM = 128, GEMM_BN = 64, GEMM_THREADS = 256;
+
+__global__ void __launch_bounds__(256) gemmPrepKernel(const double2* __restrict__ gate, unsigned D, double2* __restrict__ afrag) {
+    const unsigned MBT = D / 16;
+    const uint64_t total = 3ull * MBT * MBT * 4u * 32u;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned ln = idx & 31u, c = (idx >> 5) & 3u;
+        const uint64_t blk = idx >> 7;
+        const unsigned kb = blk % MBT, mb = (blk / MBT) % MBT, m = (unsigned)(blk / ((uint64_t)MBT * MBT));
+        double val[2];
+#pragma unroll
+        for (unsigned w = 0; w < 2; w++) {
+            const unsigned v = 2 * c + w;                            // a[v]: row g + 8(v&1), col q + 4(v>>1)
+            const double2 e = gate[(uint64_t)(16 * mb + (ln >> 2) + 8 * (v & 1)) * D + 16 * kb + (ln & 3u) + 4 * (v >> 1)];
+            val[w] = m == 0 ? e.x : (m == 1 ? e.y - e.x : e.x + e.y);
+        }
+        afrag[idx] = make_double2(val[0], val[1]);
+    }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+manyTargGemmKernel(const double2* __restrict__ amps, double2* __restrict__ ytmp, uint64_t group0, unsigned chunkGroups, BitSpec sortedTargs,
+                   const uint64_t* __restrict__ rowOff, unsigned D, const double2* __restrict__ afrag) {
+    __shared__ __align__(16) double2 xs[2][16 * GEMM_BN];             // [buffer][k][n ^ ((k & 3) << 1)]
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3u;
+    const unsigned MBT = D / 16, col0 = blockIdx.x * GEMM_BN, mb = blockIdx.y * (GEMM_BM / 16) + warp;
+    // loader role: this thread brings column n of rows kq, kq + 4, kq + 8, kq + 12 of every slice
+    const unsigned n = threadIdx.x & (GEMM_BN - 1), kq = threadIdx.x / GEMM_BN;
+    const bool colValid = col0 + n < chunkGroups;
+    const double2* colBase = amps + (colValid ? insertZeroBits(group0 + col0 + n, sortedTargs) : 0ull);
+    auto loadSlice = [&](unsigned kb, unsigned buf) {
+#pragma unroll
+        for (unsigned j = 0; j < 4; j++) {
+            const unsigned k = kq + 4 * j;
+            double2* dst = &xs[buf][k * GEMM_BN + (n ^ ((k & 3u) << 1))];
+            if (colValid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(dst)), "l"(colBase + __ldg(&rowOff[16 * kb + k])) : "memory");
+            else *dst = make_double2(0.0, 0.0);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto loadA = [&](unsigned kb, double (&ar)[8], double (&ad)[8], double (&as)[8]) {
+        const double2* base = afrag + ((uint64_t)mb * MBT + kb) * 128u + lane;
+        const uint64_t mStride = (uint64_t)MBT * MBT * 128u;
+#pragma unroll
+        for (unsigned c = 0; c < 4; c++) {
+            const double2 r0 = __ldg(base + c * 32u), r1 = __ldg(base + mStride + c * 32u), r2 = __ldg(base + 2 * mStride + c * 32u);
+            ar[2 * c] = r0.x; ar[2 * c + 1] = r0.y;
+            ad[2 * c] = r1.x; ad[2 * c + 1] = r1.y;
+            as[2 * c] = r2.x; as[2 * c + 1] = r2.y;
+        }
+    };
+    double k1[8][4], k2[8][4], k3[8][4];
+#pragma unroll
+    for (unsigned nb = 0; nb < 8; nb++)
+#pragma unroll
+        for (unsigned v = 0; v < 4; v++) { k1[nb][v] = 0.0; k2[nb][v] = 0.0; k3[nb][v] = 0.0; }
+
+    loadSlice(0, 0);
+    for (unsigned kb = 0; kb < MBT; kb++) {
+        const unsigned buf = kb & 1u;
+        double ar[8], ad[8], as[8];
+        loadA(kb, ar, ad, as);                                        // L2 -> registers, in flight while the slice lands
+        if (kb + 1 < MBT) { loadSlice(kb + 1, buf ^ 1u); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        const unsigned xB = smemAddr(&xs[buf][0]);
+#pragma unroll
+        for (unsigned nb = 0; nb < 8; nb++) {
+            double xr[4], xi[4], xsum[4];
+#pragma unroll
+            for (unsigned v = 0; v < 4; v++) {                        // b[v]: k = q + 4v, n = nb * 8 + g
+                ldsAmp(xr[v], xi[v], xB + (((q + 4 * v) * GEMM_BN + ((nb * 8 + g) ^ (q << 1))) << 4));
+                xsum[v] = xr[v] + xi[v];
+            }
+            dmma16816(k2[nb], ad, xr);
+            dmma16816(k3[nb], as, xi);
+            dmma16816(k1[nb], ar, xsum);
+        }
+        __syncthreads();                                              // the slice may be overwritten two steps from now
+    }
+    // c[v]: row 16 mb + g + 8(v>>1), column nb * 8 + 2q + (v&1)
+#pragma unroll
+    for (unsigned nb = 0; nb < 8; nb++)
+#pragma unroll
+        for (unsigned v = 0; v < 4; v++) {
+            const unsigned col = col0 + nb * 8 + 2 * q + (v & 1u);
+            if (col < chunkGroups) ytmp[(uint64_t)(16 * mb + g + 8 * (v >> 1)) * chunkGroups + col] = make_double2(k1[nb][v] - k3[nb][v], k1[nb][v] + k2[nb][v]);
+        }
+}
+
+// getSuperoperator (src/misc.hpp:58-81) on the device: S[(i d + k)][(j d + l)] = sum over Kraus operators, in their order, of
+// conj(K[i][j]) * K[k][l]  (d = 2^t, S is d^2 x d^2). One thread per entry.
+__global__ void __launch_bounds__(256) superoperatorKernel(const double2* __restrict__ kraus, unsigned numOps, unsigned d, double2* __restrict__ out) {
+    const uint64_t D = (uint64_t)d * d, total = D * D;
+    for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t row = idx / D, col = idx - row * D;
+        const unsigned i = (unsigned)(row / d), k = (unsigned)(row - (uint64_t)i * d), j = (unsigned)(col / d), l = (unsigned)(col - (uint64_t)j * d);
+        double2 acc = make_double2(0.0, 0.0);
+        for (unsigned o = 0; o < numOps; o++) {
+            const double2* K = kraus + (uint64_t)o * d * d;
+            const double2 a = K[(uint64_t)i * d + j], b = K[(uint64_t)k * d + l];
+            acc = cadd(acc, make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x));
+        }
+        out[idx] = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 
 struct Gate4 { double2 m[16]; };
 
@@ -466,9 +585,11 @@ extern "C" int dfsa_plan_manyTargLayout(const uint32_t* targets, unsigned numTar
     return DFSA_OK;
 }
 
-extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
+// `gate` = host matrix, or -- krausOps != nullptr -- the gate is the superoperator of numKraus host Kraus operators on
+// numTargets / 2 qubits, built on the device (GEMM path only; smaller superoperators are built by the caller on the host)
+static int manyTargImpl(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate, const double* krausOps, unsigned numKraus) {
     DFSA_TRY(dfsaEnsureDevice());
-    DFSA_REQUIRE(s && targets && gate, "null argument");
+    DFSA_REQUIRE(s && targets && (gate || krausOps), "null argument");
     const unsigned t = numTargets, L = s->logNumAmps;
     DFSA_REQUIRE(t >= 1 && t <= L, "manyTargGate needs 1 <= numTargets <= local bits (distributed_statevector.hpp:191)");
     BitSpec sortedT; uint64_t targMask;
@@ -526,6 +647,59 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
         }
     }
 
+    DFSA_REQUIRE(gate || (t >= 7 && t <= 11), "device-built superoperators are served by the GEMM path (7..11 effective targets)");
+    if (t >= 7 && t <= 11 && (!gate || !getenv("DFSA_MANYTARG_GENERIC"))) {
+        // scratch: [gate D^2 amps][A-fragments 3 D^2 doubles][row offsets D u64][result slab]
+        const size_t fragBytes = 3 * d * d * sizeof(double), offBytes = d * sizeof(uint64_t);
+        const uint64_t numGroups = s->numAmps >> t;
+        uint64_t chunkGroups = std::min<uint64_t>(numGroups, std::max<uint64_t>(GEMM_BN, ((256ull << 20) / sizeof(double2)) >> t));
+        chunkGroups = std::min<uint64_t>(chunkGroups, 0x7fffffc0ull);
+        const size_t slabBytes = (size_t)chunkGroups * d * sizeof(double2);
+        double2* dev;
+        DFSA_TRY(dfsaScratch(gateBytes + fragBytes + offBytes + slabBytes + 1024, &dev));
+        double2* dGate = dev;
+        double2* dFrag = (double2*)((char*)dev + gateBytes);
+        uint64_t* dOff = (uint64_t*)((char*)dFrag + fragBytes);
+        double2* dSlab = (double2*)((char*)dOff + ((offBytes + 255) / 256) * 256);
+        std::vector<uint64_t> rowOff(d);
+        for (uint64_t r = 0; r < d; r++) {
+            uint64_t off = 0;
+            for (unsigned b = 0; b < t; b++) off |= ((r >> b) & 1ULL) << targets[b];
+            rowOff[r] = off;
+        }
+        if (gate) DFSA_CUDA(cudaMemcpyAsync(dGate, gate, gateBytes, cudaMemcpyHostToDevice, ctx.compute));
+        else {
+            // the Kraus operators (numKraus x 2^(t/2) x 2^(t/2)) ride in the result slab, which is not in use yet
+            const unsigned dk = 1u << (t / 2);
+            const size_t krausBytes = (size_t)numKraus * dk * dk * sizeof(double2);
+            DFSA_REQUIRE(krausBytes <= slabBytes, "too many Kraus operators");
+            DFSA_CUDA(cudaMemcpyAsync(dSlab, krausOps, krausBytes, cudaMemcpyHostToDevice, ctx.compute));
+            superoperatorKernel<<<ctx.numSMs * 4, 256, 0, ctx.compute>>>(dSlab, numKraus, dk, dGate);
+            DFSA_LAUNCH_CHECK();
+        }
+        DFSA_CUDA(cudaMemcpyAsync(dOff, rowOff.data(), offBytes, cudaMemcpyHostToDevice, ctx.compute));
+        DFSA_CUDA(cudaStreamSynchronize(ctx.compute));        // caller-owned pageable sources
+        gemmPrepKernel<<<ctx.numSMs * 4, 256, 0, ctx.compute>>>(dGate, (unsigned)d, dFrag);
+        DFSA_LAUNCH_CHECK();
+        double2* amps = s->arr[DFSA_AMPS];
+        for (uint64_t g0 = 0; g0 < numGroups; g0 += chunkGroups) {
+            const unsigned cg = (unsigned)std::min<uint64_t>(chunkGroups, numGroups - g0);
+            dim3 grid((cg + GEMM_BN - 1) / GEMM_BN, (unsigned)(d / GEMM_BM));
+            manyTargGemmKernel<<<grid, GEMM_THREADS, 0, ctx.compute>>>(amps, dSlab, g0, cg, sortedT, dOff, (unsigned)d, dFrag);
+            DFSA_LAUNCH_CHECK();
+            // results home: amps[group | row bits] = slab[row][group]
+            const uint64_t* offs = dOff;
+            const BitSpec sp = sortedT;
+            auto ld = [=] __device__(uint64_t i) { return Amp1{dSlab[i]}; };
+            auto st = [=] __device__(uint64_t i, const Amp1& v) {
+                const uint64_t r = i / cg, gc = i - r * cg;
+                amps[insertZeroBits(g0 + gc, sp) | offs[r]] = v.a;
+            };
+            DFSA_TRY((launchStream<2, Amp1>((uint64_t)cg * d, ld, st)));
+        }
+        return DFSA_OK;
+    }
+
     DFSA_REQUIRE(d * sizeof(double2) <= 200 * 1024, "manyTargGate: 2^numTargets amplitudes must fit shared memory (numTargets <= 13)");
     BitSpec caller; caller.n = t;
     for (unsigned i = 0; i < t; i++) caller.pos[i] = (uint8_t)targets[i];
@@ -540,4 +714,35 @@ extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned 
     manyTargGenericKernel<<<grid, 256, smemBytes, ctx.compute>>>(s->arr[DFSA_AMPS], numGroups, sortedT, caller, t, dev, dev + d * d);
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
+}
+
+extern "C" int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate) {
+    DFSA_REQUIRE(gate, "null gate");
+    return manyTargImpl(s, targets, numTargets, gate, nullptr, 0);
+}
+
+// krausMap's local part (distributed_densitymatrix.hpp:79-89): the 2t-target gate sum_K conj(K) (x) K on the bits
+// {targets, targets + N} (all local by now). Small superoperators (2t <= 6) are built here on the host exactly as
+// getSuperoperator does (misc.hpp:58-81); from 2t = 8 on the 4^t x 4^t matrix is built ON THE DEVICE from the uploaded Kraus
+// operators and consumed by the GEMM kernel without ever existing on the host.
+extern "C" int dfsa_k_krausMap(dfsa_state* s, const uint32_t* targets2t, unsigned numTargets2t, const double* krausOps, unsigned numOps) {
+    DFSA_REQUIRE(s && targets2t && krausOps && numOps >= 1 && numTargets2t >= 2 && (numTargets2t & 1u) == 0, "bad argument");
+    if (numTargets2t >= 8 && numTargets2t <= 11) return manyTargImpl(s, targets2t, numTargets2t, nullptr, krausOps, numOps);
+    const uint64_t d = 1ULL << (numTargets2t / 2), D = d * d;
+    std::vector<double> super(2 * D * D, 0.0);
+    for (unsigned o = 0; o < numOps; o++) {
+        const double* K = krausOps + 2 * d * d * o;
+        for (uint64_t i = 0; i < d; i++)
+            for (uint64_t j = 0; j < d; j++) {
+                const double cr = K[2 * (i * d + j)], ci = -K[2 * (i * d + j) + 1];
+                for (uint64_t k = 0; k < d; k++)
+                    for (uint64_t l = 0; l < d; l++) {
+                        const double br = K[2 * (k * d + l)], bi = K[2 * (k * d + l) + 1];
+                        double* e = &super[2 * ((i * d + k) * D + (j * d + l))];
+                        e[0] += cr * br - ci * bi;
+                        e[1] += cr * bi + ci * br;
+                    }
+            }
+    }
+    return manyTargImpl(s, targets2t, numTargets2t, super.data(), nullptr, 0);
 }

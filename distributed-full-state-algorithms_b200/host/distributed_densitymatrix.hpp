@@ -66,7 +66,13 @@ static inline void distributed_densitymatrix_krausMap(DensityMatrix& rho, Matrix
     assert(2 * targets.size() <= rho.logNumAmpsPerNode);
     NatArray extended = targets;
     for (Nat t : targets) extended.push_back(t + rho.numQubits);
-    distributed_statevector_manyTargGate(rho, extended, getSuperoperator(krausOps));
+    // one 2t-target gate with the superoperator sum_K conj(K) (x) K (reference :79-89); the library builds that matrix itself --
+    // on the device from 4 target qubits on, where it has 65536+ entries (getSuperoperator, misc.hpp:58-81, remains available)
+    std::vector<double> flat;
+    for (const AmpMatrix& K : krausOps) { const std::vector<double> f = dfsaFlatten(K); flat.insert(flat.end(), f.begin(), f.end()); }
+    dfsa_manyTargWithRelocation(rho, extended, [&](const NatArray& placed) {
+        DFSA_CHECK(dfsa_k_krausMap(rho.handle, placed.data(), Nat(placed.size()), flat.data(), Nat(krausOps.size())));
+    });
 }
 
 static inline void distributed_densitymatrix_oneQubitDephasing(DensityMatrix& rho, Nat qb, Real prob) {

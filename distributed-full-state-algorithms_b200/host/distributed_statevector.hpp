@@ -139,7 +139,10 @@ static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const 
     return placed;
 }
 
-static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArray targets, AmpMatrix gate) {
+// manyTargGate with the local step left open: `applyLocal(placed)` runs the dense-gate kernel on the (all suffix) index bits
+// the targets occupy after relocation. krausMap uses it with a kernel that builds its own superoperator on the device.
+template <class LocalStep>
+static inline void dfsa_manyTargWithRelocation(StateVector& psi, NatArray targets, LocalStep applyLocal) {
     assert(targets.size() <= psi.logNumAmpsPerNode);
     targets = psi.physical(targets);
     const NatArray placed = dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets);
@@ -150,7 +153,7 @@ static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArr
         if (placed[i] != targets[i]) { landing.push_back(placed[i]); prefix.push_back(targets[i]); }
     assert(landing.size() <= 4 && "at most 16 ranks");
     if (!landing.empty()) DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
-    local_statevector_manyTargGate(psi, placed, gate);
+    applyLocal(placed);
     if (landing.empty()) return;
     if (dfsa_detail::lazyLayoutEnabled()) {
         // leave the targets where they are and remember it: the next gate on them is local, and the undo happens once,
@@ -159,6 +162,10 @@ static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArr
         return;
     }
     DFSA_CHECK(dfsa_xk_relocate(psi.handle, landing.data(), prefix.data(), Nat(landing.size())));
+}
+
+static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArray targets, AmpMatrix gate) {
+    dfsa_manyTargWithRelocation(psi, targets, [&](const NatArray& placed) { local_statevector_manyTargGate(psi, placed, gate); });
 }
 
 static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi, const NatArray& targets, const NatArray& paulis, Amp thisAmpFac, Amp otherAmpFac) {

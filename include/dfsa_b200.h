@@ -168,6 +168,10 @@ int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, 
 int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2);
 /* K4: dense 2^t x 2^t gate on suffix targets, gate bit i <-> targets[i]. local_statevector.hpp:72 */
 int dfsa_k_manyTarg(dfsa_state* s, const uint32_t* targets, unsigned numTargets, const double* gate);
+/* krausMap after relocation (src/distributed_densitymatrix.hpp:79-89 + getSuperoperator, src/misc.hpp:58-81): applies
+ * sum_K conj(K) (x) K as a gate on the 2t suffix bits targets2t = {targets, targets + N} (gate bit i <-> targets2t[i]).
+ * krausOps: numOps host matrices 2^t x 2^t, row-major interleaved. From t = 4 the superoperator is built on the device. */
+int dfsa_k_krausMap(dfsa_state* s, const uint32_t* targets2t, unsigned numTargets2t, const double* krausOps, unsigned numOps);
 /* Host-only (no device needed): the tile plan of the tensor-core manyTarg kernel (3 <= numTargets <= 6, logNumAmps >= 9) --
  * the 9 index bits of a tile (ascending), their roles (< numTargets: gate-row bit i = targets[i], else vector bit
  * role - numTargets), the slab byte-offset contribution of each tile bit (address order, XOR-swizzled) and the same per

@@ -116,10 +116,10 @@ def test_every_target_position_one_and_ctrl_gate(dfsa):
     compare.assert_close(st.get_amps(), o.get_amps(), tol=1e-11, what="target sweep")   # 28 chained non-unitary gates
 
 
-@pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("nt", [1, 2, 3, 4, 5, 6, 7, 8, 9])
 def test_many_targ_gate_every_kernel_and_placement(dfsa, nt):
     """manyTargGate (local_statevector.hpp:72-99) picks its kernel by target count (pair stream, quad stream, tensor-core
-    tiles for t = 3..6, generic above and on shards smaller than a tile), and the tensor-core kernel's
+    tiles for t = 3..6, the tiled tensor-core GEMM with the gate streamed from L2 for t = 7..11, generic on shards smaller than a tile), and the tensor-core kernel's
     tile layout and shared-memory swizzle depend on where the targets sit. Every kernel, targets low / high / scattered /
     just above the free bits, in caller order (not sorted), against the oracle."""
     rng = np.random.default_rng(100 + nt)
@@ -139,6 +139,22 @@ def test_many_targ_gate_every_kernel_and_placement(dfsa, nt):
             o, _ = _oracle_run("sv", nq, 1, amps, ("sv_manyTargGate", targets, gate))
             compare.assert_close(st.get_amps(), o.get_amps(), what="manyTargGate nq=%d targets=%r" % (nq, targets))
             st.close()
+
+
+@pytest.mark.parametrize("nq,nt", [(7, 4), (8, 4), (8, 5), (6, 3)])
+def test_kraus_map_on_4_and_5_qubits_builds_its_superoperator_on_the_device(dfsa, nq, nt):
+    """krausMap on 4 / 5 qubits = a dense gate on 8 / 10 index bits with a 256^2 / 1024^2 superoperator
+    (distributed_densitymatrix.hpp:79-89, misc.hpp:58-81): built on the device, applied by the GEMM kernel."""
+    rng = np.random.default_rng(nq * 10 + nt)
+    targets = [int(x) for x in rng.permutation(nq)[:nt]]
+    ops = [cases.random_matrix(rng, 1 << nt) / (1 << nt) for _ in range(3)]
+    amps = cases.random_state(rng, 2 * nq)
+    st = dfsa.DeviceState("dm", nq)
+    st.set_amps(amps)
+    st.dm_krausMap(targets, ops)
+    o, _ = _oracle_run("dm", nq, 1, amps, ("dm_krausMap", targets, ops))
+    compare.assert_close(st.get_amps(), o.get_amps(), what="krausMap nq=%d targets=%r" % (nq, targets))
+    st.close()
 
 
 def test_all_z_pauli_string_applies_the_operator(dfsa):
