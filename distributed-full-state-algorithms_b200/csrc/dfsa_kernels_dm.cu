@@ -191,7 +191,7 @@ int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, uns
         out[j | other] = cscale(c3, v.b);
         out[j | same]  = make_double2(fma(c1, v.c.x, c2 * v.a.x), fma(c1, v.c.y, c2 * v.a.y));
     };
-    return launchStream<1, Item>(s->numAmps >> 1, ld, st);
+    return launchStreamRemote<Item>(s->numAmps >> 1, ld, st);
 }
 
 // K22 fused with its one-way transfer (distributed_densitymatrix.hpp:284-313), out of place:
@@ -217,7 +217,7 @@ int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, un
         out[j] = make_double2(fma(prob, v.c.x, v.a.x), fma(prob, v.c.y, v.a.y));
         out[j | one] = cscale(c1, v.b);
     };
-    return launchStream<1, Amp3>(s->numAmps >> 1, ld, st);
+    return launchStreamRemote<Amp3>(s->numAmps >> 1, ld, st);
 }
 
 // K20: distributed_densitymatrix.hpp:152-183 (qb1 suffix, qb2 prefix). q0 = qb1, q1 = qb2, q2 = qb1+N, bit = rank bit of qb2's bra.
@@ -364,7 +364,7 @@ int dfsaLaunchFusedDepol2Pair(dfsa_state* s, const double2* remote, unsigned q0,
 #pragma unroll
         for (unsigned e = 0; e < 8; e++) out[index(k, e)] = (e == eA) ? n0 : ((e == eB) ? n1 : cscale(offFac, it.v[e]));
     };
-    return launchStream<1, Amp10>(s->numAmps >> 3, ld, st);
+    return launchStream<1, Amp10, decltype(ld), decltype(st), true>(s->numAmps >> 3, ld, st);
 }
 
 // K21 fused with its two exchanges (distributed_densitymatrix.hpp:195-237), ONE out-of-place pass over the shards of the
@@ -405,7 +405,7 @@ int dfsaLaunchFusedDepol2Quad(dfsa_state* s, const double2* const* remote /* P0,
 #pragma unroll
         for (unsigned e = 0; e < 4; e++) out[jz | ((uint64_t)(e & 1u) << q0) | ((uint64_t)(e >> 1) << q1)] = (e == eMine) ? n : cscale(offFac, it.v[e]);
     };
-    return launchStream<1, Amp7>(s->numAmps >> 2, ld, st);
+    return launchStream<1, Amp7, decltype(ld), decltype(st), true>(s->numAmps >> 2, ld, st);
 }
 
 // K22: distributed_densitymatrix.hpp:284-313.

@@ -207,7 +207,7 @@ int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, dou
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], remote[i]}; };
     auto st = [=] __device__(uint64_t i, const Amp2& v) { out[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<1, Amp2>(s->numAmps, ld, st);
+    return launchStreamRemote<Amp2>(s->numAmps, ld, st);
 }
 
 template <bool EXACT>
@@ -224,7 +224,7 @@ static int launchFusedPauli(dfsa_state* s, const double2* remote, int pairRank, 
             out[j0] = cfma(h1, v.a1, cmul(f, v.a0));
         }
     };
-    return launchStream<1, Amp2>(s->numAmps, ld, st);
+    return launchStreamRemote<Amp2>(s->numAmps, ld, st);
 }
 
 int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
@@ -238,7 +238,7 @@ int dfsaLaunchPull(dfsa_state* s, const double2* remote) {
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t i) { return Amp1{remote[i]}; };
     auto st = [=] __device__(uint64_t i, const Amp1& v) { out[i] = v.a; };
-    return launchStream<2, Amp1>(s->numAmps, ld, st);
+    return launchStreamRemote<Amp1>(s->numAmps, ld, st);
 }
 
 // K18: distributed_densitymatrix.hpp:44-49 (amp *= -1) generalised to a complex factor.
@@ -315,7 +315,7 @@ int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const BitSpe
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t j) { const uint64_t k = insertZeroBits(j, spec) | fixed; return Amp2{amps[k], remote[k]}; };
     auto st = [=] __device__(uint64_t j, const Amp2& v) { out[j] = cfma(c1, v.a1, cmul(c0, v.a0)); };
-    return launchStream<1, Amp2>(s->numAmps >> spec.n, ld, st);
+    return launchStreamRemote<Amp2>(s->numAmps >> spec.n, ld, st);
 }
 
 // unpack half a shard from an arbitrary (possibly peer-mapped) source: amps[insert(k, qb, bitValue)] = src[k]
@@ -334,7 +334,7 @@ int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsig
         out[i] = v.a0;
         out[i ^ bit] = v.a1;
     };
-    return launchStream<1, Amp2>(s->numAmps >> 1, ld, st);
+    return launchStreamRemote<Amp2>(s->numAmps >> 1, ld, st);
 }
 
 // Single-shot relocation: swap k suffix qubits s_i with k prefix qubits in ONE out-of-place pass over the
@@ -358,7 +358,7 @@ int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigne
         return Amp1{table.shard[sigma][(j & ~sMask) | rhoBits]};
     };
     auto st = [=] __device__(uint64_t j, const Amp1& v) { out[j] = v.a; };
-    return launchStream<2, Amp1>(s->numAmps, ld, st);
+    return launchStreamRemote<Amp1>(s->numAmps, ld, st);
 }
 
 // K9: distributed_statevector.hpp:133-135, 152-156

@@ -37,15 +37,19 @@ __global__ void __launch_bounds__(DFSA_TPB) streamKernel(uint64_t numItems, LD l
 // slower both with fewer (latency-bound) and with more (full occupancy: 5.8-6.0 TB/s -- more concurrent streams, fewer
 // open-page hits). So the persistent grid is SMs x B with B = inflight / (256 x loads per thread), capped by occupancy;
 // DFSA_STREAM_INFLIGHT (default 2048) overrides the target.
-template <int UNROLL, class T, class LD, class ST>
+//
+// REMOTE = some of the loads go to a peer GPU over NVLink (the fused exchange kernels): latency is a few microseconds instead
+// of ~1, so the same bandwidth-delay argument asks for several times as many loads in flight; measured on 2 B200s
+// (tools/link_sweep.py, profiles/r02_link_sweep_n2.jsonl). DFSA_REMOTE_INFLIGHT (default 8192 per SM, local + remote) overrides.
+template <int UNROLL, class T, class LD, class ST, bool REMOTE = false>
 static int launchStream(uint64_t numItems, LD ld, ST st) {
     if (numItems == 0) return DFSA_OK;
     static int blocksPerSM = 0;
     if (blocksPerSM == 0) {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, streamKernel<UNROLL, T, LD, ST>, DFSA_TPB, 0) != cudaSuccess || occ < 1) occ = 4;
-        const char* e = getenv("DFSA_STREAM_INFLIGHT");
-        const int inflight = e ? atoi(e) : 2048;
+        const char* e = getenv(REMOTE ? "DFSA_REMOTE_INFLIGHT" : "DFSA_STREAM_INFLIGHT");
+        const int inflight = e ? atoi(e) : (REMOTE ? 8192 : 2048);
         const int loadsPerThread = UNROLL * T::kLoads;
         int want = inflight / (DFSA_TPB * loadsPerThread);
         if (want < 1) want = 1;
@@ -56,6 +60,10 @@ static int launchStream(uint64_t numItems, LD ld, ST st) {
     DFSA_LAUNCH_CHECK();
     return DFSA_OK;
 }
+
+// fused exchange kernels: two items per thread, sized for NVLink latency
+template <class T, class LD, class ST>
+static int launchStreamRemote(uint64_t numItems, LD ld, ST st) { return launchStream<2, T, LD, ST, true>(numItems, ld, st); }
 
 // item types; kLoads = 16-byte loads one item keeps in flight (used to size the grid, see launchStream)
 struct Amp1 { static constexpr int kLoads = 1; double2 a; };
