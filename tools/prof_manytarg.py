@@ -16,7 +16,8 @@ for nt in [int(x) for x in (sys.argv[2].split(",") if len(sys.argv) > 2 else "4,
     d = 1 << nt
     g, _ = np.linalg.qr(rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)))
     targs = {"random": [int(x) for x in rng.permutation(nq)[:nt]], "low": list(range(nt)), "top": list(range(nq - nt, nq)),
-             "mid": [6 + 2 * i for i in range(nt)][::-1], "mixed": [3, 0, 17, nq - 1, 9, 12][:nt]}[placement]
+             "mid": [6 + 2 * i for i in range(nt)][::-1], "mixed": [3, 0, 17, nq - 1, 9, 12][:nt],
+             "mixed8": [3, 0, 17, nq - 1, 9, 12, 5, 20, 22, 14, 7][:nt]}[placement]
     for _ in range(2):
         st.sv_manyTargGate(targs, g)
 dfsa.comm_synch()
