@@ -1101,13 +1101,14 @@ extern "C" int dfsa_state_download_all(dfsa_state* s, double* hostAll) {
     DFSA_TRY(dfsa_comm_barrier());
     if (c.size == 1) return dfsa_state_download(s, DFSA_AMPS, 0, s->numAmps, hostAll);
     size_t shardBytes = s->numAmps * sizeof(double2);
-    if (c.transport == Transport::Nccl) {
-        double2* all = nullptr;
-        DFSA_CUDA(cudaMalloc((void**)&all, shardBytes * c.size));
-        DFSA_NCCL(ncclAllGather(s->arr[DFSA_AMPS], all, 2 * s->numAmps, ncclDouble, g_comm.nccl, c.comm));
-        DFSA_CUDA(cudaMemcpyAsync(hostAll, all, shardBytes * c.size, cudaMemcpyDeviceToHost, c.comm));
-        DFSA_CUDA(cudaStreamSynchronize(c.comm));
-        DFSA_CUDA(cudaFree(all));
+    if (c.transport == Transport::Nccl && !(g_comm.shm && g_comm.peersOk)) {
+        // no peer mappings: shard by shard through the exchange buffer (nothing else is in flight after the barrier above), so
+        // the gather needs no device memory beyond what the state already owns
+        for (int r = 0; r < c.size; r++) {
+            DFSA_NCCL(ncclBroadcast(s->arr[DFSA_AMPS], s->arr[DFSA_BUFFER], 2 * s->numAmps, ncclDouble, r, g_comm.nccl, c.comm));
+            DFSA_CUDA(cudaMemcpyAsync((char*)hostAll + shardBytes * r, r == c.rank ? s->arr[DFSA_AMPS] : s->arr[DFSA_BUFFER], shardBytes, cudaMemcpyDeviceToHost, c.comm));
+            DFSA_CUDA(cudaStreamSynchronize(c.comm));
+        }
     } else {
         for (int r = 0; r < c.size; r++) {
             double2* src = s->arr[DFSA_AMPS];

@@ -132,6 +132,14 @@ void dfsa_host_plan_manyTarg(unsigned L, const unsigned* targets, unsigned n, un
     NatArray placed = dfsa_planManyTargRelocation(L, toNats(targets, n));
     for (unsigned i = 0; i < n; i++) placedOut[i] = placed[i];
 }
+// lazy layout: the steps that restore index order. out = numSteps x {kind (0 = relocation pair, 1 = index-bit swap), a, b}
+unsigned dfsa_host_plan_restoreLayout(const unsigned* where, unsigned n, unsigned L, unsigned* out) {
+    dfsa_detail::RestorePlan plan = dfsa_detail::planRestore(NatArray(where, where + n), L);
+    unsigned steps = 0;
+    for (std::size_t i = 0; i < plan.relocateSuffix.size(); i++, steps++) { out[3 * steps] = 0; out[3 * steps + 1] = plan.relocateSuffix[i]; out[3 * steps + 2] = plan.relocatePrefix[i]; }
+    for (const auto& sw : plan.swaps) { out[3 * steps] = 1; out[3 * steps + 1] = sw.first; out[3 * steps + 2] = sw.second; steps++; }
+    return steps;
+}
 // sortedTargets: the ket targets, ascending; reorderedOut has 2n entries, remainingOut 2N-2n
 void dfsa_host_plan_partialTrace(unsigned N, unsigned L, const unsigned* sortedTargets, unsigned n, unsigned* reorderedOut, unsigned* remainingOut) {
     NatArray ext = toNats(sortedTargets, n);

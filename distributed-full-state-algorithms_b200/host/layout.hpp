@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <numeric>
+#include <utility>
+#include <vector>
 
 namespace dfsa_detail {
 
@@ -87,40 +89,54 @@ inline NatArray StateVector::physical(const NatArray& logical) const {
     return out;
 }
 
-// index bits posA and posB have just traded contents (or are declared to have, for a pure relabelling)
-inline void StateVector::noteSwapped(Nat posA, Nat posB) {
-    for (Nat& w : where) {
-        if (w == posA) w = posB;
-        else if (w == posB) w = posA;
-    }
-}
-
 inline Nat StateVector::numDisplacedAcrossShardBoundary() const {
     Nat n = 0;
     for (Nat q = 0; q < Nat(where.size()); q++) n += (q >= logNumAmpsPerNode && where[q] < logNumAmpsPerNode) ? 1 : 0;
     return n;
 }
 
-// Put every logical qubit back on its own index bit. What manyTargGate leaves behind are 2-cycles (a prefix qubit sitting on
-// a suffix bit and vice versa): all of those go in ONE relocation step; anything else (longer cycles after several gates) is
-// sorted out with plain index-bit swaps.
-inline void StateVector::restoreLayout() {
-    if (layoutIsIdentity()) return;
-    const Nat L = Nat(logNumAmpsPerNode), n = Nat(where.size());
-    NatArray holder(n);                                            // holder[p] = logical qubit on index bit p
-    for (Nat q = 0; q < n; q++) holder[where[q]] = q;
-    NatArray suffixBits, prefixBits;
-    for (Nat q = L; q < n && suffixBits.size() < 4; q++) {
+// The steps that put every logical qubit back on its own index bit, as a pure function of the layout (tests/test_layout_plan.py
+// replays them on a numpy array). What manyTargGate leaves behind are 2-cycles (a prefix qubit sitting on a suffix bit and vice
+// versa): up to four of those go in ONE relocation step; anything else (longer cycles after several gates) is sorted out
+// with plain index-bit swaps.
+namespace dfsa_detail {
+struct RestorePlan {
+    NatArray relocateSuffix, relocatePrefix;      // (suffix bit, prefix bit) pairs of the single relocation step (may be empty)
+    std::vector<std::pair<Nat, Nat>> swaps;       // index-bit swaps that follow, in order
+};
+
+inline void relabel(NatArray& where, Nat posA, Nat posB) {
+    for (Nat& w : where) {
+        if (w == posA) w = posB;
+        else if (w == posB) w = posA;
+    }
+}
+
+inline RestorePlan planRestore(NatArray where, Nat L) {
+    RestorePlan plan;
+    const Nat n = Nat(where.size());
+    for (Nat q = L; q < n && plan.relocateSuffix.size() < 4; q++) {
         const Nat p = where[q];                                    // logical prefix qubit q sits on bit p ...
-        if (p < L && where[p] == q) { suffixBits.push_back(p); prefixBits.push_back(q); }   // ... and bit q holds logical qubit p
+        if (p < L && where[p] == q) { plan.relocateSuffix.push_back(p); plan.relocatePrefix.push_back(q); }   // ... and bit q holds logical qubit p
     }
-    if (!suffixBits.empty()) {
-        DFSA_CHECK(dfsa_xk_relocate(handle, suffixBits.data(), prefixBits.data(), Nat(suffixBits.size())));
-        for (std::size_t i = 0; i < suffixBits.size(); i++) noteSwapped(suffixBits[i], prefixBits[i]);
-    }
+    for (std::size_t i = 0; i < plan.relocateSuffix.size(); i++) relabel(where, plan.relocateSuffix[i], plan.relocatePrefix[i]);
     for (Nat q = 0; q < n; q++) {
         if (where[q] == q) continue;
-        dfsa_detail::swapIndexBits(*this, where[q], q);
-        noteSwapped(where[q], q);
+        plan.swaps.emplace_back(where[q], q);
+        relabel(where, where[q], q);
     }
+    return plan;
+}
+}  // namespace dfsa_detail
+
+// index bits posA and posB have just traded contents (or are declared to have, for a pure relabelling)
+inline void StateVector::noteSwapped(Nat posA, Nat posB) { dfsa_detail::relabel(where, posA, posB); }
+
+inline void StateVector::restoreLayout() {
+    if (layoutIsIdentity()) return;
+    const dfsa_detail::RestorePlan plan = dfsa_detail::planRestore(where, Nat(logNumAmpsPerNode));
+    if (!plan.relocateSuffix.empty())
+        DFSA_CHECK(dfsa_xk_relocate(handle, plan.relocateSuffix.data(), plan.relocatePrefix.data(), Nat(plan.relocateSuffix.size())));
+    for (const auto& sw : plan.swaps) dfsa_detail::swapIndexBits(*this, sw.first, sw.second);
+    resetLayout();
 }
