@@ -724,7 +724,8 @@ def run_product(args, world, rank, local_rank):
     if not args.skip_configs:
         for N in ((14, 16) if world == 1 else (16,)):
             configs["config4_noisy_dm_%dq" % N] = run_config(job, "dm", peaks, reps=2, dm_qubits=N)
-        configs["config5_expec_ptrace_16q"] = run_config(job, "expec", peaks, reps=2, dm_qubits=16)
+        for N in ((14, 16) if world == 1 else (16,)):
+            configs["config5_expec_ptrace_%dq" % N] = run_config(job, "expec", peaks, reps=2, dm_qubits=N)
 
     if rank == 0:
         line = {

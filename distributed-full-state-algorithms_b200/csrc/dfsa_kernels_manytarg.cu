@@ -387,22 +387,32 @@ __global__ void __launch_bounds__(256) gemmPrepKernel(const double2* __restrict_
     }
 }
 
+// ROWS_FAST: gate bit 0 sits on index bit 0, so the 16 rows of a slice are runs of contiguous amplitudes while neighbouring
+// groups are 2^t-strided: the loader's lanes then walk rows first (otherwise groups first, which are contiguous when the
+// low index bits are not targets).
+template <bool ROWS_FAST>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 manyTargGemmKernel(const double2* __restrict__ amps, double2* __restrict__ ytmp, uint64_t group0, unsigned chunkGroups, BitSpec sortedTargs,
                    const uint64_t* __restrict__ rowOff, unsigned D, const double2* __restrict__ afrag) {
     __shared__ __align__(16) double2 xs[2][16 * GEMM_BN];             // [buffer][k][n ^ ((k & 3) << 1)]
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, g = lane >> 2, q = lane & 3u;
     const unsigned MBT = D / 16, col0 = blockIdx.x * GEMM_BN, mb = blockIdx.y * (GEMM_BM / 16) + warp;
-    // loader role: this thread brings column n of rows kq, kq + 4, kq + 8, kq + 12 of every slice
-    const unsigned n = threadIdx.x & (GEMM_BN - 1), kq = threadIdx.x / GEMM_BN;
-    const bool colValid = col0 + n < chunkGroups;
-    const double2* colBase = amps + (colValid ? insertZeroBits(group0 + col0 + n, sortedTargs) : 0ull);
+    // loader role: 4 of the 16 x 64 amplitudes of every slice -- (row kq + 4j, column n), or with ROWS_FAST (row k, column nq + 16j)
+    const unsigned n = ROWS_FAST ? (threadIdx.x >> 4) : (threadIdx.x & (GEMM_BN - 1)), kq = ROWS_FAST ? (threadIdx.x & 15u) : (threadIdx.x / GEMM_BN);
+    const double2* colBase[ROWS_FAST ? 4 : 1];
+    bool colValid[ROWS_FAST ? 4 : 1];
+#pragma unroll
+    for (unsigned j = 0; j < (ROWS_FAST ? 4u : 1u); j++) {
+        const unsigned col = col0 + n + 16 * j;
+        colValid[j] = col < chunkGroups;
+        colBase[j] = amps + (colValid[j] ? insertZeroBits(group0 + col, sortedTargs) : 0ull);
+    }
     auto loadSlice = [&](unsigned kb, unsigned buf) {
 #pragma unroll
         for (unsigned j = 0; j < 4; j++) {
-            const unsigned k = kq + 4 * j;
-            double2* dst = &xs[buf][k * GEMM_BN + (n ^ ((k & 3u) << 1))];
-            if (colValid) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(dst)), "l"(colBase + __ldg(&rowOff[16 * kb + k])) : "memory");
+            const unsigned k = ROWS_FAST ? kq : kq + 4 * j, nn = ROWS_FAST ? n + 16 * j : n, cj = ROWS_FAST ? j : 0;
+            double2* dst = &xs[buf][k * GEMM_BN + (nn ^ ((k & 3u) << 1))];
+            if (colValid[cj]) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(dst)), "l"(colBase[cj] + __ldg(&rowOff[16 * kb + k])) : "memory");
             else *dst = make_double2(0.0, 0.0);
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -654,7 +664,9 @@ static int manyTargImpl(dfsa_state* s, const uint32_t* targets, unsigned numTarg
         const uint64_t numGroups = s->numAmps >> t;
         uint64_t chunkGroups = std::min<uint64_t>(numGroups, std::max<uint64_t>(GEMM_BN, ((256ull << 20) / sizeof(double2)) >> t));
         chunkGroups = std::min<uint64_t>(chunkGroups, 0x7fffffc0ull);
-        const size_t slabBytes = (size_t)chunkGroups * d * sizeof(double2);
+        // (the result slab doubles as the landing area of the uploaded Kraus operators, so it is at least that large)
+        const size_t krausBytes = krausOps ? (size_t)numKraus * (d * sizeof(double2)) : 0;      // numKraus matrices of sqrt(d) x sqrt(d)
+        const size_t slabBytes = std::max((size_t)chunkGroups * d * sizeof(double2), krausBytes);
         double2* dev;
         DFSA_TRY(dfsaScratch(gateBytes + fragBytes + offBytes + slabBytes + 1024, &dev));
         double2* dGate = dev;
@@ -671,8 +683,6 @@ static int manyTargImpl(dfsa_state* s, const uint32_t* targets, unsigned numTarg
         else {
             // the Kraus operators (numKraus x 2^(t/2) x 2^(t/2)) ride in the result slab, which is not in use yet
             const unsigned dk = 1u << (t / 2);
-            const size_t krausBytes = (size_t)numKraus * dk * dk * sizeof(double2);
-            DFSA_REQUIRE(krausBytes <= slabBytes, "too many Kraus operators");
             DFSA_CUDA(cudaMemcpyAsync(dSlab, krausOps, krausBytes, cudaMemcpyHostToDevice, ctx.compute));
             superoperatorKernel<<<ctx.numSMs * 4, 256, 0, ctx.compute>>>(dSlab, numKraus, dk, dGate);
             DFSA_LAUNCH_CHECK();
@@ -685,7 +695,8 @@ static int manyTargImpl(dfsa_state* s, const uint32_t* targets, unsigned numTarg
         for (uint64_t g0 = 0; g0 < numGroups; g0 += chunkGroups) {
             const unsigned cg = (unsigned)std::min<uint64_t>(chunkGroups, numGroups - g0);
             dim3 grid((cg + GEMM_BN - 1) / GEMM_BN, (unsigned)(d / GEMM_BM));
-            manyTargGemmKernel<<<grid, GEMM_THREADS, 0, ctx.compute>>>(amps, dSlab, g0, cg, sortedT, dOff, (unsigned)d, dFrag);
+            if (targets[0] == 0) manyTargGemmKernel<true><<<grid, GEMM_THREADS, 0, ctx.compute>>>(amps, dSlab, g0, cg, sortedT, dOff, (unsigned)d, dFrag);
+            else manyTargGemmKernel<false><<<grid, GEMM_THREADS, 0, ctx.compute>>>(amps, dSlab, g0, cg, sortedT, dOff, (unsigned)d, dFrag);
             DFSA_LAUNCH_CHECK();
             // results home: amps[group | row bits] = slab[row][group]
             const uint64_t* offs = dOff;
