@@ -76,6 +76,7 @@ struct CommState {
     int         fusedOverride = -1;                 // dfsa_comm_set_fused: -1 = environment decides
     void*       shmDev = nullptr;                   // device address of the shared page (cudaHostRegister)
     bool        shmRegistered = false;
+    cudaEvent_t evXStart = nullptr, evXStop = nullptr;   // around the kernel(s) of the last fused exchange step (measurement)
     uint64_t    myTicket = 0;                       // last ticket this rank posted on its compute stream
     uint64_t    expecSeq = 0;
 };
@@ -686,6 +687,18 @@ extern "C" int dfsa_comm_set_fused(int mode) {
     g_comm.fusedOverride = mode;
     return DFSA_OK;
 }
+// device time of the kernel of the most recent fused exchange step on this rank (between the peers' READY and this rank's
+// DONE, so waiting for a late partner is not in it). Synchronises on that kernel. -1 if there was none.
+extern "C" int dfsa_comm_last_exchange_ms(double* ms) {
+    DFSA_REQUIRE(ms, "null argument");
+    *ms = -1.0;
+    if (!g_comm.evXStop) return DFSA_OK;
+    float f = 0.f;
+    DFSA_CUDA(cudaEventSynchronize(g_comm.evXStop));
+    DFSA_CUDA(cudaEventElapsedTime(&f, g_comm.evXStart, g_comm.evXStop));
+    *ms = f;
+    return DFSA_OK;
+}
 extern "C" int dfsa_comm_fused_active(void) { return fusedAvailable() ? (g_comm.signals ? 2 : 1) : 0; }
 
 // One fused step with the ranks in `peers` (the partner of a pairwise op; the 2^k - 1 other members of a relocation or
@@ -713,7 +726,10 @@ static int fusedGroupExchange(dfsa_state* s, const int* peers, int n, Launch lau
         DFSA_TRY(exchangeTickets(peers, n, ready, s->allocId[DFSA_AMPS], theirs, theirSlots));
         for (int i = 0; i < n; i++) DFSA_TRY(awaitTicket(peers[i], theirs[i]));
         for (int i = 0; i < n; i++) { double2* p; DFSA_TRY(peerPointer(peers[i], theirSlots[i], &p)); remote[i] = p; }
+        if (!g_comm.evXStart) { DFSA_CUDA(cudaEventCreate(&g_comm.evXStart)); DFSA_CUDA(cudaEventCreate(&g_comm.evXStop)); }
+        DFSA_CUDA(cudaEventRecord(g_comm.evXStart, c.compute));      // after the waits: the kernel's own time, without rank skew
         DFSA_TRY(launch(remote));
+        DFSA_CUDA(cudaEventRecord(g_comm.evXStop, c.compute));
         uint64_t done = 0;
         DFSA_TRY(postTicket(&done));                               // == ready + 1 on every rank: nothing else posts in between
         for (int i = 0; i < n; i++) DFSA_TRY(awaitTicket(peers[i], theirs[i] + 1));

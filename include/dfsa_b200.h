@@ -68,6 +68,9 @@ const char* dfsa_comm_transport(void);             /* "single", "nccl" or "ipc" 
  * other rank's shards). dfsa_comm_fused_active(): 0 staged, 1 fused with host synchronisation, 2 fused and stream-ordered. */
 int dfsa_comm_set_fused(int mode);
 int dfsa_comm_fused_active(void);
+/* Measurement: device time of the kernel of this rank's most recent fused exchange step (stream-ordered mode), taken after the
+ * partners' READY signals -- i.e. without the time spent waiting for a rank that arrives late. -1 if none. Synchronises. */
+int dfsa_comm_last_exchange_ms(double* ms);
 void* dfsa_stream_compute(void);                   /* cudaStream_t the kernels run on (for CUDA-event timing) */
 
 /* ---- measurement helpers (no counterpart in the reference, which times with std::chrono around comm_synch, main.cpp:28-35) */

@@ -34,7 +34,8 @@ def main():
     A = st.num_amps_per_node
     top = nq - 1
 
-    def timed(fn, reps=3):
+    def timed(fn, reps=3, kernel_only=False):
+        """best-of-reps device time of fn (max over ranks); kernel_only: the fused exchange kernel alone, as the library timed it"""
         best = None
         for r in range(reps + 1):
             e0, e1 = job.event(), job.event()
@@ -43,7 +44,12 @@ def main():
             fn()
             job.record(e1)
             job.barrier()
-            t = job.max_over_ranks(job.elapsed(e0, e1))
+            t = job.elapsed(e0, e1)
+            if kernel_only:
+                ms = C.c_double()
+                job.check(job.lib.dfsa_comm_last_exchange_ms(C.byref(ms)))
+                t = ms.value
+            t = job.max_over_ranks(t)
             if r > 0:
                 best = t if best is None else min(best, t)
         return best
