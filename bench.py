@@ -634,27 +634,41 @@ def run_product(args, world, rank, local_rank):
         run_step()
     job.barrier()
 
-    # ---- timed region: K steps, device-timed, per-gate events inside for the roofline of the dominant kernel
-    per_gate = [[(job.event(), job.event()) for _ in ops] for _ in range(args.steps)]
-    e0, e1 = job.event(), job.event()
+    # ---- timed region (the product's default behaviour): K steps, device-timed. With gate fusion on (default) the library defers
+    #      the one-target gates of a step and launches them as a few shared passes over HBM when the step is flushed.
+    fusion = dfsa.gate_fusion_enabled()
+
+    def timed_steps(steps, per_gate=None):
+        e0, e1 = job.event(), job.event()
+        launches0 = lib.dfsa_launch_count()
+        job.barrier()
+        job.record(e0)
+        for s_ in range(steps):
+            run_step(per_gate[s_] if per_gate else None)
+            st.flush()                                       # a step ends with its gates launched (no fusing across steps)
+        job.record(e1)
+        job.barrier()
+        return job.max_over_ranks(job.elapsed(e0, e1)), int(lib.dfsa_launch_count() - launches0)
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = lib.dfsa_launch_count()
-    job.barrier()
-    job.record(e0)
-    for s in range(args.steps):
-        run_step(per_gate[s])
-    job.record(e1)
-    job.barrier()
-    launches = int(lib.dfsa_launch_count() - launches0)
+    total_ms, launches = timed_steps(args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = job.max_over_ranks(job.elapsed(e0, e1))
+    step_ms = total_ms / args.steps
+    value = gates_equiv(len(ops), nq, step_ms * 1e-3)
 
-    # dominant kernel: local oneTargGate (ctrlOneTarg kernel with no controls), 32*A bytes per launch
-    one_ms = [job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(args.steps) for i, op in enumerate(ops) if op[0] == "sv_oneTargGate" and op[1] < L]
+    # ---- the same sweep gate by gate (fusion off): one kernel per gate, per-gate events -> the per-gate roofline numbers
+    dfsa.set_gate_fusion(False)
+    pg_steps = max(2, min(args.steps, 5))
+    run_step()
+    per_gate = [[(job.event(), job.event()) for _ in ops] for _ in range(pg_steps)]
+    pg_total_ms, pg_launches = timed_steps(pg_steps, per_gate)
+    pg_step_ms = pg_total_ms / pg_steps
+    # dominant per-gate kernel: local oneTargGate (ctrlOneTarg kernel with no controls), 32*A bytes per launch
+    one_ms = [job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(pg_steps) for i, op in enumerate(ops) if op[0] == "sv_oneTargGate" and op[1] < L]
     one_avg_ms = float(np.mean(one_ms))
-    gate_ms = [job.max_over_ranks(float(np.mean([job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(args.steps)]))) for i in range(len(ops))] if (args.per_gate or world > 1) else None
+    gate_ms = [job.max_over_ranks(float(np.mean([job.elapsed(per_gate[s][i][0], per_gate[s][i][1]) for s in range(pg_steps)]))) for i in range(len(ops))] if (args.per_gate or world > 1) else None
     exchange_summary = None
     if gate_ms is not None:
         ex = [(i, op) for i, op in enumerate(ops) if any(c[1] > 0 for c in op_cost(op, "sv", nq, k))]
@@ -677,11 +691,57 @@ def run_product(args, world, rank, local_rank):
                 what = "%s t=%d%s" % (op[0][3:], op[1] if op[0] == "sv_oneTargGate" else op[2], "" if op[0] == "sv_oneTargGate" else " ctrls=%s" % (op[1],))
                 b = bound_ms(op_cost(op, "sv", nq, k), peaks)
                 sys.stderr.write("gate %2d %-48s %9.3f ms  (roofline %8.3f ms, %5.1f%%)\n" % (i, what, gate_ms[i], b, 100 * b / gate_ms[i]))
-    achieved = 32.0 * shard_amps / (one_avg_ms * 1e-3) / 1e9
+    pg_achieved = 32.0 * shard_amps / (one_avg_ms * 1e-3) / 1e9
     traffic = ncu_traffic()
     bound_step = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op in ops)
-    step_ms = total_ms / args.steps
-    value = gates_equiv(len(ops), nq, step_ms * 1e-3)
+    per_gate_mode = {
+        "what": "DFSA_FUSE_GATES=0: every gate is its own kernel and its own sweep over the shard, as in the reference",
+        "value": gates_equiv(len(ops), nq, pg_step_ms * 1e-3), "ms_per_step": pg_step_ms, "steps": pg_steps, "gates_per_s_actual": len(ops) / (pg_step_ms * 1e-3),
+        "gpu_launches": pg_launches,
+        "step_roofline": {"bound_ms": bound_step, "frac": bound_step / pg_step_ms,
+                          "how": "sum over gates of max(HBM bytes / HBM peak, NVLink bytes per direction / measured NVLink rate): the bound of any one-sweep-per-gate implementation"},
+        "roofline": {"bound": "hbm", "kernel": "streamKernel<ctrlOneTarg> (local oneTargGate)", "achieved": pg_achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": pg_achieved / hbm_peak, "algorithmic_bytes_per_launch": 32 * shard_amps, "avg_launch_ms": one_avg_ms, "launches_timed": len(one_ms),
+                     "traffic": (traffic["dram_over_algorithmic"] * 32 * shard_amps) if traffic else None,
+                     "traffic_note": ("NOT measured in this run: " + traffic.get("note", "")) if traffic else None}}
+    dfsa.set_gate_fusion(fusion)
+
+    # roofline of the dominant kernel of the timed region
+    if fusion:
+        # fused passes: what must cross HBM for a pass is one read and one write of the shard, however many gates it carries;
+        # the FP64 work of its gates (16 FMA per touched pair) is the other bound
+        local_ops = [op for op in ops if all(c[1] == 0 for c in op_cost(op, "sv", nq, k))]
+        class G(C.Structure):
+            _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
+        arr = (G * len(local_ops))()
+        pairs = 0.0
+        for i, op in enumerate(local_ops):
+            ctrls = [] if op[0] == "sv_oneTargGate" else op[1]
+            arr[i].target = op[1] if op[0] == "sv_oneTargGate" else op[2]
+            arr[i].ctrlMask = sum(1 << c for c in ctrls if c < L)
+            pairs += (shard_amps / 2.0) / (1 << len(ctrls))     # averaged over ranks for rank-bit controls
+        n = len(local_ops)
+        nb = C.c_uint()
+        scratch = [(C.c_uint32 * max(1, 11 * n))() for _ in range(5)]
+        check(lib.dfsa_plan_gateSequence(arr, n, L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
+        passes = nb.value
+        exch_ms = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op in ops if op not in local_ops)
+        local_ms = max(step_ms - exch_ms, 1e-9)            # exchange gates at their bound: a lower bound on what the passes took
+        achieved = 32.0 * shard_amps * passes / (local_ms * 1e-3) / 1e9
+        fp64_ms = pairs * 32.0 / (FP64_PEAK_TFLOPS * 1e12) * 1e3
+        roofline = {"bound": "hbm", "kernel": "fusedGateTileKernel (all one-target gates of a pass applied to 32 KiB tiles in shared memory)", "achieved": achieved,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
+                    "avg_launch_ms": local_ms / passes, "passes_per_step": passes, "gates_in_passes": n,
+                    "fp64_bound_ms_per_step": fp64_ms, "hbm_bound_ms_per_step": 32.0 * shard_amps * passes / (hbm_peak * 1e9) * 1e3,
+                    "note": "algorithmic bytes of a fused pass = one read + one write of the shard (32*A), whatever the number of gates it carries; "
+                            "time per launch = (step time - exchange gates at their roofline) / passes, measured with CUDA events around whole steps",
+                    "traffic": None}
+        step_roofline = {"bound_ms": max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms, "frac": (max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms) / step_ms,
+                         "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + exchange gates at their NVLink bound",
+                         "speedup_over_per_gate_roofline": bound_step / step_ms}
+    else:
+        roofline = dict(per_gate_mode["roofline"], peak_source=peak_src)
+        step_roofline = per_gate_mode["step_roofline"]
 
     # ---- BASELINE config 3 (state-vector circuit; its own state -- the sweep state is needed again for e2e at the same size)
     configs = {}
@@ -745,16 +805,11 @@ def run_product(args, world, rank, local_rank):
                        "qubits": nq, "gates_per_step": len(ops), "shard_GiB_per_gpu": shard_bytes / 2 ** 30,
                        "parallelism": "%d-way state sharding (top %d qubits = rank)" % (world, k), "transport": lib.dfsa_comm_transport().decode(),
                        "exchange": {0: "staged", 1: "fused, host-synchronised", 2: "fused, stream-ordered"}[lib.dfsa_comm_fused_active()] if world > 1 else "none",
+                       "gate_fusion": "one-target gates deferred and applied in shared passes over HBM (DFSA_FUSE_GATES=0 turns it off)" if fusion else "off",
                        "l2": "inputs >> L2 (every gate streams the whole %d GiB shard)" % (shard_bytes >> 30)},
             "gates_per_s_actual": len(ops) / (step_ms * 1e-3),
             "amp_updates_per_s": len(ops) * float(1 << nq) / (step_ms * 1e-3),
-            "step_roofline": {"bound_ms": bound_step, "frac": bound_step / step_ms,
-                              "how": "sum over gates of max(HBM bytes / HBM peak, NVLink bytes per direction / measured NVLink rate)"},
-            "roofline": {"bound": "hbm", "kernel": "streamKernel<ctrlOneTarg> (local oneTargGate)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
-                         "avg_launch_ms": one_avg_ms, "launches_timed": len(one_ms),
-                         "traffic": (traffic["dram_over_algorithmic"] * 32 * shard_amps) if traffic else None,
-                         "traffic_note": ("NOT measured in this run: " + traffic.get("note", "")) if traffic else None},
+            "gate_fusion": fusion, "step_roofline": step_roofline, "roofline": roofline, "per_gate_mode": per_gate_mode,
             "peaks": peaks, "nvlink": nvlink, "exchange_gates": exchange_summary,
             "parity": parity, "selfcheck": selfcheck, "configs": configs,
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "norm2_after": norm2,

@@ -19,7 +19,9 @@ from .api import (  # noqa: F401
     comm_size,
     comm_synch,
     device_lib,
+    gate_fusion_enabled,
     host_lib,
+    set_gate_fusion,
 )
 
 build = _build.build

@@ -91,7 +91,20 @@ def comm_size():
 
 
 def comm_synch():
-    check(device_lib().dfsa_comm_barrier())
+    """comm_synch() of the host API: launches every state's deferred gates, then device sync + inter-rank barrier."""
+    if _host is not None:
+        _host.dfsa_host_comm_synch()
+    else:
+        check(device_lib().dfsa_comm_barrier())
+
+
+def set_gate_fusion(on):
+    """Deferred, fused one-target gates on (default, DFSA_FUSE_GATES) or off (one kernel per gate, launched at once)."""
+    host_lib().dfsa_host_setGateFusion(int(bool(on)))
+
+
+def gate_fusion_enabled():
+    return bool(host_lib().dfsa_host_gateFusionEnabled())
 
 
 def _u32(xs):
@@ -153,6 +166,13 @@ class DeviceState:
 
     def restore_layout(self):
         host_lib().dfsa_host_state_restoreLayout(self.p)
+
+    def flush(self):
+        """Launch the one-target gates this state has deferred (host/states.hpp gateQueue)."""
+        host_lib().dfsa_host_state_flushGates(self.p)
+
+    def pending_gates(self):
+        return int(host_lib().dfsa_host_state_pendingGates(self.p))
 
     # ---- state I/O
     def set_amps(self, amps):

@@ -15,7 +15,7 @@ CSRC = os.path.join(PKG, "csrc")
 HOST = os.path.join(PKG, "host")
 INCLUDE = os.path.join(ROOT, "include")
 
-CUDA_SOURCES = ["dfsa_runtime.cu", "dfsa_comm.cu", "dfsa_kernels_sv.cu", "dfsa_kernels_manytarg.cu", "dfsa_kernels_dm.cu"]
+CUDA_SOURCES = ["dfsa_runtime.cu", "dfsa_comm.cu", "dfsa_kernels_sv.cu", "dfsa_kernels_manytarg.cu", "dfsa_kernels_dm.cu", "dfsa_kernels_fused.cu"]
 LIB_DEVICE = os.path.join(PKG, "libdfsa_b200.so")
 LIB_HOST = os.path.join(PKG, "libdfsa_host.so")
 

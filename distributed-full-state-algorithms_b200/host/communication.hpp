@@ -31,11 +31,21 @@ struct DeviceAmpArray {
     Amp* data() const { return reinterpret_cast<Amp*>(dfsa_state_ptr(owner, which)); }   // DEVICE pointer
 };
 
+// Deferred work: a state may hold one-target gates it has not launched yet (states.hpp: gateQueue, fused into shared passes over
+// HBM). comm_synch() -- the reference's "everything before this point has happened" (communication.hpp:44), which is what
+// main.cpp-style timing brackets with -- launches them first; states.hpp installs the hook.
+namespace dfsa_detail {
+inline void (*&flushAllStatesHook())() { static void (*hook)() = nullptr; return hook; }
+}
+
 static inline void comm_init() { DFSA_CHECK(dfsa_comm_init()); }
 static inline void comm_end() { DFSA_CHECK(dfsa_comm_finalize()); }
 static inline Nat comm_getRank() { return Nat(dfsa_comm_rank()); }
 static inline Nat comm_getNumNodes() { return Nat(dfsa_comm_size()); }
-static inline void comm_synch() { DFSA_CHECK(dfsa_comm_barrier()); }
+static inline void comm_synch() {
+    if (dfsa_detail::flushAllStatesHook()) dfsa_detail::flushAllStatesHook()();
+    DFSA_CHECK(dfsa_comm_barrier());
+}
 
 static inline void comm_exchangeArrays(DeviceAmpArray& toSend, Index toSendStartInd, DeviceAmpArray& toReceive, Index toReceiveStartInd,
                                        Index numAmpsToExchange, Nat pairRank) {

@@ -53,6 +53,11 @@ void dfsa_host_state_layout(void* h, unsigned* out) { for (std::size_t q = 0; q 
 void dfsa_host_state_restoreLayout(void* h) { sv(h).restoreLayout(); }
 void dfsa_host_state_resetLayout(void* h) { sv(h).resetLayout(); }
 int dfsa_host_lazyLayoutEnabled() { return dfsa_detail::lazyLayoutEnabled() ? 1 : 0; }
+// deferred one-target gates (states.hpp gateQueue): launch what is pending / how many are pending / switch deferral on and off
+void dfsa_host_state_flushGates(void* h) { sv(h).flushGates(); }
+unsigned dfsa_host_state_pendingGates(void* h) { return unsigned(sv(h).gateQueue.size()); }
+int dfsa_host_gateFusionEnabled() { return StateVector::gateFusionEnabled() ? 1 : 0; }
+void dfsa_host_setGateFusion(int on) { StateVector::flushAllStates(); StateVector::gateFusionEnabled() = (on != 0); }
 double dfsa_host_state_getNorm2(void* h) { return sv(h).getNorm2(); }
 
 // ---- state-vector API (distributed_statevector.hpp)

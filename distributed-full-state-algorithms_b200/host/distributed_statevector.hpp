@@ -68,8 +68,25 @@ inline PauliPlan planPauli(Nat rank, Nat L, const NatArray& targets, const NatAr
 }
 }  // namespace dfsa_detail
 
+// oneTargGate / manyCtrlOneTargGate whose target sits on a suffix bit: deferred (states.hpp gateQueue) so that runs of such gates
+// share passes over HBM; `controls` and `target` are index bits. Controls on rank bits stay in the mask: the library drops the
+// gate on ranks that fail them (reference :92-93).
+namespace dfsa_detail {
+inline void enqueueOneTarg(StateVector& psi, const NatArray& controls, Nat target, const AmpMatrix& gate) {
+    dfsa_gate1 g;
+    const std::vector<double> flat = dfsaFlatten(gate);
+    for (int i = 0; i < 8; i++) g.matrix[i] = flat[i];
+    g.ctrlMask = getBitMask(controls);
+    g.target = target;
+    g.reserved = 0;
+    psi.gateQueue.push_back(g);
+    if (psi.gateQueue.size() >= 256) psi.flushGates();
+}
+}  // namespace dfsa_detail
+
 // A 2x2 gate on a prefix qubit mixes this shard with the partner's: amps = g[b][b]*amps + g[b][!b]*partner
 static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMatrix& gate) {
+    psi.flushGates();
     const Nat rankTarget = target - Nat(psi.logNumAmpsPerNode);
     const Nat pairRank = Nat(flipBit(psi.rank, rankTarget));
     const Nat bit = getBit(psi.rank, rankTarget);
@@ -83,6 +100,7 @@ static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMat
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
     target = psi.where[target];                               // the index bit that holds the qubit (layout.hpp)
+    if (target < psi.logNumAmpsPerNode && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, {}, target, gate); return; }
     if (target < psi.logNumAmpsPerNode) local_statevector_oneTargGate(psi, target, gate);
     else dfsa_prefixOneTarg(psi, target, gate);
 }
@@ -91,6 +109,8 @@ static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi,
     const Nat L = Nat(psi.logNumAmpsPerNode);
     controls = psi.physical(controls);
     target = psi.where[target];
+    if (target < L && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, controls, target, gate); return; }
+    psi.flushGates();
     NatArray suffixCtrls;
     const dfsa_detail::ExchangePlan plan = dfsa_detail::planCtrlOneTarg(psi.rank, L, controls, target, &suffixCtrls);
     switch (plan.kind) {
@@ -109,6 +129,7 @@ static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi,
 
 static inline void distributed_statevector_swapGate(StateVector& psi, Nat qb1, Nat qb2) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
+    psi.flushGates();
     const Nat p1 = psi.where[qb1], p2 = psi.where[qb2];
     if (p1 >= L && p2 >= L && dfsa_detail::lazyLayoutEnabled()) {
         // both qubits sit on rank bits (reference :120-137 ships whole shards between the ranks whose two bits differ): the
@@ -144,6 +165,7 @@ static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const 
 template <class LocalStep>
 static inline void dfsa_manyTargWithRelocation(StateVector& psi, NatArray targets, LocalStep applyLocal) {
     assert(targets.size() <= psi.logNumAmpsPerNode);
+    psi.flushGates();
     targets = psi.physical(targets);
     const NatArray placed = dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets);
     // the (suffix, prefix) index-bit pairs the reference swaps one after the other before and after the local gate (:213-223);
@@ -170,6 +192,7 @@ static inline void distributed_statevector_manyTargGate(StateVector& psi, NatArr
 
 static inline void distributed_statevector_pauliTensorOrGadget(StateVector& psi, const NatArray& targets, const NatArray& paulis, Amp thisAmpFac, Amp otherAmpFac) {
     assert(targets.size() == paulis.size());
+    psi.flushGates();
     const dfsa_detail::PauliPlan plan = dfsa_detail::planPauli(psi.rank, Nat(psi.logNumAmpsPerNode), psi.physical(targets), paulis);
     if (plan.pairRank == psi.rank) {
         local_statevector_pauliTensorOrGadget_subroutine(psi, plan.numY, plan.maskXY, plan.maskYZ, thisAmpFac, otherAmpFac);
@@ -192,5 +215,6 @@ static inline void distributed_statevector_pauliGadget(StateVector& psi, NatArra
 }
 
 static inline void distributed_statevector_phaseGadget(StateVector& psi, NatArray targets, Real theta) {
+    psi.flushGates();
     local_statevector_phaseGadget(psi, psi.physical(targets), theta);
 }

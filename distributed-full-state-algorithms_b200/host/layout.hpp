@@ -133,6 +133,7 @@ inline RestorePlan planRestore(NatArray where, Nat L) {
 inline void StateVector::noteSwapped(Nat posA, Nat posB) { dfsa_detail::relabel(where, posA, posB); }
 
 inline void StateVector::restoreLayout() {
+    flushGates();                                    // whoever asks for index order is about to look at the amplitudes
     if (layoutIsIdentity()) return;
     const dfsa_detail::RestorePlan plan = dfsa_detail::planRestore(where, Nat(logNumAmpsPerNode));
     if (!plan.relocateSuffix.empty())

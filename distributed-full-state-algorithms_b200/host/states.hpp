@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <numeric>
 #include <utility>
+#include <vector>
 
 #include "bit_maths.hpp"
 #include "communication.hpp"
@@ -43,6 +44,23 @@ public:
     void noteSwapped(Nat posA, Nat posB);
     Nat numDisplacedAcrossShardBoundary() const;
     void restoreLayout();
+
+    // Deferred one-target gates (oneTargGate / manyCtrlOneTargGate on suffix bits, in call order, on INDEX bits): launched
+    // together by flushGates() so that consecutive gates share passes over HBM (dfsa_k_gateSequence) -- before any other
+    // kind of operation on this state, before anything reads it, and at comm_synch(). DFSA_FUSE_GATES=0: never deferred.
+    std::vector<dfsa_gate1> gateQueue;
+    void flushGates() {
+        if (gateQueue.empty()) return;
+        DFSA_CHECK(dfsa_k_gateSequence(handle, gateQueue.data(), Nat(gateQueue.size())));
+        gateQueue.clear();
+    }
+    static bool& gateFusionEnabled() {
+        static bool on = [] { const char* e = std::getenv("DFSA_FUSE_GATES"); return !(e && std::atoi(e) == 0); }();
+        return on;
+    }
+
+    static std::vector<StateVector*>& registry() { static std::vector<StateVector*> live; return live; }      // every live state of this process
+    static void flushAllStates() { for (StateVector* s : registry()) if (s->handle) s->flushGates(); }
 
     explicit StateVector(Nat numQubits) { create(false, numQubits); }
     virtual ~StateVector() { release(); }
@@ -89,7 +107,7 @@ public:
         setLocalAmps(mine);
     }
     void setHashAmps(unsigned long long seed) { resetLayout(); DFSA_CHECK(dfsa_state_init_hash(handle, seed)); }
-    void resetLayout() { std::iota(where.begin(), where.end(), Nat(0)); }      // the contents are about to be overwritten
+    void resetLayout() { gateQueue.clear(); std::iota(where.begin(), where.end(), Nat(0)); }      // the contents are about to be overwritten
     void printAmps() {
         AmpArray all = getAllVecAmps();
         if (rank == 0)
@@ -117,7 +135,7 @@ public:
         }
         return true;
     }
-    Real getNorm2() { double n = 0; DFSA_CHECK(dfsa_state_norm2(handle, &n)); return n; }
+    Real getNorm2() { double n = 0; flushGates(); DFSA_CHECK(dfsa_state_norm2(handle, &n)); return n; }
     // device-resident utilities: nothing is gathered to the host
     void setPlusAmps() { resetLayout(); DFSA_CHECK(dfsa_state_init_plus(handle)); }
     void copyAmpsFrom(StateVector& other) { other.restoreLayout(); resetLayout(); DFSA_CHECK(dfsa_state_copy(handle, other.handle)); }
@@ -146,15 +164,22 @@ protected:
         buffer = DeviceAmpArray{handle, DFSA_BUFFER};
         where.resize(isDensity ? 2 * qubits : qubits);
         resetLayout();
+        registry().push_back(this);
+        dfsa_detail::flushAllStatesHook() = &StateVector::flushAllStates;
     }
+    void unregister() { auto& r = registry(); r.erase(std::remove(r.begin(), r.end(), this), r.end()); }
     void release() {
+        unregister();
+        gateQueue.clear();                                          // nobody can observe their effect any more
         if (handle) DFSA_CHECK(dfsa_state_destroy(handle));
         handle = nullptr;
     }
     void adopt(StateVector& o) {
         rank = o.rank; numNodes = o.numNodes; logNumNodes = o.logNumNodes; numQubits = o.numQubits;
         numAmpsPerNode = o.numAmpsPerNode; logNumAmpsPerNode = o.logNumAmpsPerNode;
-        amps = o.amps; buffer = o.buffer; handle = o.handle; where = std::move(o.where);
+        amps = o.amps; buffer = o.buffer; handle = o.handle; where = std::move(o.where); gateQueue = std::move(o.gateQueue);
+        if (handle) registry().push_back(this);
+        o.unregister();
         o.handle = nullptr; o.amps = DeviceAmpArray(); o.buffer = DeviceAmpArray();
     }
 };

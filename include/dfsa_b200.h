@@ -167,6 +167,15 @@ int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, u
 /* gate pointers are HOST pointers to row-major interleaved complex doubles */
 /* K1+K2: 2x2 gate on `target` where all `ctrls` are 1 (numCtrls may be 0). local_statevector.hpp:14,32 */
 int dfsa_k_ctrlOneTarg(dfsa_state* s, const uint32_t* ctrls, unsigned numCtrls, unsigned target, const double gate[8]);
+/* K1/K2 for a RUN of gates: gates[i] is a 2x2 gate (row-major interleaved complex) on suffix bit `target`, applied where every
+ * bit of ctrlMask (a mask on the GLOBAL index: suffix and rank bits) is 1. Applied in order; bit-identical to numGates calls of
+ * dfsa_k_ctrlOneTarg, but consecutive gates whose targets fit one shared-memory tile (bits 0..3 plus up to seven more) cross HBM
+ * once together. DFSA_FUSE_GATES=0: one pass per gate. dfsa_plan_gateSequence: the batching, host-only (numBatches <= numGates;
+ * tileBitsOut holds 11 bits per batch, groupBitsOut 3 per gate). */
+typedef struct dfsa_gate1 { double matrix[8]; uint64_t ctrlMask; uint32_t target; uint32_t reserved; } dfsa_gate1;
+int dfsa_k_gateSequence(dfsa_state* s, const dfsa_gate1* gates, unsigned numGates);
+int dfsa_plan_gateSequence(const dfsa_gate1* gates, unsigned numGates, unsigned logNumAmps, uint32_t* batchOfGate, uint32_t* groupOfGate,
+                           uint32_t* batchIsTiled, uint32_t* tileBitsOut, uint32_t* groupBitsOut, unsigned* numBatches);
 /* K3: swap of two suffix qubits. local_statevector.hpp:54 */
 int dfsa_k_swap(dfsa_state* s, unsigned qb1, unsigned qb2);
 /* K4: dense 2^t x 2^t gate on suffix targets, gate bit i <-> targets[i]. local_statevector.hpp:72 */

@@ -17,6 +17,7 @@ import torch  # noqa: E402  (events on an external stream)
 def main():
     nq = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     dfsa.comm_init()
+    dfsa.set_gate_fusion(False)      # time every gate as its own kernel
     st = dfsa.DeviceState("sv", nq)
     st.init_hash(1)
     stream = torch.cuda.ExternalStream(dfsa.device_lib().dfsa_stream_compute())

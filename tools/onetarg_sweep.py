@@ -5,6 +5,7 @@ sys.path.insert(0, ROOT)
 dfsa = importlib.import_module("distributed-full-state-algorithms_b200")
 import ctypes as C
 dfsa.comm_init()
+dfsa.set_gate_fusion(False)      # time every gate as its own kernel
 lib = dfsa.device_lib(); check = dfsa.api.check
 nq = int(sys.argv[1]) if len(sys.argv) > 1 else 31
 st = dfsa.DeviceState("sv", nq); st.init_hash(1)
