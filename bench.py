@@ -45,6 +45,9 @@ SEED = 20261017
 FP64_PEAK_TFLOPS = 36.6         # measured on B200: profiles/r01_fp64_peak_b200.jsonl (DFMA 36.6, DMMA 37.0)
 NVLINK_FALLBACK_GBS = 770.0     # per direction, B200_PROFILING.md; replaced by the in-run measurement when N > 1
 PARITY_TOL = 1e-12
+# ops that address amplitudes by index bit and therefore restore a lazily relabelled layout first (host/layout.hpp)
+INDEX_ADDRESSED_OPS = ("dm_oneQubitDephasing", "dm_twoQubitDephasing", "dm_oneQubitDepolarising", "dm_twoQubitDepolarising", "dm_damping",
+                       "dm_expecPauliString", "dm_partialTrace")
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -138,8 +141,7 @@ def op_cost(op, kind, nq, k, where=None, lazy=False):
     L = bits - k
     A = float(1 << L)
     if name == "layout_restore":
-        npre = op[1]
-        return [(32 * A, (1.0 - 0.5 ** npre) * 16 * A, 0.0)] if npre else []
+        return restore_cost(op[1], kind, nq, k)
     if where is not None and name.startswith("sv_"):
         m = lambda qs: [where[q] for q in qs]           # noqa: E731
         if name == "sv_oneTargGate":
@@ -205,7 +207,7 @@ def op_cost(op, kind, nq, k, where=None, lazy=False):
         a, b = sorted(op[1:3])
         return [(32 * A, 0, 0)] if b < thr else ([(32 * A + 4 * A, 2 * A, 0)] if a < thr else [(32 * A + 8 * A, 8 * A, 0)])
     if name == "dm_damping":
-        return [(32 * A, 0, 0)] if op[1] < thr else [(40 * A, 8 * A, 0)]
+        return [(32 * A, 0, 0)] if op[1] < thr else [(40 * A, 0, 0, 8 * A)]      # population flows one way only
     if name == "dm_expecPauliString":
         T = len(op[1])
         return [(min(16 * A, 32.0 * T * (1 << nq) / (1 << k)), 0, 0)]
@@ -218,8 +220,26 @@ def op_cost(op, kind, nq, k, where=None, lazy=False):
 
 
 def bound_ms(cost, peaks):
-    """sum over the phases of one call of max(HBM time, NVLink time, FP64 time)."""
-    return sum(max(c[0] / (peaks["hbm_GBs"] * 1e9), c[1] / (peaks["nvlink_GBs_per_dir"] * 1e9), c[2] / (peaks["fp64_TFLOPs"] * 1e12)) for c in cost) * 1e3
+    """sum over the phases of one call of max(HBM time, NVLink time, FP64 time). A phase is (hbm bytes, NVLink bytes per direction
+    with both directions busy, flop[, NVLink bytes of a ONE-WAY transfer]); the two NVLink rates are measured separately."""
+    one_way = peaks.get("nvlink_one_way_GBs", peaks["nvlink_GBs_per_dir"])
+    return sum(max(c[0] / (peaks["hbm_GBs"] * 1e9), c[1] / (peaks["nvlink_GBs_per_dir"] * 1e9), c[2] / (peaks["fp64_TFLOPs"] * 1e12),
+                   (c[3] if len(c) > 3 else 0.0) / (one_way * 1e9)) for c in cost) * 1e3
+
+
+def restore_cost(steps, kind, nq, k):
+    """cost of StateVector::restoreLayout for the plan `steps` = [(0 = relocation pair | 1 = index-bit swap, a, b), ...]"""
+    L = (nq if kind == "sv" else 2 * nq) - k
+    A = float(1 << L)
+    out = []
+    npairs = sum(1 for s in steps if s[0] == 0)
+    if npairs:
+        out.append((32 * A, (1.0 - 0.5 ** npairs) * 16 * A, 0.0))
+    for s in steps:
+        if s[0] == 1:
+            a, b = sorted(s[1:3])
+            out.append((16 * A, 0.0, 0.0) if b < L else ((24 * A, 8 * A, 0.0) if a < L else (32 * A, 16 * A, 0.0)))
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ helpers
@@ -429,7 +449,7 @@ def measure_nvlink(job, st):
         return None
     out = {}
     shard_bytes = 16.0 * st.num_amps_per_node
-    for mode, label in ((0, "kernel_remote_loads"), (1, "copy_engine")):
+    for mode, label in ((0, "kernel_remote_loads"), (1, "copy_engine"), (2, "kernel_remote_loads_one_way")):
         best = None
         for rep in range(3):
             ms = C.c_double()
@@ -538,8 +558,21 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
         evs = [(job.event(), job.event()) for _ in range(len(ops) + 1)]
         costs = []
         job.barrier()
+        def restore_steps():
+            """what restoreLayout would do now (host/layout.hpp planRestore)"""
+            where = st.layout()
+            n = len(where)
+            out = (C.c_uint * (9 * n))()
+            hl = job.dfsa.host_lib()
+            hl.dfsa_host_plan_restoreLayout.restype = C.c_uint
+            cnt = hl.dfsa_host_plan_restoreLayout((C.c_uint * n)(*where), n, (nq if kind == "sv" else 2 * nq) - k, out)
+            return [(out[3 * i], out[3 * i + 1], out[3 * i + 2]) for i in range(cnt)]
+
         for (e0, e1), op in zip(evs, ops):
-            costs.append(op_cost(op, kind, nq, k, where=st.layout(), lazy=lazy))     # what the gate needs given where its qubits sit now
+            cost = op_cost(op, kind, nq, k, where=st.layout(), lazy=lazy)            # what the gate needs given where its qubits sit now
+            if op[0] in INDEX_ADDRESSED_OPS:
+                cost = restore_cost(restore_steps(), kind, nq, k) + cost             # these ops put a lazily relabelled layout back first
+            costs.append(cost)
             job.record(e0)
             r = cases.apply(st, op)
             job.record(e1)
@@ -549,9 +582,9 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
                 st = job.dfsa.DeviceState(kind, nq)
                 st.init_hash(SEED)
         # the deferred part of the pass: put the relocated qubits back (nothing to do unless a dense gate left some displaced)
-        L = (nq if kind == "sv" else 2 * nq) - k
-        displaced = sum(1 for q, w in enumerate(st.layout()) if q >= L and w < L)
-        restore_op = ("layout_restore", displaced)
+        steps = restore_steps()
+        displaced = len(steps)
+        restore_op = ("layout_restore", steps)
         costs.append(op_cost(restore_op, kind, nq, k))
         job.record(evs[-1][0])
         st.restore_layout()
@@ -609,6 +642,7 @@ def run_product(args, world, rank, local_rank):
     nvlink = measure_nvlink(job, st)
     peaks = {"hbm_GBs": hbm_peak, "fp64_TFLOPs": FP64_PEAK_TFLOPS,
              "nvlink_GBs_per_dir": nvlink["kernel_remote_loads_GBs_per_dir"] if nvlink else NVLINK_FALLBACK_GBS,
+             "nvlink_one_way_GBs": nvlink["kernel_remote_loads_one_way_GBs_per_dir"] if nvlink else NVLINK_FALLBACK_GBS,
              "nvlink_source": "measured in this run (kernel remote loads, all pairs at once)" if nvlink else "not used at 1 GPU (fallback %g)" % NVLINK_FALLBACK_GBS,
              "hbm_source": peak_src, "fp64_source": "profiles/r01_fp64_peak_b200.jsonl (DFMA 36.6, DMMA 37.0 TFLOP/s)"}
 

@@ -885,11 +885,12 @@ extern "C" int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, d
 // Link microbenchmark (the NVLink line of the roofline must be measured on the box, not assumed): every rank pulls
 // its partner's whole shard into its own exchange buffer, all pairs at once, both directions -- the traffic pattern of a
 // prefix gate without the arithmetic. mode 0: remote loads from a kernel (what the fused kernels do), mode 1: copy engine
-// (cudaMemcpyAsync from the peer mapping). *ms = device time of this rank's pull (CUDA events on the compute stream).
+// (cudaMemcpyAsync from the peer mapping), mode 2: remote loads in ONE direction only (even ranks pull, odd ranks serve -- the
+// traffic of the one-way damping transfer). *ms = device time of this rank's pull (CUDA events on the compute stream).
 int dfsaLaunchPull(dfsa_state* s, const double2* remote);
 extern "C" int dfsa_xk_measure_link(dfsa_state* s, int pairRank, int mode, double* ms) {
     DFSA_TRY(dfsaEnsureDevice());
-    DFSA_REQUIRE(s && ms && (mode == 0 || mode == 1), "bad argument");
+    DFSA_REQUIRE(s && ms && mode >= 0 && mode <= 2, "bad argument");
     DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank));
     DFSA_REQUIRE(fusedAvailable(), "peer shards are not mapped (staged transport)");
     DfsaContext& c = dfsaCtx();
@@ -900,7 +901,8 @@ extern "C" int dfsa_xk_measure_link(dfsa_state* s, int pairRank, int mode, doubl
     int rc = fusedGroupExchange(s, &pairRank, 1,
         [&](const double2* const* remote) -> int {
             DFSA_CUDA(cudaEventRecord(e0, c.compute));
-            if (mode == 0) DFSA_TRY(dfsaLaunchPull(s, remote[0]));
+            if (mode == 2 && (c.rank & 1)) { /* one-way: odd ranks only serve */ }
+            else if (mode == 0 || mode == 2) DFSA_TRY(dfsaLaunchPull(s, remote[0]));
             else DFSA_CUDA(cudaMemcpyAsync(s->arr[DFSA_BUFFER], remote[0], bytes, cudaMemcpyDeviceToDevice, c.compute));
             DFSA_CUDA(cudaEventRecord(e1, c.compute));
             return (int)DFSA_OK;

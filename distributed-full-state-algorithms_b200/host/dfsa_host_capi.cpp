@@ -137,6 +137,11 @@ void dfsa_host_plan_manyTarg(unsigned L, const unsigned* targets, unsigned n, un
     NatArray placed = dfsa_planManyTargRelocation(L, toNats(targets, n));
     for (unsigned i = 0; i < n; i++) placedOut[i] = placed[i];
 }
+// lazy layout: where the (index-bit) targets of a dense gate land, given the current layout
+void dfsa_host_plan_relocationOnLayout(const unsigned* where, unsigned n, unsigned L, const unsigned* targets, unsigned nt, unsigned* placedOut) {
+    NatArray placed = dfsa_planRelocationOnLayout(NatArray(where, where + n), L, toNats(targets, nt));
+    for (unsigned i = 0; i < nt; i++) placedOut[i] = placed[i];
+}
 // lazy layout: the steps that restore index order. out = numSteps x {kind (0 = relocation pair, 1 = index-bit swap), a, b}
 unsigned dfsa_host_plan_restoreLayout(const unsigned* where, unsigned n, unsigned L, unsigned* out) {
     dfsa_detail::RestorePlan plan = dfsa_detail::planRestore(NatArray(where, where + n), L);

@@ -160,6 +160,33 @@ static inline NatArray dfsa_planManyTargRelocation(Nat logNumAmpsPerNode, const 
     return placed;
 }
 
+// The same plan when the layout is not the identity (lazy layout, layout.hpp): `targets` are index bits, and WHICH free suffix
+// bit a prefix target lands on decides how cheap the eventual restore is. In order of preference: (1) the suffix bit that
+// currently holds the qubit whose home is the target's prefix bit -- the swap takes that qubit home; (2) the highest free suffix
+// bit that holds its own qubit -- the swap creates a 2-cycle, which one relocation step undoes; (3) the highest free suffix bit.
+// (Always taking the highest free bit lets a second prefix target evict the first one onto a rank bit: a rank relabelling that
+// costs a full-shard exchange to undo -- config 3 at 8 GPUs spent 60 ms per pass on exactly that.)
+static inline NatArray dfsa_planRelocationOnLayout(const NatArray& where, Nat L, const NatArray& targets) {
+    const Index targetMask = getBitMask(targets);
+    Index used = 0;
+    auto isFree = [&](Nat s) { return s < L && !getBit(targetMask, s) && !getBit(used, s); };
+    NatArray placed;
+    placed.reserve(targets.size());
+    for (Nat t : targets) {
+        if (t < L) { placed.push_back(t); continue; }
+        int choice = -1;
+        if (isFree(where[t])) choice = int(where[t]);                               // (1) logical qubit t sits on a free suffix bit: bring it home
+        for (int s = int(L) - 1; s >= 0 && choice < 0; s--)
+            if (isFree(Nat(s)) && where[Nat(s)] == Nat(s)) choice = s;              // (2) a suffix bit holding its own qubit
+        for (int s = int(L) - 1; s >= 0 && choice < 0; s--)
+            if (isFree(Nat(s))) choice = s;                                         // (3) any free suffix bit
+        assert(choice >= 0);
+        used |= Index(1) << choice;
+        placed.push_back(Nat(choice));
+    }
+    return placed;
+}
+
 // manyTargGate with the local step left open: `applyLocal(placed)` runs the dense-gate kernel on the (all suffix) index bits
 // the targets occupy after relocation. krausMap uses it with a kernel that builds its own superoperator on the device.
 template <class LocalStep>
@@ -167,7 +194,7 @@ static inline void dfsa_manyTargWithRelocation(StateVector& psi, NatArray target
     assert(targets.size() <= psi.logNumAmpsPerNode);
     psi.flushGates();
     targets = psi.physical(targets);
-    const NatArray placed = dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets);
+    const NatArray placed = psi.layoutIsIdentity() ? dfsa_planManyTargRelocation(Nat(psi.logNumAmpsPerNode), targets) : dfsa_planRelocationOnLayout(psi.where, Nat(psi.logNumAmpsPerNode), targets);
     // the (suffix, prefix) index-bit pairs the reference swaps one after the other before and after the local gate (:213-223);
     // the pairs are disjoint, so they commute and go in one relocation step, which is its own inverse
     NatArray landing, prefix;

@@ -158,7 +158,8 @@ int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls, unsigned 
 int dfsa_xk_depol2Pair(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit, double prob, int corrected, int pairRank);
 int dfsa_xk_depol2Quad(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit0, unsigned bit1, double prob, int corrected, int pairRank0, int pairRank1);
 /* Measurement only: this rank pulls pairRank's whole shard into its exchange buffer (all pairs at once, both directions);
- * mode 0 = remote loads from a kernel, 1 = copy engine. *ms = device time. NVLink GB/s per direction = 16 * A / ms. */
+ * mode 0 = remote loads from a kernel, 1 = copy engine, 2 = remote loads, even ranks only (one-way traffic). *ms = device time.
+ * NVLink GB/s per direction = 16 * A / ms. */
 int dfsa_xk_measure_link(dfsa_state* s, int pairRank, int mode, double* ms);
 int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, uint64_t maskYZ, unsigned numY,
                                  const double f[2], const double g[2], int exact);

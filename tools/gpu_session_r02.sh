@@ -29,6 +29,14 @@ case $MODE in
     DFSA_NP=4 timeout 500 compute-sanitizer --tool memcheck --target-processes all python tools/sanitize_cases.py > $OUT/${TAG}_sanitizer_memcheck_np4.txt 2>&1; tail -n 3 $OUT/${TAG}_sanitizer_memcheck_np4.txt
     timeout 600 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"; tail -n 3 $OUT/${TAG}_bench_n1.err; cat $OUT/${TAG}_bench_n1.json
     ;;
+  fused)
+    timeout 900 python -m pytest tests -m gpu -q --durations=10 --maxfail=10 > $OUT/${TAG}_pytest.log 2>&1; tail -n 16 $OUT/${TAG}_pytest.log
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:fusedGateTile -c 2 -f -o $OUT/${TAG}_fused python tools/prof_fused.py 28 > $OUT/${TAG}_ncu_fused.log 2>&1
+    ncu -i $OUT/${TAG}_fused.ncu-rep --page raw --csv > $OUT/${TAG}_fused_raw.csv 2>> $OUT/${TAG}_ncu_fused.log
+    ncu -i $OUT/${TAG}_fused.ncu-rep --page source --csv > $OUT/${TAG}_fused_source.csv 2>> $OUT/${TAG}_ncu_fused.log
+    tail -n 2 $OUT/${TAG}_ncu_fused.log
+    timeout 700 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"; tail -n 3 $OUT/${TAG}_bench_n1.err; cat $OUT/${TAG}_bench_n1.json
+    ;;
   link)
     NP=${NP:-2}
     for f in ${INFLIGHTS:-2048 4096 8192 16384}; do
