@@ -744,7 +744,8 @@ def run_product(args, world, rank, local_rank):
     if fusion:
         # fused passes: what must cross HBM for a pass is one read and one write of the shard, however many gates it carries;
         # the FP64 work of its gates (16 FMA per touched pair) is the other bound
-        local_ops = [op for op in ops if all(c[1] == 0 for c in op_cost(op, "sv", nq, k))]
+        is_local = [all(c[1] == 0 for c in op_cost(op, "sv", nq, k)) for op in ops]
+        local_ops = [op for op, loc in zip(ops, is_local) if loc]
         class G(C.Structure):
             _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
         arr = (G * len(local_ops))()
@@ -759,7 +760,7 @@ def run_product(args, world, rank, local_rank):
         scratch = [(C.c_uint32 * max(1, 11 * n))() for _ in range(5)]
         check(lib.dfsa_plan_gateSequence(arr, n, L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
         passes = nb.value
-        exch_ms = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op in ops if op not in local_ops)
+        exch_ms = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op, loc in zip(ops, is_local) if not loc)
         local_ms = max(step_ms - exch_ms, 1e-9)            # exchange gates at their bound: a lower bound on what the passes took
         achieved = 32.0 * shard_amps * passes / (local_ms * 1e-3) / 1e9
         fp64_ms = pairs * 32.0 / (FP64_PEAK_TFLOPS * 1e12) * 1e3

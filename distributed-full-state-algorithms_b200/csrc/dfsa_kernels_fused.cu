@@ -39,7 +39,8 @@ struct FusedGroup { uint32_t firstGate, numGates, r0, r1, r2, pad; };   // r0 < 
 __device__ __forceinline__ unsigned swz(unsigned e) { return e ^ (((e >> 3) ^ (e >> 6)) & 7u); }
 
 template <unsigned RPOS>
-__device__ __forceinline__ void applyInRegisters(double2 (&v)[8], const FusedGate& g, unsigned elemBase, unsigned b0, unsigned b1, unsigned b2) {
+__device__ __forceinline__ void applyInRegisters(double2 (&v)[8], const FusedGate& gs, unsigned elemBase, unsigned b0, unsigned b1, unsigned b2) {
+    struct { double2 m00, m01, m10, m11; unsigned ctrlTile; } g = {gs.m00, gs.m01, gs.m10, gs.m11, gs.ctrlTile};    // shared -> registers, once per gate
 #pragma unroll
     for (unsigned p = 0; p < 4; p++) {
         // pair p: the two other register bits take the values of p's bits; i0 has the target bit clear
@@ -55,28 +56,47 @@ __device__ __forceinline__ void applyInRegisters(double2 (&v)[8], const FusedGat
     }
 }
 
+// Shared memory per block: two tile slabs (the next tile streams in with cp.async while the current one is being worked on)
+// and the pass's gate / group descriptors (read as warp-wide broadcasts: the first version fetched them from global memory
+// per gate and per thread and spent a third of its stall samples waiting for those loads -- profiles/r02_ncu_fused.txt).
+constexpr unsigned FT_SLAB_BYTES = FT_AMPS * sizeof(double2);
+constexpr unsigned FT_DESC_BYTES = FT_MAX_GATES * (sizeof(FusedGate) + sizeof(FusedGroup));
+constexpr unsigned FT_SMEM_BYTES = 2 * FT_SLAB_BYTES + FT_DESC_BYTES;
+
 __global__ void __launch_bounds__(FT_THREADS, 3)
-fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const FusedGate* __restrict__ gates, const FusedGroup* __restrict__ groups,
-                    unsigned numGroups, uint64_t rankShift) {
-    __shared__ __align__(16) double2 tile[FT_AMPS];
-    // element e = tid + 256 i: its offset inside a tile's span of the shard
-    uint64_t off[FT_PER_THREAD];
+fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const FusedGate* __restrict__ gatesGlobal, const FusedGroup* __restrict__ groupsGlobal,
+                    unsigned numGates, unsigned numGroups, uint64_t rankShift) {
+    extern __shared__ __align__(16) unsigned char fusedSmem[];
+    auto slab = [&](unsigned which) { return reinterpret_cast<double2*>(fusedSmem + which * FT_SLAB_BYTES); };
+    FusedGate* gates = reinterpret_cast<FusedGate*>(fusedSmem + 2 * FT_SLAB_BYTES);
+    FusedGroup* groups = reinterpret_cast<FusedGroup*>(fusedSmem + 2 * FT_SLAB_BYTES + FT_MAX_GATES * sizeof(FusedGate));
+    for (unsigned i = threadIdx.x; i < numGates * (sizeof(FusedGate) / 16); i += FT_THREADS)
+        reinterpret_cast<uint4*>(gates)[i] = reinterpret_cast<const uint4*>(gatesGlobal)[i];
+    for (unsigned i = threadIdx.x; i < numGroups * (sizeof(FusedGroup) / 8); i += FT_THREADS)
+        reinterpret_cast<uint2*>(groups)[i] = reinterpret_cast<const uint2*>(groupsGlobal)[i];
+    // element e = tid + 256 i: its offset inside a tile's span of the shard = (thread part) | (i part: tile bits 8..10)
+    uint64_t offTid = 0;
 #pragma unroll
-    for (unsigned i = 0; i < FT_PER_THREAD; i++) {
-        const unsigned e = threadIdx.x + FT_THREADS * i;
-        uint64_t o = 0;
-#pragma unroll
-        for (unsigned b = 0; b < FT_BITS; b++) o |= (uint64_t)((e >> b) & 1u) << tileSpec.pos[b];
-        off[i] = o;
-    }
-    for (uint64_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
+    for (unsigned b = 0; b < 8; b++) offTid |= (uint64_t)((threadIdx.x >> b) & 1u) << tileSpec.pos[b];
+    const uint64_t hi0 = 1ULL << tileSpec.pos[8], hi1 = 1ULL << tileSpec.pos[9], hi2 = 1ULL << tileSpec.pos[10];
+    auto off = [&](unsigned i) { return offTid | ((i & 1u) ? hi0 : 0ULL) | ((i & 2u) ? hi1 : 0ULL) | ((i & 4u) ? hi2 : 0ULL); };
+    auto fetch = [&](uint64_t t, double2* dstSlab) {
         const uint64_t base = insertZeroBitsN<FT_BITS>(t, tileSpec);
 #pragma unroll
         for (unsigned i = 0; i < FT_PER_THREAD; i++) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[swz(threadIdx.x + FT_THREADS * i)]);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(amps + (base | off[i])) : "memory");
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&dstSlab[swz(threadIdx.x + FT_THREADS * i)]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(amps + (base | off(i))) : "memory");
         }
-        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (blockIdx.x < numTiles) fetch(blockIdx.x, slab(0));
+    unsigned cur = 0;
+    for (uint64_t t = blockIdx.x; t < numTiles; t += gridDim.x, cur ^= 1u) {
+        double2* tile = slab(cur);
+        const uint64_t base = insertZeroBitsN<FT_BITS>(t, tileSpec);
+        // the other slab was read out (stored to HBM) before the __syncthreads that ended the previous iteration: refill it now
+        if (t + gridDim.x < numTiles) { fetch(t + gridDim.x, slab(cur ^ 1u)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const uint64_t gidx = rankShift | base;
         for (unsigned gi = 0; gi < numGroups; gi++) {
@@ -91,10 +111,11 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
 #pragma unroll
             for (unsigned i = 0; i < 8; i++) v[i] = tile[swz(eb | ((i & 1u) ? b0 : 0u) | ((i & 2u) ? b1 : 0u) | ((i & 4u) ? b2 : 0u))];
             for (unsigned k = 0; k < grp.numGates; k++) {
-                const FusedGate g = gates[grp.firstGate + k];
+                const FusedGate& g = gates[grp.firstGate + k];
                 if ((gidx & g.ctrlExt) != g.ctrlExt) continue;            // a control outside the tile is 0 for this whole tile
-                if (g.rpos == 0) applyInRegisters<0>(v, g, eb, b0, b1, b2);
-                else if (g.rpos == 1) applyInRegisters<1>(v, g, eb, b0, b1, b2);
+                const unsigned rpos = g.rpos;
+                if (rpos == 0) applyInRegisters<0>(v, g, eb, b0, b1, b2);
+                else if (rpos == 1) applyInRegisters<1>(v, g, eb, b0, b1, b2);
                 else applyInRegisters<2>(v, g, eb, b0, b1, b2);
             }
 #pragma unroll
@@ -102,8 +123,8 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
             __syncthreads();
         }
 #pragma unroll
-        for (unsigned i = 0; i < FT_PER_THREAD; i++) amps[base | off[i]] = tile[swz(threadIdx.x + FT_THREADS * i)];
-        __syncthreads();                                                  // the next tile's copies overwrite the slab
+        for (unsigned i = 0; i < FT_PER_THREAD; i++) amps[base | off(i)] = tile[swz(threadIdx.x + FT_THREADS * i)];
+        __syncthreads();                                                  // this slab is free for the tile after next
     }
 }
 
@@ -240,8 +261,13 @@ extern "C" int dfsa_k_gateSequence(dfsa_state* s, const dfsa_gate1* gates, unsig
         DFSA_TRY(dfsaStagingCommit(slot));
         const uint64_t numTiles = s->numAmps >> FT_BITS;
         const unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 3);
-        fusedGateTileKernel<<<grid, FT_THREADS, 0, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, (const FusedGate*)dev,
-                                                                  (const FusedGroup*)((const char*)dev + gateBytes), (unsigned)b.groups.size(), rankShift);
+        static bool configured = false;
+        if (!configured) {
+            DFSA_CUDA(cudaFuncSetAttribute(fusedGateTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM_BYTES));
+            configured = true;
+        }
+        fusedGateTileKernel<<<grid, FT_THREADS, FT_SMEM_BYTES, ctx.compute>>>(s->arr[DFSA_AMPS], numTiles, tileSpec, (const FusedGate*)dev,
+                                                                              (const FusedGroup*)((const char*)dev + gateBytes), b.count, (unsigned)b.groups.size(), rankShift);
         DFSA_LAUNCH_CHECK();
     }
     return DFSA_OK;
