@@ -578,9 +578,8 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
             job.record(e1)
             if op[0] == "dm_partialTrace":
                 r.close()
-                st.close()                                   # partialTrace mutates its input: start from a fresh state
-                st = job.dfsa.DeviceState(kind, nq)
-                st.init_hash(SEED)
+                st.init_hash(SEED)                           # partialTrace mutates its input: same contents for the next op (the shard and
+                                                             # its peer mappings stay: a fresh allocation would be re-mapped inside the next timed op)
         # the deferred part of the pass: put the relocated qubits back (nothing to do unless a dense gate left some displaced)
         steps = restore_steps()
         displaced = len(steps)

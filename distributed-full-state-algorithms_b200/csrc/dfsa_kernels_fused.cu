@@ -27,32 +27,32 @@ constexpr unsigned FT_BITS = 11, FT_AMPS = 1u << FT_BITS, FT_THREADS = 256, FT_P
 constexpr unsigned FT_LOW_BITS = 4;                 // index bits 0..3 are always in the tile: 256-byte runs
 constexpr unsigned FT_MAX_GATES = 64;
 
-struct FusedGate {                                  // 96 bytes
+struct FusedGate {                                  // 96 bytes, read with 16-byte shared-memory loads
     double2  m00, m01, m10, m11;
     uint64_t ctrlExt;                               // controls outside the tile, as a mask on the GLOBAL index (rank bits included)
-    uint32_t ctrlTile;                              // controls inside the tile, as a mask on the tile-local element index
-    uint32_t rpos;                                  // which of the group's three register bits is the target (0..2)
+    uint32_t ctrlThread;                            // controls inside the tile but outside the group's three register bits: a mask on the
+                                                    // tile-local element index -- the same for all 8 amplitudes a thread holds
+    uint32_t rposAndCtrlReg;                        // bits 0-1: which register bit is the target; bits 4-6: which register bits are controls
     uint32_t pad[4];
 };
 struct FusedGroup { uint32_t firstGate, numGates, r0, r1, r2, pad; };   // r0 < r1 < r2: tile-local bit positions pulled into registers
 
 __device__ __forceinline__ unsigned swz(unsigned e) { return e ^ (((e >> 3) ^ (e >> 6)) & 7u); }
+__device__ __forceinline__ void ldsAmp2(double2& out, unsigned addr) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(out.x), "=d"(out.y) : "r"(addr));
+}
 
 template <unsigned RPOS>
-__device__ __forceinline__ void applyInRegisters(double2 (&v)[8], const FusedGate& gs, unsigned elemBase, unsigned b0, unsigned b1, unsigned b2) {
-    struct { double2 m00, m01, m10, m11; unsigned ctrlTile; } g = {gs.m00, gs.m01, gs.m10, gs.m11, gs.ctrlTile};    // shared -> registers, once per gate
+__device__ __forceinline__ void applyInRegisters(double2 (&v)[8], double2 m00, double2 m01, double2 m10, double2 m11, unsigned ctrlReg) {
 #pragma unroll
     for (unsigned p = 0; p < 4; p++) {
         // pair p: the two other register bits take the values of p's bits; i0 has the target bit clear
         const unsigned lo = p & ((1u << RPOS) - 1u), hi = p >> RPOS;
         const unsigned i0 = lo | (hi << (RPOS + 1)), i1 = i0 | (1u << RPOS);
-        if (g.ctrlTile) {
-            const unsigned e1 = elemBase | ((i1 & 1u) ? b0 : 0u) | ((i1 & 2u) ? b1 : 0u) | ((i1 & 4u) ? b2 : 0u);
-            if ((e1 & g.ctrlTile) != g.ctrlTile) continue;
-        }
+        if ((i1 & ctrlReg) != ctrlReg) continue;                          // a control on one of the other two register bits is 0 for this pair
         const double2 a0 = v[i0], a1 = v[i1];
-        v[i0] = cfma(g.m01, a1, cmul(g.m00, a0));
-        v[i1] = cfma(g.m11, a1, cmul(g.m10, a0));
+        v[i0] = cfma(m01, a1, cmul(m00, a0));
+        v[i1] = cfma(m11, a1, cmul(m10, a0));
     }
 }
 
@@ -110,13 +110,21 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
             double2 v[8];
 #pragma unroll
             for (unsigned i = 0; i < 8; i++) v[i] = tile[swz(eb | ((i & 1u) ? b0 : 0u) | ((i & 2u) ? b1 : 0u) | ((i & 4u) ? b2 : 0u))];
-            for (unsigned k = 0; k < grp.numGates; k++) {
-                const FusedGate& g = gates[grp.firstGate + k];
-                if ((gidx & g.ctrlExt) != g.ctrlExt) continue;            // a control outside the tile is 0 for this whole tile
-                const unsigned rpos = g.rpos;
-                if (rpos == 0) applyInRegisters<0>(v, g, eb, b0, b1, b2);
-                else if (rpos == 1) applyInRegisters<1>(v, g, eb, b0, b1, b2);
-                else applyInRegisters<2>(v, g, eb, b0, b1, b2);
+            unsigned gAddr = (unsigned)__cvta_generic_to_shared(&gates[grp.firstGate]);
+            for (unsigned k = 0; k < grp.numGates; k++, gAddr += (unsigned)sizeof(FusedGate)) {
+                // the descriptor comes as five 16-byte broadcast loads straight into vector registers (left to the compiler it went
+                // through uniform registers: a dozen R2UR + as many moves per gate, profiles/r02_ncu_fused.txt)
+                unsigned long long ctrlExt, second;                       // second = ctrlThread | rposAndCtrlReg << 32
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ctrlExt), "=l"(second) : "r"(gAddr + 64u));
+                const unsigned ctrlThread = (unsigned)second, packed = (unsigned)(second >> 32);
+                if ((gidx & ctrlExt) != ctrlExt) continue;                // a control outside the tile is 0 for this whole tile
+                if ((eb & ctrlThread) != ctrlThread) continue;            // ... or for everything this thread holds
+                double2 m00, m01, m10, m11;
+                ldsAmp2(m00, gAddr); ldsAmp2(m01, gAddr + 16u); ldsAmp2(m10, gAddr + 32u); ldsAmp2(m11, gAddr + 48u);
+                const unsigned rpos = packed & 3u, ctrlReg = (packed >> 4) & 7u;
+                if (rpos == 0) applyInRegisters<0>(v, m00, m01, m10, m11, ctrlReg);
+                else if (rpos == 1) applyInRegisters<1>(v, m00, m01, m10, m11, ctrlReg);
+                else applyInRegisters<2>(v, m00, m01, m10, m11, ctrlReg);
             }
 #pragma unroll
             for (unsigned i = 0; i < 8; i++) tile[swz(eb | ((i & 1u) ? b0 : 0u) | ((i & 2u) ? b1 : 0u) | ((i & 4u) ? b2 : 0u))] = v[i];
@@ -249,9 +257,16 @@ extern "C" int dfsa_k_gateSequence(dfsa_state* s, const dfsa_gate1* gates, unsig
             d.m00 = hostAmp(src.matrix); d.m01 = hostAmp(src.matrix + 2); d.m10 = hostAmp(src.matrix + 4); d.m11 = hostAmp(src.matrix + 6);
             const uint64_t local = src.ctrlMask & localMask;
             d.ctrlExt = (local & ~tileMask) | (src.ctrlMask & ~localMask);     // satisfied rank-bit controls test true against rankShift
-            d.ctrlTile = 0;
-            for (unsigned q = 0; q < FT_BITS; q++) if ((local >> b.tileBits[q]) & 1ULL) d.ctrlTile |= 1u << q;
-            d.rpos = b.rpos[x];
+            unsigned ctrlTile = 0;
+            for (unsigned q = 0; q < FT_BITS; q++) if ((local >> b.tileBits[q]) & 1ULL) ctrlTile |= 1u << q;
+            // the group this gate belongs to decides which tile bits live in registers
+            const FusedGroup* grp = nullptr;
+            for (const FusedGroup& gg : b.groups) if (x >= gg.firstGate && x < gg.firstGate + gg.numGates) grp = &gg;
+            const unsigned rbit[3] = {grp->r0, grp->r1, grp->r2};
+            unsigned ctrlReg = 0;
+            for (unsigned r = 0; r < 3; r++) if ((ctrlTile >> rbit[r]) & 1u) { ctrlReg |= 1u << r; ctrlTile &= ~(1u << rbit[r]); }
+            d.ctrlThread = ctrlTile;
+            d.rposAndCtrlReg = b.rpos[x] | (ctrlReg << 4);
             memset(d.pad, 0, sizeof(d.pad));
         }
         memcpy((char*)stage + gateBytes, b.groups.data(), groupBytes);

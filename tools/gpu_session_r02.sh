@@ -37,6 +37,15 @@ case $MODE in
     tail -n 2 $OUT/${TAG}_ncu_fused.log
     timeout 700 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"; tail -n 3 $OUT/${TAG}_bench_n1.err; cat $OUT/${TAG}_bench_n1.json
     ;;
+  fused2)
+    timeout 400 python -m pytest tests -m gpu -q -k "fused or every_target or config1" > $OUT/${TAG}_pytest_fused.log 2>&1; tail -n 5 $OUT/${TAG}_pytest_fused.log
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:fusedGateTile -c 2 -f -o $OUT/${TAG}_fused python tools/prof_fused.py 28 > $OUT/${TAG}_ncu_fused.log 2>&1
+    ncu -i $OUT/${TAG}_fused.ncu-rep --page raw --csv > $OUT/${TAG}_fused_raw.csv 2>> $OUT/${TAG}_ncu_fused.log
+    ncu -i $OUT/${TAG}_fused.ncu-rep --page source --csv > $OUT/${TAG}_fused_source.csv 2>> $OUT/${TAG}_ncu_fused.log
+    tail -n 2 $OUT/${TAG}_ncu_fused.log
+    timeout 300 python tools/bench_dm_extras.py 14 > $OUT/${TAG}_dm_extras_14q.jsonl 2> $OUT/${TAG}_dm_extras.err; cat $OUT/${TAG}_dm_extras_14q.jsonl; tail -n 3 $OUT/${TAG}_dm_extras.err
+    timeout 700 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; echo "bench rc=$?"; tail -n 3 $OUT/${TAG}_bench_n1.err; cat $OUT/${TAG}_bench_n1.json
+    ;;
   link)
     NP=${NP:-2}
     for f in ${INFLIGHTS:-2048 4096 8192 16384}; do
