@@ -56,20 +56,23 @@ __device__ __forceinline__ void applyInRegisters(double2 (&v)[8], double2 m00, d
     }
 }
 
-// Shared memory per block: two tile slabs (the next tile streams in with cp.async while the current one is being worked on)
-// and the pass's gate / group descriptors (read as warp-wide broadcasts: the first version fetched them from global memory
-// per gate and per thread and spent a third of its stall samples waiting for those loads -- profiles/r02_ncu_fused.txt).
+// Shared memory per block: one tile slab and the pass's gate / group descriptors (read as warp-wide broadcasts: the first version
+// fetched them from global memory per gate and per thread and spent a third of its stall samples waiting for those loads --
+// profiles/r02_ncu_fused.txt). 64 registers and 39.5 KiB per block: FOUR blocks per SM, so one block's load / store / barrier
+// phases are covered by the arithmetic of the other three (a second slab per block with prefetch was measured: no gain, and it
+// limits the SM to three blocks).
 constexpr unsigned FT_SLAB_BYTES = FT_AMPS * sizeof(double2);
 constexpr unsigned FT_DESC_BYTES = FT_MAX_GATES * (sizeof(FusedGate) + sizeof(FusedGroup));
-constexpr unsigned FT_SMEM_BYTES = 2 * FT_SLAB_BYTES + FT_DESC_BYTES;
+constexpr unsigned FT_SMEM_BYTES = FT_SLAB_BYTES + FT_DESC_BYTES;
+constexpr unsigned FT_BLOCKS_PER_SM = 4;
 
-__global__ void __launch_bounds__(FT_THREADS, 3)
+__global__ void __launch_bounds__(FT_THREADS, FT_BLOCKS_PER_SM)
 fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const FusedGate* __restrict__ gatesGlobal, const FusedGroup* __restrict__ groupsGlobal,
                     unsigned numGates, unsigned numGroups, uint64_t rankShift) {
     extern __shared__ __align__(16) unsigned char fusedSmem[];
-    auto slab = [&](unsigned which) { return reinterpret_cast<double2*>(fusedSmem + which * FT_SLAB_BYTES); };
-    FusedGate* gates = reinterpret_cast<FusedGate*>(fusedSmem + 2 * FT_SLAB_BYTES);
-    FusedGroup* groups = reinterpret_cast<FusedGroup*>(fusedSmem + 2 * FT_SLAB_BYTES + FT_MAX_GATES * sizeof(FusedGate));
+    double2* tile = reinterpret_cast<double2*>(fusedSmem);
+    FusedGate* gates = reinterpret_cast<FusedGate*>(fusedSmem + FT_SLAB_BYTES);
+    FusedGroup* groups = reinterpret_cast<FusedGroup*>(fusedSmem + FT_SLAB_BYTES + FT_MAX_GATES * sizeof(FusedGate));
     for (unsigned i = threadIdx.x; i < numGates * (sizeof(FusedGate) / 16); i += FT_THREADS)
         reinterpret_cast<uint4*>(gates)[i] = reinterpret_cast<const uint4*>(gatesGlobal)[i];
     for (unsigned i = threadIdx.x; i < numGroups * (sizeof(FusedGroup) / 8); i += FT_THREADS)
@@ -80,23 +83,14 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
     for (unsigned b = 0; b < 8; b++) offTid |= (uint64_t)((threadIdx.x >> b) & 1u) << tileSpec.pos[b];
     const uint64_t hi0 = 1ULL << tileSpec.pos[8], hi1 = 1ULL << tileSpec.pos[9], hi2 = 1ULL << tileSpec.pos[10];
     auto off = [&](unsigned i) { return offTid | ((i & 1u) ? hi0 : 0ULL) | ((i & 2u) ? hi1 : 0ULL) | ((i & 4u) ? hi2 : 0ULL); };
-    auto fetch = [&](uint64_t t, double2* dstSlab) {
+    for (uint64_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
         const uint64_t base = insertZeroBitsN<FT_BITS>(t, tileSpec);
 #pragma unroll
         for (unsigned i = 0; i < FT_PER_THREAD; i++) {
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&dstSlab[swz(threadIdx.x + FT_THREADS * i)]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&tile[swz(threadIdx.x + FT_THREADS * i)]);
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(amps + (base | off(i))) : "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    if (blockIdx.x < numTiles) fetch(blockIdx.x, slab(0));
-    unsigned cur = 0;
-    for (uint64_t t = blockIdx.x; t < numTiles; t += gridDim.x, cur ^= 1u) {
-        double2* tile = slab(cur);
-        const uint64_t base = insertZeroBitsN<FT_BITS>(t, tileSpec);
-        // the other slab was read out (stored to HBM) before the __syncthreads that ended the previous iteration: refill it now
-        if (t + gridDim.x < numTiles) { fetch(t + gridDim.x, slab(cur ^ 1u)); asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         const uint64_t gidx = rankShift | base;
         for (unsigned gi = 0; gi < numGroups; gi++) {
@@ -116,11 +110,11 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
                 // through uniform registers: a dozen R2UR + as many moves per gate, profiles/r02_ncu_fused.txt)
                 unsigned long long ctrlExt, second;                       // second = ctrlThread | rposAndCtrlReg << 32
                 asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ctrlExt), "=l"(second) : "r"(gAddr + 64u));
+                double2 m00, m01, m10, m11;
+                ldsAmp2(m00, gAddr); ldsAmp2(m01, gAddr + 16u); ldsAmp2(m10, gAddr + 32u); ldsAmp2(m11, gAddr + 48u);
                 const unsigned ctrlThread = (unsigned)second, packed = (unsigned)(second >> 32);
                 if ((gidx & ctrlExt) != ctrlExt) continue;                // a control outside the tile is 0 for this whole tile
                 if ((eb & ctrlThread) != ctrlThread) continue;            // ... or for everything this thread holds
-                double2 m00, m01, m10, m11;
-                ldsAmp2(m00, gAddr); ldsAmp2(m01, gAddr + 16u); ldsAmp2(m10, gAddr + 32u); ldsAmp2(m11, gAddr + 48u);
                 const unsigned rpos = packed & 3u, ctrlReg = (packed >> 4) & 7u;
                 if (rpos == 0) applyInRegisters<0>(v, m00, m01, m10, m11, ctrlReg);
                 else if (rpos == 1) applyInRegisters<1>(v, m00, m01, m10, m11, ctrlReg);
@@ -132,7 +126,7 @@ fusedGateTileKernel(double2* amps, uint64_t numTiles, BitSpec tileSpec, const Fu
         }
 #pragma unroll
         for (unsigned i = 0; i < FT_PER_THREAD; i++) amps[base | off(i)] = tile[swz(threadIdx.x + FT_THREADS * i)];
-        __syncthreads();                                                  // this slab is free for the tile after next
+        __syncthreads();                                                  // the next tile's copies overwrite the slab
     }
 }
 
@@ -275,7 +269,7 @@ extern "C" int dfsa_k_gateSequence(dfsa_state* s, const dfsa_gate1* gates, unsig
         DFSA_CUDA(cudaMemcpyAsync(dev, stage, gateBytes + groupBytes, cudaMemcpyHostToDevice, ctx.compute));
         DFSA_TRY(dfsaStagingCommit(slot));
         const uint64_t numTiles = s->numAmps >> FT_BITS;
-        const unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * 3);
+        const unsigned grid = (unsigned)std::min<uint64_t>(numTiles, (uint64_t)ctx.numSMs * FT_BLOCKS_PER_SM);
         static bool configured = false;
         if (!configured) {
             DFSA_CUDA(cudaFuncSetAttribute(fusedGateTileKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FT_SMEM_BYTES));

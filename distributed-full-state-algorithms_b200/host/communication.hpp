@@ -39,6 +39,12 @@ inline void (*&flushAllStatesHook())() { static void (*hook)() = nullptr; return
 }
 
 static inline void comm_init() { DFSA_CHECK(dfsa_comm_init()); }
+// Joining a job whose ranks do not share a parent process or a node-local rendezvous (srun / mpirun wrappers that set neither
+// MASTER_PORT nor DFSA_JOB_ID): rank 0 obtains a 128-byte id with dfsa_comm_get_unique_id, the launcher's own mechanism
+// broadcasts it, every rank calls this instead of comm_init(). Exchanges then run on the staged NCCL transport.
+static inline void comm_initWithId(Nat rank, Nat numRanks, const void* uniqueId128, int device = -1) {
+    DFSA_CHECK(dfsa_comm_init_with_id(int(rank), int(numRanks), uniqueId128, device));
+}
 static inline void comm_end() { DFSA_CHECK(dfsa_comm_finalize()); }
 static inline Nat comm_getRank() { return Nat(dfsa_comm_rank()); }
 static inline Nat comm_getNumNodes() { return Nat(dfsa_comm_size()); }

@@ -75,3 +75,51 @@ def test_restore_plan_returns_every_qubit_to_its_own_index_bit(n, k):
         assert sum(1 for s in steps if s[0] == 0) <= 4
         if where == list(range(n)):
             assert steps == []
+
+
+def relocation_on_layout(where, L, targets):
+    h = product.pkg().host_lib()
+    n, nt = len(where), len(targets)
+    out = (C.c_uint * nt)()
+    h.dfsa_host_plan_relocationOnLayout((C.c_uint * n)(*where), n, L, (C.c_uint * nt)(*targets), nt, out)
+    return list(out)
+
+
+@pytest.mark.parametrize("n,k", [(10, 1), (12, 3), (12, 4)])
+def test_relocation_lands_where_the_restore_stays_cheap(n, k):
+    """dfsa_planRelocationOnLayout (host/distributed_statevector.hpp): every prefix target lands on a distinct free suffix
+    bit, suffix targets stay; a displaced qubit whose home is the target's prefix bit is brought home; over a random
+    circuit of dense gates the layout never holds a rank relabelling (a qubit whose home is a rank bit sitting on ANOTHER
+    rank bit), so the restore plan never needs a full-shard exchange."""
+    rng = np.random.default_rng(n + k)
+    L = n - k
+    for trial in range(200):
+        where = list(range(n))
+        forced = False                                             # a landing had neither a home slot nor a clean slot to go to
+        for gate in range(int(rng.integers(1, 9))):
+            logical = [int(x) for x in rng.permutation(n)[: int(rng.integers(1, min(L, 6) + 1))]]
+            targets = [where[q] for q in logical]                  # index bits
+            placed = relocation_on_layout(where, L, targets)
+            assert all(p < L for p in placed) and len(set(placed)) == len(placed)
+            before = list(where)
+            used = set()
+            for t, p in zip(targets, placed):
+                if t < L:
+                    assert p == t
+                    continue
+                home_now = before[t]                               # where the qubit whose home is bit t sits
+                free = [s_ for s_ in range(L) if s_ not in targets and s_ not in used]
+                if home_now in free:
+                    assert p == home_now, "a displaced qubit must be brought home"
+                elif any(before[s_] == s_ for s_ in free):
+                    assert before[p] == p, "a slot holding its own qubit was available"
+                else:
+                    forced = True
+                used.add(p)
+                where = relabel(where, p, t)
+            if not forced:
+                for q in range(L, n):
+                    assert where[q] < L or where[q] == q, "rank relabelling in the layout: %r" % (where,)
+        if not forced:
+            for kind, a, b in restore_plan(where, L):
+                assert not (a >= L and b >= L), "restore needs a full-shard exchange: %r" % (where,)
