@@ -743,35 +743,53 @@ def run_product(args, world, rank, local_rank):
     if fusion:
         # fused passes: what must cross HBM for a pass is one read and one write of the shard, however many gates it carries;
         # the FP64 work of its gates (16 FMA per touched pair) is the other bound
-        is_local = [all(c[1] == 0 for c in op_cost(op, "sv", nq, k)) for op in ops]
-        local_ops = [op for op, loc in zip(ops, is_local) if loc]
+        # In this mode a gate whose qubit sits on a rank bit first swaps it into the shard (8*A bytes per direction, the layout
+        # remembers it) and is then a local gate like the others; which gates that hits depends on the layout the previous
+        # step left behind, so one untimed step is walked to count them.
         class G(C.Structure):
             _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
-        arr = (G * len(local_ops))()
-        pairs = 0.0
-        for i, op in enumerate(local_ops):
+
+        def plan_passes(segment):
+            """passes over HBM the library makes for a run of (index-bit target, index-bit controls) gates"""
+            if not segment:
+                return 0
+            arr = (G * len(segment))()
+            for i, (t, ctrls) in enumerate(segment):
+                arr[i].target = t
+                arr[i].ctrlMask = sum(1 << c for c in ctrls if c < L)
+            nb = C.c_uint()
+            scratch = [(C.c_uint32 * max(1, 11 * len(segment)))() for _ in range(5)]
+            check(lib.dfsa_plan_gateSequence(arr, len(segment), L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
+            return nb.value
+
+        relocations, passes, pairs, segment = 0, 0, 0.0, []
+        for op in ops:
+            tq = op[1] if op[0] == "sv_oneTargGate" else op[2]
             ctrls = [] if op[0] == "sv_oneTargGate" else op[1]
-            arr[i].target = op[1] if op[0] == "sv_oneTargGate" else op[2]
-            arr[i].ctrlMask = sum(1 << c for c in ctrls if c < L)
+            if st.layout()[tq] >= L:                         # the call below swaps the qubit into the shard: the queue is flushed first
+                relocations += 1
+                passes += plan_passes(segment)
+                segment = []
+            cases.apply(st, op)
+            where = st.layout()
+            segment.append((where[tq], [where[c] for c in ctrls]))
             pairs += (shard_amps / 2.0) / (1 << len(ctrls))     # averaged over ranks for rank-bit controls
-        n = len(local_ops)
-        nb = C.c_uint()
-        scratch = [(C.c_uint32 * max(1, 11 * n))() for _ in range(5)]
-        check(lib.dfsa_plan_gateSequence(arr, n, L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
-        passes = nb.value
-        exch_ms = sum(bound_ms(op_cost(op, "sv", nq, k), peaks) for op, loc in zip(ops, is_local) if not loc)
+        passes += plan_passes(segment)
+        st.flush()
+        n = len(ops)
+        exch_ms = relocations * bound_ms([(32.0 * shard_amps, 8.0 * shard_amps, 0.0)], peaks)
         local_ms = max(step_ms - exch_ms, 1e-9)            # exchange gates at their bound: a lower bound on what the passes took
         achieved = 32.0 * shard_amps * passes / (local_ms * 1e-3) / 1e9
         fp64_ms = pairs * 32.0 / (FP64_PEAK_TFLOPS * 1e12) * 1e3
         roofline = {"bound": "hbm", "kernel": "fusedGateTileKernel (all one-target gates of a pass applied to 32 KiB tiles in shared memory)", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
-                    "avg_launch_ms": local_ms / passes, "passes_per_step": passes, "gates_in_passes": n,
+                    "avg_launch_ms": local_ms / passes, "passes_per_step": passes, "gates_in_passes": n, "relocations_per_step": relocations,
                     "fp64_bound_ms_per_step": fp64_ms, "hbm_bound_ms_per_step": 32.0 * shard_amps * passes / (hbm_peak * 1e9) * 1e3,
                     "note": "algorithmic bytes of a fused pass = one read + one write of the shard (32*A), whatever the number of gates it carries; "
                             "time per launch = (step time - exchange gates at their roofline) / passes, measured with CUDA events around whole steps",
                     "traffic": None}
         step_roofline = {"bound_ms": max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms, "frac": (max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms) / step_ms,
-                         "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + exchange gates at their NVLink bound",
+                         "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + one suffix<->prefix swap (8*A bytes per direction at the measured NVLink rate) per gate whose qubit sat on a rank bit",
                          "speedup_over_per_gate_roofline": bound_step / step_ms}
     else:
         roofline = dict(per_gate_mode["roofline"], peak_source=peak_src)

@@ -84,6 +84,25 @@ inline void enqueueOneTarg(StateVector& psi, const NatArray& controls, Nat targe
 }
 }  // namespace dfsa_detail
 
+static inline NatArray dfsa_planRelocationOnLayout(const NatArray& where, Nat L, const NatArray& targets);
+
+// With the lazy layout and the gate queue both on, a one-target gate whose qubit sits on a RANK bit is not applied through a
+// full-shard exchange (reference :26-38, 16*A bytes per direction): the qubit is swapped into the shard (8*A bytes per
+// direction, layout.hpp remembers it), the gate is queued like any local gate, and every later gate on that qubit is local
+// too. Never more NVLink bytes than the exchange (8*A now + at most 8*A when the layout is restored), usually far fewer.
+static inline bool dfsa_bringQubitIntoShard(StateVector& psi, Nat logicalQubit) {
+    const Nat L = Nat(psi.logNumAmpsPerNode);
+    if (psi.where[logicalQubit] < L) return true;
+    if (!(dfsa_detail::lazyLayoutEnabled() && StateVector::gateFusionEnabled())) return false;
+    psi.flushGates();                                         // queued gates name index bits of the layout as it is now
+    const Nat prefixBit = psi.where[logicalQubit];
+    const NatArray placed = dfsa_planRelocationOnLayout(psi.where, L, NatArray{prefixBit});
+    const Nat landing = placed[0];
+    DFSA_CHECK(dfsa_xk_relocate(psi.handle, &landing, &prefixBit, 1));
+    psi.noteSwapped(landing, prefixBit);
+    return true;
+}
+
 // A 2x2 gate on a prefix qubit mixes this shard with the partner's: amps = g[b][b]*amps + g[b][!b]*partner
 static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMatrix& gate) {
     psi.flushGates();
@@ -99,6 +118,7 @@ static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMat
 }
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
+    dfsa_bringQubitIntoShard(psi, target);
     target = psi.where[target];                               // the index bit that holds the qubit (layout.hpp)
     if (target < psi.logNumAmpsPerNode && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, {}, target, gate); return; }
     if (target < psi.logNumAmpsPerNode) local_statevector_oneTargGate(psi, target, gate);
@@ -107,6 +127,7 @@ inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, Am
 
 static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi, NatArray controls, Nat target, AmpMatrix gate) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
+    dfsa_bringQubitIntoShard(psi, target);
     controls = psi.physical(controls);
     target = psi.where[target];
     if (target < L && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, controls, target, gate); return; }
