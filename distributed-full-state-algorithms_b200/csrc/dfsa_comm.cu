@@ -758,14 +758,15 @@ extern "C" int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double
     DFSA_REQUIRE(f0 && f1, "null factor");
     DFSA_TRY(checkXArgs(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s ? s->numAmps : 0, pairRank));
     const double2 c0 = make_double2(f0[0], f0[1]), c1 = make_double2(f1[0], f1[1]);
+    const bool partnerFirst = dfsaCtx().rank > pairRank;          // this rank holds bit 1 of the target: same FMA nesting as the local kernel's upper output
     if (fusedAvailable())
-        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedCombine(s, remote, c0, c1); });
+        return fusedExchange(s, pairRank, [&](const double2* remote) { return dfsaLaunchFusedCombine(s, remote, c0, c1, partnerFirst); });
     const int chunks = (dfsaCtx().transport == Transport::Nccl) ? chunkCountFor(s->numAmps) : 1;
     if (chunks == 1) {
         DFSA_TRY(transfer(s, DFSA_AMPS, 0, DFSA_BUFFER, 0, s->numAmps, pairRank, true, true));
-        return dfsaLaunchCombineRange(s, 0, s->numAmps, c0, c1);
+        return dfsaLaunchCombineRange(s, 0, s->numAmps, c0, c1, partnerFirst);
     }
-    return pipelinedExchange(s, pairRank, chunks, [&](uint64_t first, uint64_t num) { return dfsaLaunchCombineRange(s, first, num, c0, c1); });
+    return pipelinedExchange(s, pairRank, chunks, [&](uint64_t first, uint64_t num) { return dfsaLaunchCombineRange(s, first, num, c0, c1, partnerFirst); });
 }
 
 extern "C" int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, int pairRank) {
@@ -931,12 +932,12 @@ extern "C" int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls
         DFSA_TRY(sortedSpec(suffixCtrls, numCtrls, s->logNumAmps, &spec, &ones));
         const double2 c0 = make_double2(f0[0], f0[1]), c1 = make_double2(f1[0], f1[1]);
         return fusedGroupExchange(s, &pairRank, 1,
-            [&](const double2* const* remote) { return dfsaLaunchFusedCombineSub(s, remote[0], spec, ones, c0, c1); },
+            [&](const double2* const* remote) { return dfsaLaunchFusedCombineSub(s, remote[0], spec, ones, c0, c1, dfsaCtx().rank > pairRank); },
             [&](dfsa_state* st) { return dfsa_k_unpack(st, suffixCtrls, numCtrls, allOnes, 0); });      // both ranks are done reading: results go home
     }
     DFSA_TRY(dfsa_k_pack(s, suffixCtrls, numCtrls, allOnes, 0));
     DFSA_TRY(transfer(s, DFSA_BUFFER, 0, DFSA_BUFFER, m, m, pairRank, true, true));
-    return dfsa_k_combineSub(s, suffixCtrls, numCtrls, allOnes, m, f0, f1);
+    return dfsaCombineSub(s, suffixCtrls, numCtrls, allOnes, m, f0, f1, dfsaCtx().rank > pairRank);
 }
 
 // twoQubitDepolarising, qb1 suffix / qb2 prefix (distributed_densitymatrix.hpp:146-183)

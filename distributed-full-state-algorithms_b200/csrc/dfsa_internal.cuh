@@ -73,18 +73,19 @@ int  dfsaPoolDrain();                            // release the recycled small s
 #define DFSA_LAUNCH_CHECK() do { DFSA_COUNT_LAUNCH(); DFSA_CUDA(cudaGetLastError()); } while (0)
 
 // range forms of the combine kernels (dfsa_kernels_sv.cu), used by the pipelined exchange in dfsa_comm.cu
-int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1);
+int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1, bool partnerFirst);
 int dfsaLaunchPauliCombineRange(dfsa_state* s, uint64_t first, uint64_t num, int pairRank, uint64_t maskXY, uint64_t maskYZ,
                                 unsigned numY, double2 f, double2 h, bool exact);
 
 // fused remote-load kernels (dfsa_kernels_sv.cu): buffer[j] = f0*amps[j] + f1*remote[j]  /  the Pauli form; the caller swaps arrays
-int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1);
+int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1, bool partnerFirst);
 int dfsaLaunchFusedPauliCombine(dfsa_state* s, const double2* remote, int pairRank, uint64_t maskXY, uint64_t maskYZ,
                                 unsigned numY, double2 f, double2 h, bool exact);
 int dfsaLaunchFusedSwap(dfsa_state* s, const double2* remote, unsigned qb, unsigned myBit);   // buffer = shard after swapping suffix qubit qb with this pair's prefix qubit
 int dfsaLaunchFusedDepol1(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);    // prefix oneQubitDepolarising, buffer = result
 int dfsaLaunchFusedDamping(dfsa_state* s, const double2* remote, unsigned qb, unsigned bit, double prob);   // prefix damping, buffer = result
-int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const struct BitSpec& spec, uint64_t fixed, double2 c0, double2 c1);   // buffer[j] = c0*amps[k(j)] + c1*remote[k(j)] on a control sub-cube
+int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const struct BitSpec& spec, uint64_t fixed, double2 c0, double2 c1, bool partnerFirst);
+int dfsaCombineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart, const double f0[2], const double f1[2], bool partnerFirst);   // buffer[j] = c0*amps[k(j)] + c1*remote[k(j)] on a control sub-cube
 int dfsaLaunchFusedDepol2Pair(dfsa_state* s, const double2* remote, unsigned q0, unsigned q1, unsigned q2, unsigned bit, double prob, bool corrected);
 int dfsaLaunchFusedDepol2Quad(dfsa_state* s, const double2* const* remote, unsigned q0, unsigned q1, unsigned bit0, unsigned bit1, double prob, bool corrected);
 int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigned* suffixPos, unsigned k, unsigned rho);   // buffer = shard after swapping k suffix with k prefix qubits

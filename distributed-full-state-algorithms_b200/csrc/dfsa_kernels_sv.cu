@@ -183,18 +183,21 @@ extern "C" int dfsa_k_pauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY,
 
 // ---------------------------------------------------------------------------------------------------------
 // K7: distributed_statevector.hpp:36-38. amps[i] = f0*amps[i] + f1*buffer[i]. 48*A bytes. Range form: i in [first, first+num).
-int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1) {
+// partnerFirst: the rank holding bit 1 of the target forms m10*partner first and then adds m11*own -- the FMA nesting the local
+// kernel uses for its upper output (K1: cfma(m11, a1, cmul(m10, a0))), so a gate gives the same bits whether its qubit sits on
+// a suffix bit or a rank bit (the lazy layout may move it between the two).
+int dfsaLaunchCombineRange(dfsa_state* s, uint64_t first, uint64_t num, double2 c0, double2 c1, bool partnerFirst) {
     double2* amps = s->arr[DFSA_AMPS] + first;
     const double2* buf = s->arr[DFSA_BUFFER] + first;
     auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], buf[i]}; };
-    auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    auto st = [=] __device__(uint64_t i, const Amp2& v) { amps[i] = partnerFirst ? cfma(c0, v.a0, cmul(c1, v.a1)) : cfma(c1, v.a1, cmul(c0, v.a0)); };
     return launchStream<1, Amp2>(num, ld, st);
 }
 
 extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1[2]) {
     DFSA_TRY(dfsaEnsureDevice());
     DFSA_REQUIRE(s && f0 && f1 && s->arr[DFSA_BUFFER], "null argument / no exchange buffer");
-    return dfsaLaunchCombineRange(s, 0, s->numAmps, hostAmp(f0), hostAmp(f1));
+    return dfsaLaunchCombineRange(s, 0, s->numAmps, hostAmp(f0), hostAmp(f1), false);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -202,11 +205,11 @@ extern "C" int dfsa_k_combine(dfsa_state* s, const double f0[2], const double f1
 // (CUDA IPC; NVLink peer access between GPUs), so the combine loads the partner's amplitudes directly over NVLink while
 // streaming its own shard from HBM, and writes the result out-of-place into `buffer`; the caller then swaps amps<->buffer.
 // Per rank: 16*A bytes over NVLink, 32*A bytes of HBM traffic (the staged path moves 80*A through HBM), no staging pass.
-int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1) {
+int dfsaLaunchFusedCombine(dfsa_state* s, const double2* remote, double2 c0, double2 c1, bool partnerFirst) {
     const double2* amps = s->arr[DFSA_AMPS];
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t i) { return Amp2{amps[i], remote[i]}; };
-    auto st = [=] __device__(uint64_t i, const Amp2& v) { out[i] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    auto st = [=] __device__(uint64_t i, const Amp2& v) { out[i] = partnerFirst ? cfma(c0, v.a0, cmul(c1, v.a1)) : cfma(c1, v.a1, cmul(c0, v.a0)); };
     return launchStreamRemote<Amp2>(s->numAmps, ld, st);
 }
 
@@ -290,8 +293,14 @@ extern "C" int dfsa_k_unpack(dfsa_state* s, const uint32_t* positions, unsigned 
     return launchStream<2, Amp1>(items, ld, st);
 }
 
+int dfsaCombineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
+                   const double f0[2], const double f1[2], bool partnerFirst);
 extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
                                  const double f0[2], const double f1[2]) {
+    return dfsaCombineSub(s, positions, numPositions, values, srcStart, f0, f1, false);
+}
+int dfsaCombineSub(dfsa_state* s, const uint32_t* positions, unsigned numPositions, uint64_t values, uint64_t srcStart,
+                   const double f0[2], const double f1[2], bool partnerFirst) {
     DFSA_TRY(dfsaEnsureDevice());
     BitSpec spec; uint64_t fixed;
     DFSA_TRY(subcubeSpec(s, positions, numPositions, values, &spec, &fixed));
@@ -301,7 +310,7 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
     const double2* buf = s->arr[DFSA_BUFFER] + srcStart;
     double2 c0 = hostAmp(f0), c1 = hostAmp(f1);
     auto ld = [=] __device__(uint64_t j) { return Amp2{amps[insertZeroBits(j, spec) | fixed], buf[j]}; };
-    auto st = [=] __device__(uint64_t j, const Amp2& v) { amps[insertZeroBits(j, spec) | fixed] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    auto st = [=] __device__(uint64_t j, const Amp2& v) { amps[insertZeroBits(j, spec) | fixed] = partnerFirst ? cfma(c0, v.a0, cmul(c1, v.a1)) : cfma(c1, v.a1, cmul(c0, v.a0)); };
     return launchStream<1, Amp2>(items, ld, st);
 }
 
@@ -310,11 +319,11 @@ extern "C" int dfsa_k_combineSub(dfsa_state* s, const uint32_t* positions, unsig
 // Two small passes instead: buffer[j] = f0*amps[k(j)] + f1*partner_amps[k(j)] (partner read over NVLink), then -- once both
 // ranks have finished reading each other -- amps[k(j)] = buffer[j] (dfsa_k_unpack). 64 bytes of HBM traffic per touched
 // amplitude against the staged path's 112 (pack, send + receive staging, combine), NVLink 16 per direction either way.
-int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const BitSpec& spec, uint64_t fixed, double2 c0, double2 c1) {
+int dfsaLaunchFusedCombineSub(dfsa_state* s, const double2* remote, const BitSpec& spec, uint64_t fixed, double2 c0, double2 c1, bool partnerFirst) {
     const double2* amps = s->arr[DFSA_AMPS];
     double2* out = s->arr[DFSA_BUFFER];
     auto ld = [=] __device__(uint64_t j) { const uint64_t k = insertZeroBits(j, spec) | fixed; return Amp2{amps[k], remote[k]}; };
-    auto st = [=] __device__(uint64_t j, const Amp2& v) { out[j] = cfma(c1, v.a1, cmul(c0, v.a0)); };
+    auto st = [=] __device__(uint64_t j, const Amp2& v) { out[j] = partnerFirst ? cfma(c0, v.a0, cmul(c1, v.a1)) : cfma(c1, v.a1, cmul(c0, v.a0)); };
     return launchStreamRemote<Amp2>(s->numAmps >> spec.n, ld, st);
 }
 
