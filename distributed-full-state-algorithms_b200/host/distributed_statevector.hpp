@@ -84,20 +84,35 @@ inline void enqueueOneTarg(StateVector& psi, const NatArray& controls, Nat targe
 }
 }  // namespace dfsa_detail
 
-static inline NatArray dfsa_planRelocationOnLayout(const NatArray& where, Nat L, const NatArray& targets);
-
 // With the lazy layout and the gate queue both on, a one-target gate whose qubit sits on a RANK bit is not applied through a
 // full-shard exchange (reference :26-38, 16*A bytes per direction): the qubit is swapped into the shard (8*A bytes per
 // direction, layout.hpp remembers it), the gate is queued like any local gate, and every later gate on that qubit is local
 // too. Never more NVLink bytes than the exchange (8*A now + at most 8*A when the layout is restored), usually far fewer.
-static inline bool dfsa_bringQubitIntoShard(StateVector& psi, Nat logicalQubit) {
+// Which suffix bit it lands on = which qubit is evicted onto the rank bit. Circuits are mostly layers that visit the qubits in
+// the same order again and again; for such scans the qubit to evict is the one used MOST recently (its next use is the
+// furthest away -- Belady's choice; evicting the least recently used one, or sending displaced qubits straight home, makes
+// every layer pay two swaps per rank bit instead of one). "Used" means used as a TARGET: controls work from rank bits too.
+// Qubits the current gate itself uses are not evicted. For bench.py's sweep this gives log2(P) swaps per layer, the minimum.
+static inline Nat dfsa_pickEvictionBit(const StateVector& psi, const NatArray& busyLogical) {
+    const Nat L = Nat(psi.logNumAmpsPerNode);
+    int best = -1;
+    unsigned long long bestUse = 0;
+    for (Nat q = 0; q < Nat(psi.where.size()); q++) {
+        const Nat pos = psi.where[q];
+        if (pos >= L || std::find(busyLogical.begin(), busyLogical.end(), q) != busyLogical.end()) continue;
+        if (best < 0 || psi.lastUse[q] > bestUse || (psi.lastUse[q] == bestUse && pos > Nat(best))) { best = int(pos); bestUse = psi.lastUse[q]; }
+    }
+    if (best < 0) best = int(L) - 1;                          // every suffix qubit is busy (a gate controlled on all of them)
+    return Nat(best);
+}
+
+static inline bool dfsa_bringQubitIntoShard(StateVector& psi, Nat logicalQubit, const NatArray& alsoUsed = {}) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
     if (psi.where[logicalQubit] < L) return true;
     if (!(dfsa_detail::lazyLayoutEnabled() && StateVector::gateFusionEnabled())) return false;
     psi.flushGates();                                         // queued gates name index bits of the layout as it is now
     const Nat prefixBit = psi.where[logicalQubit];
-    const NatArray placed = dfsa_planRelocationOnLayout(psi.where, L, NatArray{prefixBit});
-    const Nat landing = placed[0];
+    const Nat landing = dfsa_pickEvictionBit(psi, alsoUsed);
     DFSA_CHECK(dfsa_xk_relocate(psi.handle, &landing, &prefixBit, 1));
     psi.noteSwapped(landing, prefixBit);
     return true;
@@ -119,6 +134,7 @@ static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMat
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
     dfsa_bringQubitIntoShard(psi, target);
+    psi.touch(target);
     target = psi.where[target];                               // the index bit that holds the qubit (layout.hpp)
     if (target < psi.logNumAmpsPerNode && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, {}, target, gate); return; }
     if (target < psi.logNumAmpsPerNode) local_statevector_oneTargGate(psi, target, gate);
@@ -127,7 +143,8 @@ inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, Am
 
 static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi, NatArray controls, Nat target, AmpMatrix gate) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
-    dfsa_bringQubitIntoShard(psi, target);
+    dfsa_bringQubitIntoShard(psi, target, controls);
+    psi.touch(target);                                        // (controls do not count: a control is just as good on a rank bit)
     controls = psi.physical(controls);
     target = psi.where[target];
     if (target < L && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, controls, target, gate); return; }

@@ -39,6 +39,9 @@ public:
     // lazy qubit layout (layout.hpp): where[q] = index bit currently holding logical qubit q; identity unless a gate left
     // its relocated targets in place. Anything that addresses amplitudes by index calls restoreLayout() first.
     NatArray where;
+    std::vector<unsigned long long> lastUse;      // per logical qubit: when a one-target gate last touched it (layout.hpp: which qubit a swap-in evicts)
+    unsigned long long useClock = 0;
+    void touch(Nat logicalQubit) { lastUse[logicalQubit] = ++useClock; }
     bool layoutIsIdentity() const;
     NatArray physical(const NatArray& logical) const;
     void noteSwapped(Nat posA, Nat posB);
@@ -107,7 +110,7 @@ public:
         setLocalAmps(mine);
     }
     void setHashAmps(unsigned long long seed) { resetLayout(); DFSA_CHECK(dfsa_state_init_hash(handle, seed)); }
-    void resetLayout() { gateQueue.clear(); std::iota(where.begin(), where.end(), Nat(0)); }      // the contents are about to be overwritten
+    void resetLayout() { gateQueue.clear(); std::iota(where.begin(), where.end(), Nat(0)); std::fill(lastUse.begin(), lastUse.end(), 0ULL); useClock = 0; }      // the contents are about to be overwritten
     void printAmps() {
         AmpArray all = getAllVecAmps();
         if (rank == 0)
@@ -163,6 +166,7 @@ protected:
         amps = DeviceAmpArray{handle, DFSA_AMPS};
         buffer = DeviceAmpArray{handle, DFSA_BUFFER};
         where.resize(isDensity ? 2 * qubits : qubits);
+        lastUse.resize(where.size());
         resetLayout();
         registry().push_back(this);
         dfsa_detail::flushAllStatesHook() = &StateVector::flushAllStates;
@@ -178,6 +182,7 @@ protected:
         rank = o.rank; numNodes = o.numNodes; logNumNodes = o.logNumNodes; numQubits = o.numQubits;
         numAmpsPerNode = o.numAmpsPerNode; logNumAmpsPerNode = o.logNumAmpsPerNode;
         amps = o.amps; buffer = o.buffer; handle = o.handle; where = std::move(o.where); gateQueue = std::move(o.gateQueue);
+        lastUse = std::move(o.lastUse); useClock = o.useClock;
         if (handle) registry().push_back(this);
         o.unregister();
         o.handle = nullptr; o.amps = DeviceAmpArray(); o.buffer = DeviceAmpArray();
