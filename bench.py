@@ -824,14 +824,14 @@ def run_product(args, world, rank, local_rank):
                "skipped": "host RAM too small to pin %d x %d GiB (MemAvailable %d GiB)" % (world, shard_bytes >> 30, mem_avail >> 30)}
     if ram_ok and lib.dfsa_host_alloc_pinned(C.c_uint64(shard_bytes), C.byref(host)) == 0:
         hp = C.cast(host, C.POINTER(C.c_double))
-        check(lib.dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))     # fill the host buffer (untimed)
+        st.download_shard_to(hp)                             # fill the host buffer (untimed)
         e2e_steps = max(1, min(args.steps, 2))
         job.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            check(lib.dfsa_state_upload(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))
+            st.upload_shard_from(hp)
             run_step()
-            check(lib.dfsa_state_download(st.handle, 0, C.c_uint64(0), C.c_uint64(shard_amps), hp))
+            st.download_shard_to(hp)                         # launches the deferred gates, restores index order, copies out
         job.barrier()
         e2e_s = job.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": gates_equiv(len(ops), nq, e2e_s), "unit": "gates/s", "h2d_bytes_per_step": shard_bytes * world,

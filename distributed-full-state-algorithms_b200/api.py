@@ -207,6 +207,16 @@ class DeviceState:
         host_lib().dfsa_host_state_resetLayout(self.p)
         check(device_lib().dfsa_state_upload(self.handle, 0, C.c_uint64(0), C.c_uint64(a.size), ptr))
 
+    def upload_shard_from(self, host_ptr):
+        """Overwrite this rank's whole shard from (pinned) host memory. The old contents are dead, so a lazily relabelled layout
+        is simply forgotten instead of being put back first."""
+        host_lib().dfsa_host_state_resetLayout(self.p)
+        check(device_lib().dfsa_state_upload(C.c_void_p(host_lib().dfsa_host_state_handle(self.p)), 0, C.c_uint64(0), C.c_uint64(self.num_amps_per_node), host_ptr))
+
+    def download_shard_to(self, host_ptr):
+        """This rank's shard, in index order, into (pinned) host memory."""
+        check(device_lib().dfsa_state_download(self.handle, 0, C.c_uint64(0), C.c_uint64(self.num_amps_per_node), host_ptr))
+
     def compare(self, other):
         """On-device two-sided comparison with another state of the same shape (collective):
         (max |delta component|, number of amplitudes that differ in value, max |component| of `other`)."""
