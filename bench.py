@@ -691,7 +691,10 @@ def run_product(args, world, rank, local_rank):
     step_ms = total_ms / args.steps
     value = gates_equiv(len(ops), nq, step_ms * 1e-3)
 
-    # ---- the same sweep gate by gate (fusion off): one kernel per gate, per-gate events -> the per-gate roofline numbers
+    # ---- the same sweep gate by gate (fusion off): one kernel per gate, per-gate events -> the per-gate roofline numbers.
+    #      Index order first: the default mode leaves rank-bit qubits swapped into the shard, and in this mode the gates on the top
+    #      log2 N qubits are meant to be the exchange gates.
+    st.restore_layout()
     dfsa.set_gate_fusion(False)
     pg_steps = max(2, min(args.steps, 5))
     run_step()
