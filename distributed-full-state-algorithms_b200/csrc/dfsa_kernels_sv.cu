@@ -361,12 +361,17 @@ int dfsaLaunchRelocate(dfsa_state* s, const double2* const* peers, const unsigne
     for (unsigned i = 0; i < k; i++) { sMask |= 1ULL << suffixPos[i]; rhoBits |= (uint64_t)((rho >> i) & 1u) << suffixPos[i]; }
     for (unsigned g = 0; g < 16; g++) table.shard[g] = g < (1u << k) ? peers[g] : nullptr;
     double2* out = s->arr[DFSA_BUFFER];
-    auto ld = [=] __device__(uint64_t j) {
+    // Item jj stands for output index j = jj ^ rhoBits: every rank walks the 2^k source shards starting with its OWN one. Walking
+    // them in the same order on every rank makes all 2^k ranks of a group pull from the same owner at the same time (its NVLink
+    // egress shared 2^k - 1 ways while the other owners idle): 72.8 ms instead of 19 for the 2-pair relocation of partialTrace at
+    // 4 GPUs (profiles/r02_bench_n4.json). With the XOR, at any time the readers of a group form a perfect matching.
+    auto ld = [=] __device__(uint64_t jj) {
+        const uint64_t j = jj ^ rhoBits;
         unsigned sigma = 0;
         for (unsigned i = 0; i < k; i++) sigma |= (unsigned)((j >> bits.pos[i]) & 1ULL) << i;
         return Amp1{table.shard[sigma][(j & ~sMask) | rhoBits]};
     };
-    auto st = [=] __device__(uint64_t j, const Amp1& v) { out[j] = v.a; };
+    auto st = [=] __device__(uint64_t jj, const Amp1& v) { out[jj ^ rhoBits] = v.a; };
     return launchStreamRemote<Amp1>(s->numAmps, ld, st);
 }
 
