@@ -790,7 +790,8 @@ def run_product(args, world, rank, local_rank):
                     "fp64_bound_ms_per_step": fp64_ms, "hbm_bound_ms_per_step": 32.0 * shard_amps * passes / (hbm_peak * 1e9) * 1e3,
                     "note": "algorithmic bytes of a fused pass = one read + one write of the shard (32*A), whatever the number of gates it carries; "
                             "time per launch = (step time - exchange gates at their roofline) / passes, measured with CUDA events around whole steps",
-                    "traffic": None}
+                    "traffic": (traffic["fused"]["dram_over_algorithmic"] * 32 * shard_amps) if traffic and "fused" in traffic else None,
+                    "traffic_note": ("NOT measured in this run: " + traffic["fused"].get("note", "")) if traffic and "fused" in traffic else None}
         step_roofline = {"bound_ms": max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms, "frac": (max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms) / step_ms,
                          "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + one suffix<->prefix swap (8*A bytes per direction at the measured NVLink rate) per gate whose qubit sat on a rank bit",
                          "speedup_over_per_gate_roofline": bound_step / step_ms}
