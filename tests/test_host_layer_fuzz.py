@@ -1,0 +1,85 @@
+"""CPU test of the drop-in host layer's decisions at 1...16 ranks (no GPU): random circuits through host/*.hpp -- local vs.
+exchange, partner ranks, relocation plans, the lazy qubit layout, swap-in of rank-bit qubits and which qubit it evicts, the
+deferred gate queue, layout restores, partialTrace's reordering -- running on tests/hostsim/dfsa_hostsim.cpp, a CPU stand-in
+that implements what include/dfsa_b200.h documents for each C-ABI entry (one forked process per rank, pairwise steps
+synchronised pairwise), compared with a dense ground truth that knows nothing about ranks (tests/hostsim/fuzz.cpp).
+
+The stand-in is test infrastructure: nothing in the package or bench.py links or loads it (checked below), and the GPU
+suite is what proves the kernels. What this adds is breadth the GPU box has no time for: thousands of random circuits per rank
+count, in every layout / fusion mode, where a wrong host decision shows up as a mismatch or as "rank r waits for rank p".
+"""
+import os
+import re
+import signal
+import subprocess
+
+import pytest
+
+import product
+
+HERE = os.path.join(product.ROOT, "tests", "hostsim")
+BIN = os.path.join(HERE, "_build", "fuzz")
+
+
+@pytest.fixture(scope="module")
+def fuzz_binary():
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    subprocess.run(["bash", os.path.join(HERE, "build.sh")], check=True, env=env, stdout=subprocess.DEVNULL)
+    return BIN
+
+
+def run_fuzz(binary, nodes, trials, seed, lazy, fuse):
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    env.update(DFSA_NP=str(nodes), DFSA_LAZY_LAYOUT=str(lazy), DFSA_FUSE_GATES=str(fuse))
+    proc = subprocess.Popen([binary, str(trials), str(seed)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)            # the rank processes it forked share its process group
+        out, err = proc.communicate()
+        pytest.fail("hostsim fuzz hung at %d ranks:\n%s" % (nodes, err[-3000:]))
+    return proc.returncode, out, err
+
+
+@pytest.mark.parametrize("lazy,fuse", [(1, 1), (0, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("nodes", [1, 2, 4, 8, 16])
+def test_random_circuits_through_the_host_layer_match_dense_truth(fuzz_binary, nodes, lazy, fuse):
+    trials = 600 if (lazy, fuse) == (1, 1) else 250
+    rc, out, err = run_fuzz(fuzz_binary, nodes, trials, seed=20 + nodes, lazy=lazy, fuse=fuse)
+    assert rc == 0, (out + err)[-3000:]
+    m = re.search(r"P=(\d+) lazy_layout=(\d) gate_fusion=(\d) trials=(\d+) comparisons=(\d+) failures=(\d+)", out)
+    assert m, out[-2000:]
+    assert (int(m.group(1)), int(m.group(2)), int(m.group(3)), int(m.group(4))) == (nodes, lazy, fuse, trials)
+    assert int(m.group(5)) >= trials * nodes and int(m.group(6)) == 0          # every rank compared at least once per trial
+    # the paths this test is about were taken (calls summed over ranks)
+    calls = {k: int(v) for k, v in re.findall(r" (\w+)=(\d+)", out.split("calls, all ranks:")[1])}
+    assert calls["k_manyTarg"] > 0 and calls["k_pauli"] > 0 and calls["k_partialTrace"] > 0 and calls["k_krausMap"] > 0
+    assert (calls["k_gateSequence"] > 0) == bool(fuse) and (calls["k_ctrlOneTarg"] > 0) == (not fuse)
+    if nodes > 1:
+        assert calls["xk_relocate"] > 0 and calls["xk_swapSuffixPrefix"] > 0 and calls["xk_exchangePauliCombine"] > 0
+        if not (lazy and fuse):        # with both on, one-target gates on rank-bit qubits swap the qubit in instead of exchanging shards
+            assert calls["xk_exchangeCombine"] > 0 and calls["xk_ctrlPrefixTarg"] > 0
+        else:
+            assert calls["xk_exchangeCombine"] == 0 and calls["xk_ctrlPrefixTarg"] == 0
+    if nodes > 2:
+        assert calls["x_exchange"] > 0                                         # rank-bit <-> rank-bit swaps (swapGate, or a layout restore)
+
+
+def test_the_stand_in_is_not_part_of_the_product():
+    """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
+    for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):
+        for f in files:
+            if f.endswith((".py", ".hpp", ".cpp", ".cu", ".cuh", ".h")):
+                with open(os.path.join(base, f), errors="ignore") as fh:
+                    assert "hostsim" not in fh.read(), os.path.join(base, f)
+    for f in ("bench.py", os.path.join("include", "dfsa_b200.h")):
+        with open(os.path.join(product.ROOT, f)) as fh:
+            assert "hostsim" not in fh.read(), f
+    host_lib = os.path.join(product.ROOT, "distributed-full-state-algorithms_b200", "libdfsa_host.so")
+    if os.path.exists(host_lib):
+        needed = subprocess.run(["readelf", "-d", host_lib], capture_output=True, text=True).stdout
+        assert "libdfsa_b200.so" in needed and "hostsim" not in needed
