@@ -545,6 +545,65 @@ def parity_selfcheck(job):
             "cases": results}
 
 
+def relocation_cost(num_pairs, shard_amps):
+    """One relocation step of `num_pairs` disjoint (suffix bit, rank bit) pairs (dfsa_xk_relocate): an out-of-place pass over the shard
+    that gathers from the 2^k shards of the rank's group -- (HBM bytes, NVLink bytes per direction, flop)."""
+    return (32.0 * shard_amps, (1.0 - 0.5 ** num_pairs) * 16.0 * shard_amps, 0.0)
+
+
+def fused_plan_summary(steps, L, count_passes):
+    """Pure part of the fused-step accounting: from the flush plan (api.plan_flush format) the relocation steps (pairs each), the
+    number of passes over HBM (count_passes(gates) per run of gates) and a short description."""
+    relocation_pairs, passes, summary = [], 0, []
+    for kind, body in steps:
+        if kind == "relocate":
+            relocation_pairs.append(len(body))
+            summary.append("relocate %d pair(s) %s" % (len(body), body))
+        else:
+            p = count_passes([(t, [c for c in range(L) if (mask >> c) & 1]) for t, mask in body])
+            passes += p
+            summary.append("%d gates in %d pass(es)" % (len(body), p))
+    return relocation_pairs, passes, summary
+
+
+def fused_accounting(plans, ops, lib, L, check):
+    """The flush plans the host layer reported for the timed steps (api.plan_pending_flush, taken just before every flush) -> per-step
+    relocation steps and passes over HBM. Never raises: a failure of the accounting must not cost the measurement (it is reported
+    in the line instead)."""
+    class G(C.Structure):
+        _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
+
+    def count_passes(segment):
+        """passes over HBM the library makes for a run of (index-bit target, index-bit suffix controls) gates"""
+        if not segment:
+            return 0
+        arr = (G * len(segment))()
+        for i, (t, ctrls) in enumerate(segment):
+            arr[i].target = t
+            arr[i].ctrlMask = sum(1 << c for c in ctrls if c < L)
+        nb = C.c_uint()
+        scratch = [(C.c_uint32 * max(1, 11 * len(segment)))() for _ in range(5)]
+        check(lib.dfsa_plan_gateSequence(arr, len(segment), L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
+        return nb.value
+
+    shard_amps = float(1 << L)
+    pairs = sum((shard_amps / 2.0) / (1 << len([] if op[0] == "sv_oneTargGate" else op[1])) for op in ops)     # averaged over ranks for rank-bit controls
+    out = {"relocation_pairs": [], "passes": [], "pairs": pairs, "summary": [], "error": None}
+    for plan in plans or []:
+        if isinstance(plan, str):
+            out["error"] = plan
+            continue
+        try:
+            rel, passes, summary = fused_plan_summary(plan, L, count_passes)
+        except Exception as e:                               # noqa: BLE001 -- reported, not fatal
+            out["error"] = "fused_plan_summary failed: %r" % (e,)
+            continue
+        out["relocation_pairs"].append(rel)
+        out["passes"].append(passes)
+        out["summary"].append(summary)
+    return out
+
+
 def run_config(job, name, peaks, reps, dm_qubits=None):
     """One BASELINE config: per-op device times (max over ranks) and roofline fractions."""
     import cases
@@ -671,13 +730,20 @@ def run_product(args, world, rank, local_rank):
     #      the one-target gates of a step and launches them as a few shared passes over HBM when the step is flushed.
     fusion = dfsa.gate_fusion_enabled()
 
-    def timed_steps(steps, per_gate=None):
+    def timed_steps(steps, per_gate=None, plans=None):
         e0, e1 = job.event(), job.event()
         launches0 = lib.dfsa_launch_count()
         job.barrier()
         job.record(e0)
         for s_ in range(steps):
             run_step(per_gate[s_] if per_gate else None)
+            if plans is not None:
+                # what this flush is about to do (host-only, microseconds): relocation steps and runs of gates, for the roofline
+                try:
+                    plans.append(st.plan_pending_flush()[0] if st.pending_gates() == len(ops) else
+                                 "%d of %d gates pending before the flush: plan not taken" % (st.pending_gates(), len(ops)))
+                except Exception as e:                       # noqa: BLE001 -- the accounting must not cost the measurement
+                    plans.append("plan_pending_flush failed: %r" % (e,))
             st.flush()                                       # a step ends with its gates launched (no fusing across steps)
         job.record(e1)
         job.barrier()
@@ -686,7 +752,8 @@ def run_product(args, world, rank, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    total_ms, launches = timed_steps(args.steps)
+    flush_plans = [] if fusion else None
+    total_ms, launches = timed_steps(args.steps, plans=flush_plans)
     clocks = sampler.stop() if rank == 0 else None
     step_ms = total_ms / args.steps
     value = gates_equiv(len(ops), nq, step_ms * 1e-3)
@@ -745,55 +812,35 @@ def run_product(args, world, rank, local_rank):
     # roofline of the dominant kernel of the timed region
     if fusion:
         # fused passes: what must cross HBM for a pass is one read and one write of the shard, however many gates it carries;
-        # the FP64 work of its gates (16 FMA per touched pair) is the other bound
-        # In this mode a gate whose qubit sits on a rank bit first swaps it into the shard (8*A bytes per direction, the layout
-        # remembers it) and is then a local gate like the others; which gates that hits depends on the layout the previous
-        # step left behind, so one untimed step is walked to count them.
-        class G(C.Structure):
-            _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
-
-        def plan_passes(segment):
-            """passes over HBM the library makes for a run of (index-bit target, index-bit controls) gates"""
-            if not segment:
-                return 0
-            arr = (G * len(segment))()
-            for i, (t, ctrls) in enumerate(segment):
-                arr[i].target = t
-                arr[i].ctrlMask = sum(1 << c for c in ctrls if c < L)
-            nb = C.c_uint()
-            scratch = [(C.c_uint32 * max(1, 11 * len(segment)))() for _ in range(5)]
-            check(lib.dfsa_plan_gateSequence(arr, len(segment), L, scratch[0], scratch[1], scratch[2], scratch[3], scratch[4], C.byref(nb)))
-            return nb.value
-
-        relocations, passes, pairs, segment = 0, 0, 0.0, []
-        for op in ops:
-            tq = op[1] if op[0] == "sv_oneTargGate" else op[2]
-            ctrls = [] if op[0] == "sv_oneTargGate" else op[1]
-            if st.layout()[tq] >= L:                         # the call below swaps the qubit into the shard: the queue is flushed first
-                relocations += 1
-                passes += plan_passes(segment)
-                segment = []
-            cases.apply(st, op)
-            where = st.layout()
-            segment.append((where[tq], [where[c] for c in ctrls]))
-            pairs += (shard_amps / 2.0) / (1 << len(ctrls))     # averaged over ranks for rank-bit controls
-        passes += plan_passes(segment)
-        st.flush()
+        # the FP64 work of its gates (16 FMA per touched pair) is the other bound.
+        # In this mode gates on rank-bit qubits are queued like the others; when the step is flushed the host layer brings those
+        # qubits into the shard (one relocation step for all it can, host/layout.hpp planFlush) and the layout remembers it. Which
+        # gates that hits depends on the layout the previous step left behind, so the host layer was asked for the plan of every
+        # timed flush (exactly what flush() then did); the bound is computed from those plans, averaged over the timed steps.
+        fused_plan = fused_accounting(flush_plans, ops, lib, L, check)
         n = len(ops)
-        exch_ms = relocations * bound_ms([(32.0 * shard_amps, 8.0 * shard_amps, 0.0)], peaks)
-        local_ms = max(step_ms - exch_ms, 1e-9)            # exchange gates at their bound: a lower bound on what the passes took
+        planned = max(1, len(fused_plan["passes"]))
+        relocation_pairs = [m for step in fused_plan["relocation_pairs"] for m in step]
+        passes = max(1.0, sum(fused_plan["passes"]) / planned)                 # per step
+        exch_ms = sum(bound_ms([relocation_cost(m, shard_amps)], peaks) for m in relocation_pairs) / planned
+        local_ms = max(step_ms - exch_ms, 1e-9)            # relocations at their bound: a lower bound on what the passes took
         achieved = 32.0 * shard_amps * passes / (local_ms * 1e-3) / 1e9
-        fp64_ms = pairs * 32.0 / (FP64_PEAK_TFLOPS * 1e12) * 1e3
+        fp64_ms = fused_plan["pairs"] * 32.0 / (FP64_PEAK_TFLOPS * 1e12) * 1e3
         roofline = {"bound": "hbm", "kernel": "fusedGateTileKernel (all one-target gates of a pass applied to 32 KiB tiles in shared memory)", "achieved": achieved,
                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "peak_source": peak_src, "algorithmic_bytes_per_launch": 32 * shard_amps,
-                    "avg_launch_ms": local_ms / passes, "passes_per_step": passes, "gates_in_passes": n, "relocations_per_step": relocations,
+                    "avg_launch_ms": local_ms / passes, "passes_per_step": passes, "gates_in_passes": n, "relocations_per_step": len(relocation_pairs) / planned,
+                    "passes_by_step": fused_plan["passes"], "relocation_pairs_by_step": fused_plan["relocation_pairs"],
+                    "flush_plan_first_timed_step": fused_plan["summary"][0] if fused_plan["summary"] else None,
                     "fp64_bound_ms_per_step": fp64_ms, "hbm_bound_ms_per_step": 32.0 * shard_amps * passes / (hbm_peak * 1e9) * 1e3,
                     "note": "algorithmic bytes of a fused pass = one read + one write of the shard (32*A), whatever the number of gates it carries; "
-                            "time per launch = (step time - exchange gates at their roofline) / passes, measured with CUDA events around whole steps",
+                            "time per launch = (step time - relocations at their roofline) / passes, measured with CUDA events around whole steps",
                     "traffic": (traffic["fused"]["dram_over_algorithmic"] * 32 * shard_amps) if traffic and "fused" in traffic else None,
                     "traffic_note": ("NOT measured in this run: " + traffic["fused"].get("note", "")) if traffic and "fused" in traffic else None}
+        if fused_plan.get("error"):
+            roofline["accounting_error"] = fused_plan["error"]
         step_roofline = {"bound_ms": max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms, "frac": (max(roofline["hbm_bound_ms_per_step"], fp64_ms) + exch_ms) / step_ms,
-                         "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + one suffix<->prefix swap (8*A bytes per direction at the measured NVLink rate) per gate whose qubit sat on a rank bit",
+                         "how": "fused passes: max(passes x 32*A / HBM peak, FP64 work of all gates / FP64 peak) + one relocation step per group of rank-bit qubits brought into the shard "
+                                "(k pairs: (1 - 2^-k) * 16*A bytes per direction at the measured NVLink rate, 32*A bytes of HBM)",
                          "speedup_over_per_gate_roofline": bound_step / step_ms}
     else:
         roofline = dict(per_gate_mode["roofline"], peak_source=peak_src)

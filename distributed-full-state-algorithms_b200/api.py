@@ -107,6 +107,44 @@ def gate_fusion_enabled():
     return bool(host_lib().dfsa_host_gateFusionEnabled())
 
 
+class Gate1(C.Structure):
+    """dfsa_gate1 of include/dfsa_b200.h"""
+    _fields_ = [("matrix", C.c_double * 8), ("ctrlMask", C.c_uint64), ("target", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def _flush_plan_buffers(num_gates, num_bits):
+    return ((C.c_uint * (3 * (2 * num_gates + 1)))(), (C.c_uint * (8 * (num_gates + 1)))(), (C.c_uint * max(1, num_gates))(),
+            (C.c_uint64 * max(1, num_gates))(), (C.c_uint * max(1, num_bits))())
+
+
+def _decode_flush_plan(num_steps, steps, pairs, phys_target, phys_ctrl, where_out, num_bits):
+    """-> (steps, layout afterwards); a step is ("relocate", [(suffix bit, rank bit), ...]) or ("gates", [(index-bit target,
+    index-bit control mask), ...])"""
+    out = []
+    for i in range(num_steps):
+        kind, count, off = steps[3 * i], steps[3 * i + 1], steps[3 * i + 2]
+        if kind == 1:
+            out.append(("relocate", [(int(pairs[2 * (off + p)]), int(pairs[2 * (off + p) + 1])) for p in range(count)]))
+        else:
+            out.append(("gates", [(int(phys_target[g]), int(phys_ctrl[g])) for g in range(off, off + count)]))
+    return out, [int(where_out[q]) for q in range(num_bits)]
+
+
+def plan_flush(where, log_num_amps_per_node, last_use, gates):
+    """Host-only (no device): the steps StateVector::flushGates() (host/layout.hpp planFlush) takes for a queue of one-target gates
+    `gates` = [(logical target, [logical controls]), ...], given the layout `where` and the per-qubit last-use stamps."""
+    h = host_lib()
+    h.dfsa_host_plan_flush.restype = C.c_uint
+    n, bits = len(gates), len(where)
+    arr = (Gate1 * max(1, n))()
+    for i, (t, ctrls) in enumerate(gates):
+        arr[i].target = t
+        arr[i].ctrlMask = sum(1 << c for c in ctrls)
+    bufs = _flush_plan_buffers(n, bits)
+    cnt = h.dfsa_host_plan_flush((C.c_uint * bits)(*where), bits, int(log_num_amps_per_node), (C.c_ulonglong * bits)(*last_use), arr, n, *bufs)
+    return _decode_flush_plan(cnt, *bufs, bits)
+
+
 def _u32(xs):
     a = np.ascontiguousarray(np.asarray(xs).reshape(-1), dtype=np.uint32)
     n = int(a.size)
@@ -173,6 +211,14 @@ class DeviceState:
 
     def pending_gates(self):
         return int(host_lib().dfsa_host_state_pendingGates(self.p))
+
+    def plan_pending_flush(self):
+        """What the next flush() will do with the gates pending now: (steps, layout afterwards), steps as in plan_flush()."""
+        h = host_lib()
+        h.dfsa_host_state_planPendingFlush.restype = C.c_uint
+        bufs = _flush_plan_buffers(self.pending_gates(), self.total_bits)
+        cnt = h.dfsa_host_state_planPendingFlush(self.p, *bufs)
+        return _decode_flush_plan(cnt, *bufs, self.total_bits)
 
     # ---- state I/O
     def set_amps(self, amps):

@@ -150,6 +150,44 @@ unsigned dfsa_host_plan_restoreLayout(const unsigned* where, unsigned n, unsigne
     for (const auto& sw : plan.swaps) { out[3 * steps] = 1; out[3 * steps + 1] = sw.first; out[3 * steps + 2] = sw.second; steps++; }
     return steps;
 }
+// gate queue: the steps flushGates() takes for a queue of one-target gates (layout.hpp planFlush), given the layout and the
+// last-use stamps. logicalGates: target / ctrlMask name LOGICAL qubits. Outputs: steps = numSteps x {kind (0 = run of gates,
+// 1 = relocation), count (gates | pairs), offset (first gate | first pair)}; pairs = {suffix bit, rank bit} per relocation pair;
+// physTarget / physCtrlMask = every gate as the library gets it (index bits at the time it runs); whereOut = the layout afterwards.
+// Buffers: steps 3 * (2 * numGates + 1), pairs 8 * (numGates + 1), physTarget / physCtrlMask numGates, whereOut numBits.
+static unsigned writeFlushPlan(NatArray where, unsigned L, const std::vector<unsigned long long>& lastUse, const dfsa_gate1* gates, unsigned numGates,
+                               unsigned* steps, unsigned* pairs, unsigned* physTarget, unsigned long long* physCtrlMask, unsigned* whereOut) {
+    const std::vector<dfsa_detail::FlushStep> plan = dfsa_detail::planFlush(where, L, lastUse, gates, numGates);
+    unsigned numPairs = 0, n = 0;
+    for (const dfsa_detail::FlushStep& st : plan) {
+        if (st.relocation) {
+            steps[3 * n] = 1; steps[3 * n + 1] = unsigned(st.landing.size()); steps[3 * n + 2] = numPairs;
+            for (std::size_t p = 0; p < st.landing.size(); p++, numPairs++) {
+                pairs[2 * numPairs] = st.landing[p]; pairs[2 * numPairs + 1] = st.prefix[p];
+                dfsa_detail::relabel(where, st.landing[p], st.prefix[p]);
+            }
+        } else {
+            steps[3 * n] = 0; steps[3 * n + 1] = unsigned(st.count); steps[3 * n + 2] = unsigned(st.first);
+            for (std::size_t g = st.first; g < st.first + st.count; g++) {
+                const dfsa_gate1 phys = dfsa_detail::physicalGate(gates[g], where);
+                physTarget[g] = phys.target; physCtrlMask[g] = phys.ctrlMask;
+            }
+        }
+        n++;
+    }
+    for (std::size_t q = 0; q < where.size(); q++) whereOut[q] = where[q];
+    return n;
+}
+unsigned dfsa_host_plan_flush(const unsigned* where, unsigned numBits, unsigned L, const unsigned long long* lastUse, const dfsa_gate1* logicalGates, unsigned numGates,
+                              unsigned* steps, unsigned* pairs, unsigned* physTarget, unsigned long long* physCtrlMask, unsigned* whereOut) {
+    return writeFlushPlan(NatArray(where, where + numBits), L, std::vector<unsigned long long>(lastUse, lastUse + numBits), logicalGates, numGates,
+                          steps, pairs, physTarget, physCtrlMask, whereOut);
+}
+// ... for the gates a state has pending right now (what its next flushGates() will do); same buffers, sized with pendingGates
+unsigned dfsa_host_state_planPendingFlush(void* h, unsigned* steps, unsigned* pairs, unsigned* physTarget, unsigned long long* physCtrlMask, unsigned* whereOut) {
+    StateVector& s = sv(h);
+    return writeFlushPlan(s.where, unsigned(s.logNumAmpsPerNode), s.lastUse, s.gateQueue.data(), unsigned(s.gateQueue.size()), steps, pairs, physTarget, physCtrlMask, whereOut);
+}
 // sortedTargets: the ket targets, ascending; reorderedOut has 2n entries, remainingOut 2N-2n
 void dfsa_host_plan_partialTrace(unsigned N, unsigned L, const unsigned* sortedTargets, unsigned n, unsigned* reorderedOut, unsigned* remainingOut) {
     NatArray ext = toNats(sortedTargets, n);

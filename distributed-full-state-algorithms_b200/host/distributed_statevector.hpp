@@ -68,9 +68,11 @@ inline PauliPlan planPauli(Nat rank, Nat L, const NatArray& targets, const NatAr
 }
 }  // namespace dfsa_detail
 
-// oneTargGate / manyCtrlOneTargGate whose target sits on a suffix bit: deferred (states.hpp gateQueue) so that runs of such gates
-// share passes over HBM; `controls` and `target` are index bits. Controls on rank bits stay in the mask: the library drops the
-// gate on ranks that fail them (reference :92-93).
+// oneTargGate / manyCtrlOneTargGate are DEFERRED (states.hpp gateQueue) so that runs of such gates share passes over HBM; the
+// queue holds logical qubits, flushGates() (layout.hpp) translates them through the layout at launch time. Controls that end up
+// on rank bits stay in the mask: the library drops the gate on ranks that fail them (reference :92-93). With the lazy layout on,
+// a gate whose qubit sits on a rank bit is queued like any other -- flushGates() swaps the qubit into the shard (8*A bytes per
+// direction instead of the 16*A of the full-shard exchange, less when several qubits come in together) and the gate is local.
 namespace dfsa_detail {
 inline void enqueueOneTarg(StateVector& psi, const NatArray& controls, Nat target, const AmpMatrix& gate) {
     dfsa_gate1 g;
@@ -82,41 +84,11 @@ inline void enqueueOneTarg(StateVector& psi, const NatArray& controls, Nat targe
     psi.gateQueue.push_back(g);
     if (psi.gateQueue.size() >= 256) psi.flushGates();
 }
+// deferred unless fusion is off; a rank-bit qubit can only be deferred if the layout may change under it
+inline bool deferOneTarg(const StateVector& psi, Nat target) {
+    return StateVector::gateFusionEnabled() && (psi.where[target] < psi.logNumAmpsPerNode || lazyLayoutEnabled());
+}
 }  // namespace dfsa_detail
-
-// With the lazy layout and the gate queue both on, a one-target gate whose qubit sits on a RANK bit is not applied through a
-// full-shard exchange (reference :26-38, 16*A bytes per direction): the qubit is swapped into the shard (8*A bytes per
-// direction, layout.hpp remembers it), the gate is queued like any local gate, and every later gate on that qubit is local
-// too. Never more NVLink bytes than the exchange (8*A now + at most 8*A when the layout is restored), usually far fewer.
-// Which suffix bit it lands on = which qubit is evicted onto the rank bit. Circuits are mostly layers that visit the qubits in
-// the same order again and again; for such scans the qubit to evict is the one used MOST recently (its next use is the
-// furthest away -- Belady's choice; evicting the least recently used one, or sending displaced qubits straight home, makes
-// every layer pay two swaps per rank bit instead of one). "Used" means used as a TARGET: controls work from rank bits too.
-// Qubits the current gate itself uses are not evicted. For bench.py's sweep this gives log2(P) swaps per layer, the minimum.
-static inline Nat dfsa_pickEvictionBit(const StateVector& psi, const NatArray& busyLogical) {
-    const Nat L = Nat(psi.logNumAmpsPerNode);
-    int best = -1;
-    unsigned long long bestUse = 0;
-    for (Nat q = 0; q < Nat(psi.where.size()); q++) {
-        const Nat pos = psi.where[q];
-        if (pos >= L || std::find(busyLogical.begin(), busyLogical.end(), q) != busyLogical.end()) continue;
-        if (best < 0 || psi.lastUse[q] > bestUse || (psi.lastUse[q] == bestUse && pos > Nat(best))) { best = int(pos); bestUse = psi.lastUse[q]; }
-    }
-    if (best < 0) best = int(L) - 1;                          // every suffix qubit is busy (a gate controlled on all of them)
-    return Nat(best);
-}
-
-static inline bool dfsa_bringQubitIntoShard(StateVector& psi, Nat logicalQubit, const NatArray& alsoUsed = {}) {
-    const Nat L = Nat(psi.logNumAmpsPerNode);
-    if (psi.where[logicalQubit] < L) return true;
-    if (!(dfsa_detail::lazyLayoutEnabled() && StateVector::gateFusionEnabled())) return false;
-    psi.flushGates();                                         // queued gates name index bits of the layout as it is now
-    const Nat prefixBit = psi.where[logicalQubit];
-    const Nat landing = dfsa_pickEvictionBit(psi, alsoUsed);
-    DFSA_CHECK(dfsa_xk_relocate(psi.handle, &landing, &prefixBit, 1));
-    psi.noteSwapped(landing, prefixBit);
-    return true;
-}
 
 // A 2x2 gate on a prefix qubit mixes this shard with the partner's: amps = g[b][b]*amps + g[b][!b]*partner
 static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMatrix& gate) {
@@ -133,22 +105,21 @@ static inline void dfsa_prefixOneTarg(StateVector& psi, Nat target, const AmpMat
 }
 
 inline void distributed_statevector_oneTargGate(StateVector& psi, Nat target, AmpMatrix gate) {
-    dfsa_bringQubitIntoShard(psi, target);
     psi.touch(target);
+    if (dfsa_detail::deferOneTarg(psi, target)) { dfsa_detail::enqueueOneTarg(psi, {}, target, gate); return; }
+    psi.flushGates();
     target = psi.where[target];                               // the index bit that holds the qubit (layout.hpp)
-    if (target < psi.logNumAmpsPerNode && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, {}, target, gate); return; }
     if (target < psi.logNumAmpsPerNode) local_statevector_oneTargGate(psi, target, gate);
     else dfsa_prefixOneTarg(psi, target, gate);
 }
 
 static inline void distributed_statevector_manyCtrlOneTargGate(StateVector& psi, NatArray controls, Nat target, AmpMatrix gate) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
-    dfsa_bringQubitIntoShard(psi, target, controls);
     psi.touch(target);                                        // (controls do not count: a control is just as good on a rank bit)
+    if (dfsa_detail::deferOneTarg(psi, target)) { dfsa_detail::enqueueOneTarg(psi, controls, target, gate); return; }
+    psi.flushGates();
     controls = psi.physical(controls);
     target = psi.where[target];
-    if (target < L && StateVector::gateFusionEnabled()) { dfsa_detail::enqueueOneTarg(psi, controls, target, gate); return; }
-    psi.flushGates();
     NatArray suffixCtrls;
     const dfsa_detail::ExchangePlan plan = dfsa_detail::planCtrlOneTarg(psi.rank, L, controls, target, &suffixCtrls);
     switch (plan.kind) {

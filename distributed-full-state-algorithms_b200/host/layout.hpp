@@ -132,6 +132,92 @@ inline RestorePlan planRestore(NatArray where, Nat L) {
 // index bits posA and posB have just traded contents (or are declared to have, for a pure relabelling)
 inline void StateVector::noteSwapped(Nat posA, Nat posB) { dfsa_detail::relabel(where, posA, posB); }
 
+// ---- launching the deferred one-target gates (states.hpp gateQueue) --------------------------------------------------------
+// A queued gate whose qubit sits on a RANK bit is not applied through a full-shard exchange (reference
+// distributed_statevector.hpp:26-38, 16*A bytes per direction): the qubit is swapped into the shard, the layout remembers it,
+// and the gate -- like every later gate on that qubit -- is a local one. Because the gates are deferred, the swap-in is planned
+// with the whole queue in view (planFlush, a pure function; tests/test_flush_plan.py and the host-layer fuzz under tests/):
+//   * gates run in call order; a run of gates whose targets all sit on suffix bits is one dfsa_k_gateSequence call;
+//   * when the next gate targets a rank-bit qubit, ONE relocation step brings in that qubit and every other rank-bit qubit the
+//     rest of the queue targets, as long as the suffix qubit each one evicts is not needed sooner than it is: k pairs cost
+//     (1 - 2^-k) * 16A bytes per direction in one pass instead of k * 8A in k passes (dfsa_xk_relocate);
+//   * the qubits evicted onto the rank bits are those whose next turn as a TARGET is furthest away (Belady's choice; controls do
+//     not count, they work from rank bits too): never again in this queue first, and among those the most recently targeted one
+//     -- circuits are mostly layers that visit the qubits in the same order again and again, so the most recent target is the
+//     one whose next turn is furthest away. bench.py's sweep pays one log2(P)-pair relocation per layer.
+namespace dfsa_detail {
+struct FlushStep {
+    bool relocation = false;
+    NatArray landing, prefix;              // relocation: (suffix bit, rank bit) index-bit pairs of one dfsa_xk_relocate call
+    std::size_t first = 0, count = 0;      // gate run: queue entries [first, first + count)
+};
+
+inline std::vector<FlushStep> planFlush(NatArray where, Nat L, const std::vector<unsigned long long>& lastUse, const dfsa_gate1* queue, std::size_t n) {
+    std::vector<FlushStep> plan;
+    const Nat bits = Nat(where.size());
+    const std::size_t never = ~std::size_t(0);
+    std::size_t i = 0;
+    while (i < n) {
+        std::size_t j = i;
+        while (j < n && where[queue[j].target] < L) j++;
+        if (j > i) { FlushStep run; run.first = i; run.count = j - i; plan.push_back(run); }
+        if (j == n) break;
+        // queue[j] targets a qubit that sits on a rank bit
+        std::vector<std::size_t> nextUse(bits, never);
+        for (std::size_t g = n; g-- > j;) nextUse[queue[g].target] = g;
+        NatArray wanted, victims;
+        for (Nat q = 0; q < bits; q++) {
+            if (where[q] >= L && nextUse[q] != never) wanted.push_back(q);
+            if (where[q] < L) victims.push_back(q);
+        }
+        std::sort(wanted.begin(), wanted.end(), [&](Nat a, Nat b) { return nextUse[a] < nextUse[b]; });
+        std::sort(victims.begin(), victims.end(), [&](Nat a, Nat b) {
+            if (nextUse[a] != nextUse[b]) return nextUse[a] > nextUse[b];
+            if (lastUse[a] != lastUse[b]) return lastUse[a] > lastUse[b];
+            return where[a] > where[b];
+        });
+        FlushStep reloc;
+        reloc.relocation = true;
+        for (std::size_t w = 0; w < wanted.size() && w < victims.size() && w < 4; w++) {
+            if (w > 0 && !(nextUse[victims[w]] > nextUse[wanted[w]])) break;      // it would evict a qubit that is needed sooner
+            reloc.landing.push_back(where[victims[w]]);
+            reloc.prefix.push_back(where[wanted[w]]);
+        }
+        for (std::size_t p = 0; p < reloc.landing.size(); p++) relabel(where, reloc.landing[p], reloc.prefix[p]);
+        plan.push_back(reloc);
+        i = j;
+    }
+    return plan;
+}
+
+// a queued gate (logical qubits) as the library wants it (index bits), given the layout at the time it runs
+inline dfsa_gate1 physicalGate(const dfsa_gate1& logical, const NatArray& where) {
+    dfsa_gate1 g = logical;
+    g.target = where[logical.target];
+    g.ctrlMask = 0;
+    for (Nat q = 0; q < Nat(where.size()); q++) if ((logical.ctrlMask >> q) & 1ULL) g.ctrlMask |= 1ULL << where[q];
+    return g;
+}
+}  // namespace dfsa_detail
+
+inline void StateVector::flushGates() {
+    if (gateQueue.empty()) return;
+    std::vector<dfsa_gate1> queue;
+    queue.swap(gateQueue);                           // (nothing below enqueues; the member is empty from here on whatever happens)
+    const std::vector<dfsa_detail::FlushStep> plan = dfsa_detail::planFlush(where, Nat(logNumAmpsPerNode), lastUse, queue.data(), queue.size());
+    std::vector<dfsa_gate1> run;
+    for (const dfsa_detail::FlushStep& step : plan) {
+        if (step.relocation) {
+            DFSA_CHECK(dfsa_xk_relocate(handle, step.landing.data(), step.prefix.data(), Nat(step.landing.size())));
+            for (std::size_t p = 0; p < step.landing.size(); p++) noteSwapped(step.landing[p], step.prefix[p]);
+            continue;
+        }
+        run.clear();
+        for (std::size_t g = step.first; g < step.first + step.count; g++) run.push_back(dfsa_detail::physicalGate(queue[g], where));
+        DFSA_CHECK(dfsa_k_gateSequence(handle, run.data(), Nat(run.size())));
+    }
+}
+
 inline void StateVector::restoreLayout() {
     flushGates();                                    // whoever asks for index order is about to look at the amplitudes
     if (layoutIsIdentity()) return;

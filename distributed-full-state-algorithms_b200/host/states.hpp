@@ -48,15 +48,13 @@ public:
     Nat numDisplacedAcrossShardBoundary() const;
     void restoreLayout();
 
-    // Deferred one-target gates (oneTargGate / manyCtrlOneTargGate on suffix bits, in call order, on INDEX bits): launched
-    // together by flushGates() so that consecutive gates share passes over HBM (dfsa_k_gateSequence) -- before any other
-    // kind of operation on this state, before anything reads it, and at comm_synch(). DFSA_FUSE_GATES=0: never deferred.
+    // Deferred one-target gates (oneTargGate / manyCtrlOneTargGate, in call order; `target` and `ctrlMask` name LOGICAL qubits):
+    // launched together by flushGates() so that consecutive gates share passes over HBM (dfsa_k_gateSequence) -- before any
+    // other kind of operation on this state, before anything reads it, and at comm_synch(). flushGates() (layout.hpp) translates
+    // them through the layout and, with the lazy layout on, brings the rank-bit qubits they target into the shard with as few
+    // relocation steps as the queue allows (planFlush). DFSA_FUSE_GATES=0: never deferred.
     std::vector<dfsa_gate1> gateQueue;
-    void flushGates() {
-        if (gateQueue.empty()) return;
-        DFSA_CHECK(dfsa_k_gateSequence(handle, gateQueue.data(), Nat(gateQueue.size())));
-        gateQueue.clear();
-    }
+    void flushGates();
     static bool& gateFusionEnabled() {
         static bool on = [] { const char* e = std::getenv("DFSA_FUSE_GATES"); return !(e && std::atoi(e) == 0); }();
         return on;

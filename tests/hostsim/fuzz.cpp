@@ -135,8 +135,23 @@ std::string show(const NatArray& a) { std::string s = "["; for (Nat x : a) s += 
 void svOps(Rng& rng, StateVector& psi, AmpArray& truth, Nat n, Nat numOps, Stats& st, std::string& log, const std::string& tag) {
     const Nat L = Nat(psi.logNumAmpsPerNode);
     for (Nat op = 0; op < numOps; op++) {
-        const Nat kind = rng.below(10);
-        if (kind == 0) {
+        const Nat kind = rng.below(11);
+        if (kind == 10) {
+            // a burst of one-target gates (what the gate queue and its swap-in planning are for): either a sweep over consecutive
+            // qubits starting anywhere, or random targets; each gate with 0-3 controls
+            const Nat count = rng.between(3, 40), start = rng.below(n);
+            const bool sweep = rng.below(2) == 0;
+            log += sweep ? " sweep(" + std::to_string(start) + "x" + std::to_string(count) + ")" : " burst(" + std::to_string(count) + ")";
+            for (Nat b = 0; b < count; b++) {
+                const Nat t = sweep ? (start + b / 2) % n : rng.below(n);
+                NatArray ctrls;
+                for (Nat q : rng.distinct(rng.below(std::min<Nat>(4, n)), n)) if (q != t) ctrls.push_back(q);
+                const AmpMatrix g = randomUnitary(rng, 2);
+                if (ctrls.empty()) distributed_statevector_oneTargGate(psi, t, g);
+                else distributed_statevector_manyCtrlOneTargGate(psi, ctrls, t, g);
+                truthCtrlOneTarg(truth, ctrls, t, g);
+            }
+        } else if (kind == 0) {
             const Nat t = rng.below(n);
             const AmpMatrix g = randomUnitary(rng, 2);
             log += " one(" + std::to_string(t) + ")";

@@ -46,3 +46,28 @@ def test_inverse_ops_and_workloads_are_deterministic():
         a = bench.config_workload(name, 8)
         b = bench.config_workload(name, 8)
         assert a[1] == b[1] and len(a[2]) == len(b[2]) and [o[0] for o in a[2]] == [o[0] for o in b[2]]
+
+
+def test_fused_step_accounting_is_a_pure_function_of_the_flush_plan():
+    A = float(1 << 32)
+    assert bench.relocation_cost(1, A) == (32 * A, 8 * A, 0.0)
+    assert bench.relocation_cost(3, A) == (32 * A, 14 * A, 0.0)
+    plan = [("gates", [(0, 0), (1, 0b100), (2, 1 << 40)]), ("relocate", [(31, 32), (30, 33)]), ("gates", [(31, 0)])]
+    seen = []
+
+    def count_passes(segment):
+        seen.append(segment)
+        return 2 if len(segment) > 1 else 1
+
+    rel, passes, summary = bench.fused_plan_summary(plan, 32, count_passes)
+    assert rel == [2] and passes == 3 and len(summary) == 3
+    assert seen == [[(0, []), (1, [2]), (2, [])], [(31, [])]]              # controls on rank bits do not reach the pass planner
+    # the accounting never raises: a broken plan entry becomes an error string, the decodable steps still count
+    class Lib:
+        @staticmethod
+        def dfsa_plan_gateSequence(*a):
+            raise RuntimeError("no library here")
+    out = bench.fused_accounting([plan, "plan_pending_flush failed: boom"], [("sv_oneTargGate", 0, None)], Lib, 32, lambda rc: None)
+    assert out["error"] and out["passes"] == [] and out["relocation_pairs"] == []
+    out = bench.fused_accounting(None, [("sv_oneTargGate", 0, None), ("sv_manyCtrlOneTargGate", [1, 2], 0, None)], Lib, 32, lambda rc: None)
+    assert out["pairs"] == A / 2 + A / 8 and out["error"] is None
