@@ -8,9 +8,14 @@ root="$(cd "$here/../.." && pwd)"
 pkg="$root/distributed-full-state-algorithms_b200"
 out="$here/_build"
 mkdir -p "$out"
-if [ -x "$out/fuzz" ] && [ -z "$(find "$pkg/host" "$root/include" "$here/fuzz.cpp" "$here/dfsa_hostsim.cpp" "$here/build.sh" -newer "$out/fuzz" -type f 2>/dev/null | head -1)" ]; then
-    exit 0
-fi
 unset CC CXX
-g++ -std=c++17 -O2 -Wall -I"$pkg/host" -I"$root/include" "$here/fuzz.cpp" "$here/dfsa_hostsim.cpp" -o "$out/fuzz"
-echo "hostsim: built $out/fuzz"
+if [ ! -x "$out/fuzz" ] || [ -n "$(find "$pkg/host" "$root/include" "$here/fuzz.cpp" "$here/dfsa_hostsim.cpp" "$here/build.sh" -newer "$out/fuzz" -type f 2>/dev/null | head -1)" ]; then
+    g++ -std=c++17 -O2 -Wall -I"$pkg/host" -I"$root/include" "$here/fuzz.cpp" "$here/dfsa_hostsim.cpp" -o "$out/fuzz"
+    echo "hostsim: built $out/fuzz"
+fi
+# the extern "C" face of the host layer (host/dfsa_host_capi.cpp, what ctypes users and bench.py call) on the stand-in: lets a CPU
+# test drive the per-state entry points that need a live StateVector (tests/hostsim/capi_on_standin.py)
+if [ ! -f "$out/libdfsa_host_on_standin.so" ] || [ -n "$(find "$pkg/host" "$root/include" "$here/dfsa_hostsim.cpp" "$here/build.sh" -newer "$out/libdfsa_host_on_standin.so" -type f 2>/dev/null | head -1)" ]; then
+    g++ -std=c++17 -O2 -Wall -fPIC -shared -I"$pkg/host" -I"$root/include" "$pkg/host/dfsa_host_capi.cpp" "$here/dfsa_hostsim.cpp" -o "$out/libdfsa_host_on_standin.so"
+    echo "hostsim: built $out/libdfsa_host_on_standin.so"
+fi

@@ -69,6 +69,26 @@ def test_random_circuits_through_the_host_layer_match_dense_truth(fuzz_binary, n
         assert calls["x_exchange"] > 0                                         # rank-bit <-> rank-bit swaps (swapGate, or a layout restore)
 
 
+@pytest.mark.parametrize("nodes", [1, 2, 4, 8])
+def test_host_c_api_on_the_stand_in(fuzz_binary, nodes):
+    """The extern "C" face of the host layer (what api.py / bench.py call through ctypes) with a live StateVector: pending gates,
+    the flush plan of a state (decoded by api.py's decoder, equal to the stateless planner's), layouts before / after the flush,
+    amplitudes against numpy -- tests/hostsim/capi_on_standin.py, every rank running the script."""
+    import sys
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES"):
+        env.pop(k, None)
+    env["DFSA_NP"] = str(nodes)
+    proc = subprocess.Popen([sys.executable, os.path.join(HERE, "capi_on_standin.py")], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("capi_on_standin.py hung at %d ranks:\n%s" % (nodes, err[-3000:]))
+    assert proc.returncode == 0 and "capi on stand-in: ok P=%d" % nodes in out, (out + err)[-3000:]
+
+
 def test_the_stand_in_is_not_part_of_the_product():
     """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
     for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):
