@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE (CPU): dry run of bench.py's product arm on the CPU stand-in of the C-ABI, at a toy size, at DFSA_NP ranks
+(the stand-in forks them; bench.py's Job is replaced by one without torch.distributed, everything else is bench.py's own code).
+
+Why: bench.py is what the driver runs on the GPU box, and its control flow (warm-up, timed steps taking the flush plan of every
+step, fused-pass accounting, per-gate mode, end-to-end leg, the JSON line) cannot otherwise be executed where there is no GPU. The
+NUMBERS of this run mean nothing (host time stamps instead of CUDA events, plain loops instead of kernels) and it is never
+reported anywhere; what the test checks is that the line is produced and has the shape the contract asks for.
+
+How: THIS script (not the product) points api.py's cached library handles at tests/hostsim/_build/libdfsa_host_on_standin.so;
+the host-only planners (dfsa_plan_*) still come from the real libdfsa_b200.so, which loads without a GPU. The product itself has
+no switch that would let it run on anything but the CUDA library.
+
+    [DFSA_NP=4] python tests/hostsim/bench_dry_run.py [qubits-per-rank=13]     -> the JSON line on stdout (rank 0)
+"""
+import ctypes as C
+import importlib
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+PKG = "distributed-full-state-algorithms_b200"
+
+
+class DeviceLibOnStandIn:
+    """attribute access like a ctypes.CDLL: host-only planners from the real library, everything else from the stand-in"""
+
+    def __init__(self, standin, real):
+        self._standin, self._real = standin, real
+
+    def __getattr__(self, name):
+        return getattr(self._real if name.startswith("dfsa_plan_") else self._standin, name)
+
+
+def main():
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        os.environ.pop(k, None)
+    api = importlib.import_module(PKG + ".api")
+    standin = C.CDLL(os.path.join(HERE, "_build", "libdfsa_host_on_standin.so"), mode=C.RTLD_GLOBAL)
+    real = C.CDLL(os.path.join(ROOT, PKG, "libdfsa_b200.so"))
+    # the restypes api.device_lib() / api.host_lib() set on the real libraries
+    standin.dfsa_last_error.restype = C.c_char_p
+    standin.dfsa_version.restype = C.c_char_p
+    standin.dfsa_comm_transport.restype = C.c_char_p
+    standin.dfsa_stream_compute.restype = C.c_void_p
+    standin.dfsa_state_ptr.restype = C.c_void_p
+    standin.dfsa_state_ptr.argtypes = [C.c_void_p, C.c_int]
+    standin.dfsa_state_num_amps_per_node.restype = C.c_uint64
+    standin.dfsa_state_num_amps_per_node.argtypes = [C.c_void_p]
+    standin.dfsa_launch_count.restype = C.c_uint64
+    for name in ("dfsa_host_StateVector_new", "dfsa_host_DensityMatrix_new", "dfsa_host_dm_partialTrace", "dfsa_host_state_handle"):
+        getattr(standin, name).restype = C.c_void_p
+    standin.dfsa_host_state_numAmpsPerNode.restype = C.c_uint64
+    standin.dfsa_host_state_getNorm2.restype = C.c_double
+    standin.dfsa_host_comm_getRank.restype = C.c_uint
+    standin.dfsa_host_comm_getNumNodes.restype = C.c_uint
+    api._dev = DeviceLibOnStandIn(standin, real)
+    api._host = standin
+    import bench
+    api.comm_init()                                        # the stand-in forks the ranks here: from now on every rank runs this script
+    world, rank = api.comm_size(), api.comm_rank()
+
+    class DryJob(bench.Job):
+        """bench.Job without torch.distributed (NCCL, CUDA tensors): the reductions go through the stand-in"""
+
+        def __init__(self, world_, rank_, local_rank_):
+            self.world, self.rank, self.local_rank = world_, rank_, local_rank_
+            self.k = world_.bit_length() - 1
+            self.torch = self.dist = None
+            self.dfsa = importlib.import_module(PKG)
+            self.lib = self.dfsa.device_lib()
+            self.check = self.dfsa.api.check
+            self.lib.dfsa_comm_fused_active.restype = C.c_int
+
+        def max_over_ranks(self, v):
+            box = C.c_double(float(v))
+            standin.hostsim_allreduce_max(C.byref(box))
+            return box.value
+
+        def broadcast_obj(self, obj):
+            raise NotImplementedError("only the parity block needs it, and the dry run skips that block")
+
+        def close(self):
+            self.dfsa.comm_end()
+
+    bench.Job = DryJob
+    per_rank = int(sys.argv[1]) if len(sys.argv) > 1 else 13
+    args = types.SimpleNamespace(gpus=world, steps=2, warmup=1, impl="product", qubits=per_rank + world.bit_length() - 1,
+                                 no_cpu_baseline=True, skip_parity=False, skip_configs=True, per_gate=False)
+    # the parity block needs the oracle and every channel of the API: only the full-size self-check part of it is kept
+    bench.parity_selfcheck = lambda job: None
+    bench.run_product(args, world, rank, rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -134,6 +134,14 @@ inline uint64_t insertZeros(uint64_t x, std::vector<unsigned> sortedPos) {
     return x;
 }
 inline Amp amp2(const double v[2]) { return Amp(v[0], v[1]); }
+// synthetic state: any reproducible function of (seed, GLOBAL index) will do here -- the host layer never looks at the values
+inline Amp hashAmp(uint64_t seed, uint64_t globalIndex) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (globalIndex + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return Amp(double(z >> 40) / double(1 << 24) - 0.5, double((z >> 16) & 0xFFFFFF) / double(1 << 24) - 0.5);
+}
 inline int parity(uint64_t x) { return __builtin_parityll(x); }
 std::map<std::string, unsigned long long>& callCounts() { static std::map<std::string, unsigned long long> c; return c; }
 inline void touchOp(const char* entry) { if (g.ctl) g.ctl->opCount[g.rank].fetch_add(1); callCounts()[entry]++; }
@@ -216,6 +224,18 @@ int dfsa_x_allreduce_amp(double reim[2]) {
     return DFSA_OK;
 }
 
+// stand-in only (bench_dry_run.py's replacement for the torch.distributed max-reduce of bench.py's Job)
+int hostsim_allreduce_max(double* value) {
+    if (g.size == 1) return DFSA_OK;
+    g.ctl->reduce[g.rank][2] = *value;
+    barrierAll();
+    double m = g.ctl->reduce[0][2];
+    for (int r = 1; r < g.size; r++) m = std::max(m, g.ctl->reduce[r][2]);
+    barrierAll();
+    *value = m;
+    return DFSA_OK;
+}
+
 // ---- state storage ------------------------------------------------------------------------------------------------------
 int dfsa_state_create(int isDensity, unsigned numQubits, dfsa_state** out) {
     touchOp();
@@ -287,14 +307,7 @@ int dfsa_state_upload_all(dfsa_state* s, const double* hostAll) {
 int dfsa_state_init_zero(dfsa_state* s) { touchOp(); memset(static_cast<void*>(s->amps()), 0, s->numAmps * sizeof(Amp)); return DFSA_OK; }
 int dfsa_state_init_hash(dfsa_state* s, uint64_t seed) {
     touchOp();
-    // any reproducible function of (seed, GLOBAL index) will do here: the host layer never looks at the values
-    for (uint64_t j = 0; j < s->numAmps; j++) {
-        uint64_t z = seed + 0x9E3779B97F4A7C15ULL * ((s->rankShift() | j) + 1);
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-        z ^= z >> 31;
-        s->amps()[j] = Amp(double(z >> 40) / double(1 << 24) - 0.5, double((z >> 16) & 0xFFFFFF) / double(1 << 24) - 0.5);
-    }
+    for (uint64_t j = 0; j < s->numAmps; j++) s->amps()[j] = hashAmp(seed, s->rankShift() | j);
     return DFSA_OK;
 }
 int dfsa_state_init_plus(dfsa_state* s) {
@@ -339,7 +352,37 @@ int dfsa_state_compare(dfsa_state* a, dfsa_state* b, double* maxAbsDiff, uint64_
     if (maxAbsRef) *maxAbsRef = mr;
     return DFSA_OK;
 }
-int dfsa_state_compare_hash(dfsa_state*, uint64_t, double*, uint64_t*, double*) { setError("hostsim: not needed by the host layer"); return DFSA_ERR_UNSUPPORTED; }
+int dfsa_state_compare_hash(dfsa_state* s, uint64_t seed, double* maxAbsDiff, uint64_t* numUnequal, double* maxAbsRef) {
+    touchOp();
+    barrierAll();
+    double d = 0, mr = 0;
+    uint64_t ne = 0;
+    for (int r = 0; r < g.size; r++)
+        for (uint64_t j = 0; j < s->numAmps; j++) {
+            const Amp x = s->arr(r, DFSA_AMPS)[j], y = hashAmp(seed, (uint64_t(r) << s->logNumAmps) | j);
+            d = std::max(d, std::max(std::abs(x.real() - y.real()), std::abs(x.imag() - y.imag())));
+            mr = std::max(mr, std::max(std::abs(y.real()), std::abs(y.imag())));
+            ne += !(x.real() == y.real() && x.imag() == y.imag());
+        }
+    barrierAll();
+    if (maxAbsDiff) *maxAbsDiff = d;
+    if (numUnequal) *numUnequal = ne;
+    if (maxAbsRef) *maxAbsRef = mr;
+    return DFSA_OK;
+}
+
+// ---- measurement helpers of the C-ABI, so that bench.py's control flow can be dry-run on the CPU (tests/hostsim/bench_dry_run.py):
+//      "events" are host time stamps, the "launch count" counts C-ABI calls, "pinned" memory is malloc
+int dfsa_event_create(void** event) { *event = new double(0); return DFSA_OK; }
+int dfsa_event_record(void* event) { *static_cast<double*>(event) = now(); return DFSA_OK; }
+int dfsa_event_elapsed_ms(void* start, void* stop, double* ms) { *ms = std::max(1e-6, (*static_cast<double*>(stop) - *static_cast<double*>(start)) * 1e3); return DFSA_OK; }
+int dfsa_event_destroy(void* event) { delete static_cast<double*>(event); return DFSA_OK; }
+uint64_t dfsa_launch_count(void) { return g.ctl ? g.ctl->opCount[g.rank].load() : 0; }
+int dfsa_host_alloc_pinned(uint64_t bytes, void** out) { *out = malloc(bytes); return *out ? DFSA_OK : DFSA_ERR_CUDA; }
+int dfsa_host_free_pinned(void* ptr) { free(ptr); return DFSA_OK; }
+void* dfsa_stream_compute(void) { return nullptr; }
+int dfsa_comm_last_exchange_ms(double* ms) { *ms = -1.0; return DFSA_OK; }
+int dfsa_xk_measure_link(dfsa_state*, int, int, double*) { setError("hostsim: nothing to measure"); return DFSA_ERR_UNSUPPORTED; }
 
 // ---- pairwise exchange --------------------------------------------------------------------------------------------------
 int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWhich, uint64_t recvStart, uint64_t num, int pairRank) {

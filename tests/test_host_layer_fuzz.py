@@ -89,6 +89,43 @@ def test_host_c_api_on_the_stand_in(fuzz_binary, nodes):
     assert proc.returncode == 0 and "capi on stand-in: ok P=%d" % nodes in out, (out + err)[-3000:]
 
 
+@pytest.mark.parametrize("nodes", [1, 2, 8])
+def test_bench_product_arm_dry_run_on_the_stand_in(fuzz_binary, nodes):
+    """bench.py's own control flow (warm-up, self-check, timed steps taking the flush plan of every step, fused-pass accounting,
+    per-gate mode, exchange summary, end-to-end leg, the JSON line) executed on the CPU at a toy size -- tests/hostsim/
+    bench_dry_run.py. The numbers are meaningless and go nowhere; the line must exist, carry the contract's keys, pass its own
+    full-state self-check (sweep, then inverse, against the regenerated state) and account for the relocations it planned."""
+    import json
+    import sys
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES"):
+        env.pop(k, None)
+    env["DFSA_NP"] = str(nodes)
+    proc = subprocess.Popen([sys.executable, os.path.join(HERE, "bench_dry_run.py"), "12"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("bench_dry_run.py hung at %d ranks:\n%s" % (nodes, err[-3000:]))
+    assert proc.returncode == 0, (out + err)[-3000:]
+    lines = [ln for ln in out.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out[-2000:]
+    line = json.loads(lines[0])
+    k = nodes.bit_length() - 1
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "roofline", "step_roofline", "per_gate_mode", "e2e", "gpu_launches", "clocks", "selfcheck"):
+        assert key in line, key
+    assert line["n_gpus"] == nodes and line["config"]["qubits"] == 12 + k and line["config"]["gates_per_step"] == 2 * (12 + k)
+    assert line["selfcheck"]["ok"] and line["gate_fusion"] is True
+    roof = line["roofline"]
+    assert "accounting_error" not in roof and len(roof["passes_by_step"]) == line["steps"] and all(p >= 1 for p in roof["passes_by_step"])
+    for step in roof["relocation_pairs_by_step"]:
+        assert (len(step) >= 1) == (nodes > 1) and all(1 <= m <= max(k, 1) for m in step)
+    assert 0 < roof["frac"] and 0 < line["step_roofline"]["frac"] and line["e2e"]["h2d_bytes_per_step"] == 16 * (1 << (12 + k))
+    assert (line["exchange_gates"] is not None) == (nodes > 1)
+
+
 def test_the_stand_in_is_not_part_of_the_product():
     """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
     for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):
