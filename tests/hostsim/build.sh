@@ -19,3 +19,12 @@ if [ ! -f "$out/libdfsa_host_on_standin.so" ] || [ -n "$(find "$pkg/host" "$root
     g++ -std=c++17 -O2 -Wall -fPIC -shared -I"$pkg/host" -I"$root/include" "$pkg/host/dfsa_host_capi.cpp" "$here/dfsa_hostsim.cpp" -o "$out/libdfsa_host_on_standin.so"
     echo "hostsim: built $out/libdfsa_host_on_standin.so"
 fi
+# the reference's own Catch2 suite (the objects tests/catch_dropin/build.sh compiled against host/*.hpp) linked against the stand-in
+# instead of libdfsa_b200.so: its 20 cases then exercise the host layer's dispatch of every API function at up to 16 ranks on the CPU
+catch="$here/../catch_dropin/_build"
+if [ -f "$catch/tests.o" ] && [ -f "$catch/catch_amalgamated.o" ]; then
+    if [ ! -x "$out/catch_on_standin" ] || [ "$catch/tests.o" -nt "$out/catch_on_standin" ] || [ "$here/dfsa_hostsim.cpp" -nt "$out/catch_on_standin" ]; then
+        g++ -std=c++17 -O2 -I"$root/include" "$catch/tests.o" "$catch/catch_amalgamated.o" "$here/dfsa_hostsim.cpp" -o "$out/catch_on_standin"
+        echo "hostsim: built $out/catch_on_standin"
+    fi
+fi

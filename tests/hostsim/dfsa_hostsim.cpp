@@ -11,7 +11,7 @@
 // What it is NOT: it is not part of the product, is never built into or loaded by the package (libdfsa_b200.so /
 // libdfsa_host.so), and nothing under distributed-full-state-algorithms_b200/ or bench.py refers to it. The product has no CPU
 // path: without a CUDA device every entry of libdfsa_b200.so fails (tests/test_cabi_symbols.py). Only the fuzz binary of this
-// directory links it. Entries the fuzz does not need return DFSA_ERR_UNSUPPORTED.
+// directory links it. Entries the host layer never calls (staged building blocks) return DFSA_ERR_UNSUPPORTED.
 //
 // Pairwise operations synchronise PAIRWISE (a rank that fails a prefix control never enters them, reference
 // distributed_statevector.hpp:92-93), collective ones with a barrier over all ranks; every wait times out with a message, so a
@@ -486,10 +486,6 @@ int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, u
     return DFSA_OK;
 }
 
-int dfsa_xk_depol1Prefix(dfsa_state*, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_xk_dampingPrefix(dfsa_state*, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_xk_depol2Pair(dfsa_state*, unsigned, unsigned, unsigned, double, int, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_xk_depol2Quad(dfsa_state*, unsigned, unsigned, unsigned, unsigned, double, int, int, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
 
 // ---- rank-local kernels -------------------------------------------------------------------------------------------------
 static int applyCtrlOneTarg(dfsa_state* s, uint64_t localCtrlMask, unsigned target, const double gate[8]) {
@@ -633,9 +629,6 @@ int dfsa_k_twoQubitDephasing(dfsa_state* s, unsigned qb1, unsigned qb2, double p
     }
     return DFSA_OK;
 }
-int dfsa_k_oneQubitDepolarising(dfsa_state*, unsigned, double) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_k_twoQubitDepolarising(dfsa_state*, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_k_damping(dfsa_state*, unsigned, double) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
 // out[l] = sum_k in[l with k on `targets` and k on `pairTargets`], all traced bits rank-local   (local_densitymatrix.hpp:134-164)
 int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32_t* targets, const uint32_t* pairTargets, unsigned numTargets) {
     touchOp();
@@ -657,11 +650,145 @@ int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32_t* targets
     }
     return DFSA_OK;
 }
+}  // extern "C"
+
+// ---- the remaining channels and the expectation value, written against the GLOBAL Choi index (flat = 2^N col + row; bit q = ket bit
+// of qubit q, bit q + N = its bra bit) wherever the amplitude lives: an entry that needs other ranks' amplitudes reads them from the
+// arena between two barriers over all ranks (every rank makes these calls: the host layer never skips a rank for a channel).
+static Amp globalAmp(const dfsa_state* s, uint64_t i) { return s->arr(int(i >> s->logNumAmps), DFSA_AMPS)[i & (s->numAmps - 1)]; }
+
+template <class F>      // f(global index) -> new amplitude, from the OLD global state
+static int channelFromGlobal(dfsa_state* s, bool collective, F f) {
+    std::vector<Amp> out(s->numAmps);
+    if (collective) barrierAll();
+    for (uint64_t j = 0; j < s->numAmps; j++) out[j] = f(s->rankShift() | j);
+    if (collective) barrierAll();
+    memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
+    return DFSA_OK;
+}
+static bool braOnRankBit(const dfsa_state* s, unsigned qb) { return qb + s->numQubits >= s->logNumAmps; }
+
+// rho -> (1 - p) rho + p/3 (X rho X + Y rho Y + Z rho Z): coherences * (1 - 4p/3); populations mixed with 2p/3, 1 - 2p/3
+static int simDepol1(dfsa_state* s, unsigned qb, double p, bool collective) {
+    const unsigned N = s->numQubits;
+    return channelFromGlobal(s, collective, [=](uint64_t i) {
+        const Amp a = globalAmp(s, i);
+        if (((i >> qb) ^ (i >> (qb + N))) & 1ULL) return (1 - 4 * p / 3) * a;
+        return (1 - 2 * p / 3) * a + (2 * p / 3) * globalAmp(s, i ^ (1ULL << qb) ^ (1ULL << (qb + N)));
+    });
+}
+// amplitude damping: rho_00 += p rho_11; rho_11 *= 1 - p; coherences *= sqrt(1 - p)
+static int simDamping(dfsa_state* s, unsigned qb, double p, bool collective) {
+    const unsigned N = s->numQubits;
+    return channelFromGlobal(s, collective, [=](uint64_t i) {
+        const Amp a = globalAmp(s, i);
+        const unsigned ket = (i >> qb) & 1ULL, bra = (i >> (qb + N)) & 1ULL;
+        if (ket != bra) return std::sqrt(1 - p) * a;
+        if (ket) return (1 - p) * a;
+        return a + p * globalAmp(s, i | (1ULL << qb) | (1ULL << (qb + N)));
+    });
+}
+// keep * rho + (4p/15) I (x) Tr_2 rho on the two qubits; keep = 1 - 16p/15 is the depolarising channel (`corrected`), keep = 1 - 4p/5
+// on the populations is what the reference's LOCAL branch computes (local_densitymatrix.hpp:83-108)
+static int simDepol2(dfsa_state* s, unsigned q1, unsigned q2, double p, bool corrected, bool collective) {
+    const unsigned N = s->numQubits;
+    const uint64_t all = (1ULL << q1) | (1ULL << q2) | (1ULL << (q1 + N)) | (1ULL << (q2 + N));
+    return channelFromGlobal(s, collective, [=](uint64_t i) {
+        const Amp a = globalAmp(s, i);
+        const bool same = !((((i >> q1) ^ (i >> (q1 + N))) | ((i >> q2) ^ (i >> (q2 + N)))) & 1ULL);
+        if (!same) return (1 - 16 * p / 15) * a;
+        Amp sum(0, 0);
+        for (unsigned c = 0; c < 4; c++) {
+            uint64_t idx = i & ~all;
+            if (c & 1u) idx |= (1ULL << q1) | (1ULL << (q1 + N));
+            if (c & 2u) idx |= (1ULL << q2) | (1ULL << (q2 + N));
+            sum += globalAmp(s, idx);
+        }
+        return (corrected ? 1 - 16 * p / 15 : 1 - 4 * p / 5) * a + (4 * p / 15) * sum;
+    });
+}
+extern "C" {
+
+int dfsa_k_oneQubitDepolarising(dfsa_state* s, unsigned qb, double prob) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && qb < s->numQubits && !braOnRankBit(s, qb), "the local kernel needs a qubit whose bra bit is a suffix bit");
+    return simDepol1(s, qb, prob, false);
+}
+int dfsa_xk_depol1Prefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && qb < s->numQubits && braOnRankBit(s, qb), "needs a qubit whose bra bit is a rank bit");
+    const unsigned rankBit = qb + s->numQubits - s->logNumAmps;
+    SIM_REQUIRE(bit == ((unsigned(g.rank) >> rankBit) & 1u) && pairRank == (g.rank ^ (1 << rankBit)), "bit / pairRank do not belong to this rank and qubit");
+    return simDepol1(s, qb, prob, true);
+}
+int dfsa_k_damping(dfsa_state* s, unsigned qb, double prob) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && qb < s->numQubits && !braOnRankBit(s, qb), "the local kernel needs a qubit whose bra bit is a suffix bit");
+    return simDamping(s, qb, prob, false);
+}
+int dfsa_xk_dampingPrefix(dfsa_state* s, unsigned qb, unsigned bit, double prob, int pairRank) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && qb < s->numQubits && braOnRankBit(s, qb), "needs a qubit whose bra bit is a rank bit");
+    const unsigned rankBit = qb + s->numQubits - s->logNumAmps;
+    SIM_REQUIRE(bit == ((unsigned(g.rank) >> rankBit) & 1u) && pairRank == (g.rank ^ (1 << rankBit)), "bit / pairRank do not belong to this rank and qubit");
+    return simDamping(s, qb, prob, true);
+}
+int dfsa_k_twoQubitDepolarising(dfsa_state* s, unsigned qb1, unsigned qb2, double prob, int corrected) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && qb1 < s->numQubits && qb2 < s->numQubits && qb1 != qb2 && !braOnRankBit(s, qb1) && !braOnRankBit(s, qb2), "the local kernel needs suffix bra bits");
+    return simDepol2(s, qb1, qb2, prob, corrected != 0, false);
+}
+// the reference's formulas for these two branches (distributed_densitymatrix.hpp:146-237, with their read-after-write) are pinned
+// by tests/golden on the GPU; here only the true channel
+int dfsa_xk_depol2Pair(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit, double prob, int corrected, int pairRank) {
+    touchOp();
+    SIM_REQUIRE(corrected, "hostsim simulates the corrected channel only on the prefix branches");
+    SIM_REQUIRE(s && s->isDensity && qb1 < qb2 && qb2 < s->numQubits && !braOnRankBit(s, qb1) && braOnRankBit(s, qb2), "pair branch: qb1 suffix, qb2 prefix");
+    const unsigned rankBit = qb2 + s->numQubits - s->logNumAmps;
+    SIM_REQUIRE(bit == ((unsigned(g.rank) >> rankBit) & 1u) && pairRank == (g.rank ^ (1 << rankBit)), "bit / pairRank do not belong to this rank and qubit");
+    return simDepol2(s, qb1, qb2, prob, true, true);
+}
+int dfsa_xk_depol2Quad(dfsa_state* s, unsigned qb1, unsigned qb2, unsigned bit0, unsigned bit1, double prob, int corrected, int pairRank0, int pairRank1) {
+    touchOp();
+    SIM_REQUIRE(corrected, "hostsim simulates the corrected channel only on the prefix branches");
+    SIM_REQUIRE(s && s->isDensity && qb1 < qb2 && qb2 < s->numQubits && braOnRankBit(s, qb1) && braOnRankBit(s, qb2), "quad branch: both bra bits are rank bits");
+    const unsigned r0 = qb1 + s->numQubits - s->logNumAmps, r1 = qb2 + s->numQubits - s->logNumAmps;
+    SIM_REQUIRE(bit0 == ((unsigned(g.rank) >> r0) & 1u) && bit1 == ((unsigned(g.rank) >> r1) & 1u) && pairRank0 == (g.rank ^ (1 << r0)) && pairRank1 == (g.rank ^ (1 << r1)),
+                "bits / pairRanks do not belong to this rank and qubits");
+    return simDepol2(s, qb1, qb2, prob, true, true);
+}
+// this rank's part of sum_t coeff_t Tr(P_t rho) = sum_t coeff_t sum_i <row(i)| P_t |col(i)> rho_flat[i]; row = bra bits, col = ket bits
+// (misc.hpp:16-38). The host layer adds the parts up with comm_reduceAmp (*outIsGlobal = 0).
+int dfsa_k_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2]) {
+    touchOp();
+    SIM_REQUIRE(s && s->isDensity && coeffs && paulis && out, "arguments");
+    static const Amp mats[4][2][2] = {{{1, 0}, {0, 1}}, {{0, 1}, {1, 0}}, {{0, Amp(0, -1)}, {Amp(0, 1), 0}}, {{1, 0}, {0, -1}}};
+    const unsigned N = s->numQubits;
+    Amp total(0, 0);
+    for (unsigned t = 0; t < numTerms; t++) {
+        Amp termSum(0, 0);
+        for (uint64_t j = 0; j < s->numAmps; j++) {
+            const uint64_t i = s->rankShift() | j;
+            Amp elem(1, 0);
+            for (unsigned q = 0; q < N && elem != Amp(0, 0); q++) {
+                SIM_REQUIRE(paulis[t * N + q] < 4, "Pauli codes are 0..3");
+                elem *= mats[paulis[t * N + q]][(i >> (q + N)) & 1ULL][(i >> q) & 1ULL];
+            }
+            termSum += elem * s->amps()[j];
+        }
+        total += coeffs[t] * termSum;
+    }
+    out[0] = total.real();
+    out[1] = total.imag();
+    return DFSA_OK;
+}
+int dfsa_kx_expecPauliString(dfsa_state* s, const double* coeffs, unsigned numTerms, const uint32_t* paulis, double out[2], int* outIsGlobal) {
+    if (outIsGlobal) *outIsGlobal = 0;
+    return dfsa_k_expecPauliString(s, coeffs, numTerms, paulis, out);
+}
 int dfsa_k_depol1Combine(dfsa_state*, unsigned, unsigned, double) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
 int dfsa_k_depol2Pair(dfsa_state*, unsigned, unsigned, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
 int dfsa_k_depol2Quad(dfsa_state*, unsigned, unsigned, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
 int dfsa_k_dampingPrefix(dfsa_state*, unsigned, unsigned, double, int) { setError("hostsim: channel not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_k_expecPauliString(dfsa_state*, const double*, unsigned, const uint32_t*, double[2]) { setError("hostsim: not simulated"); return DFSA_ERR_UNSUPPORTED; }
-int dfsa_kx_expecPauliString(dfsa_state*, const double*, unsigned, const uint32_t*, double[2], int*) { setError("hostsim: not simulated"); return DFSA_ERR_UNSUPPORTED; }
 
 }  // extern "C"

@@ -126,6 +126,33 @@ def test_bench_product_arm_dry_run_on_the_stand_in(fuzz_binary, nodes):
     assert (line["exchange_gates"] is not None) == (nodes > 1)
 
 
+@pytest.mark.parametrize("nodes", [1, 2, 4, 8, 16])
+def test_reference_catch2_cases_pass_on_the_host_layer_over_the_stand_in(fuzz_binary, nodes):
+    """The reference's OWN 20 Catch2 cases (compiled against host/*.hpp by tests/catch_dropin/build.sh) linked against the CPU
+    stand-in instead of libdfsa_b200.so: every API function's host-side dispatch -- including the noise channels' prefix / suffix
+    branches, expecPauliString's reduction and partialTrace's relocation -- at up to 16 ranks, with this repo's two-sided 1e-12
+    comparator against the suite's dense Kraus-operator ground truth. (The kernels' own parity is the GPU run of the same suite,
+    tests/test_gpu_catch_dropin.py.)"""
+    binary = os.path.join(HERE, "_build", "catch_on_standin")
+    if not os.path.exists(binary):
+        pytest.skip("tests/catch_dropin/_build objects are not there (they need /root/reference at build time)")
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES"):
+        env.pop(k, None)
+    trials = 400
+    env.update(DFSA_NP=str(nodes), DFSA_CATCH_TRIALS=str(trials))
+    proc = subprocess.Popen([binary], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=280)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("catch_on_standin hung at %d ranks:\n%s" % (nodes, (out + err)[-3000:]))
+    assert proc.returncode == 0, (out + err)[-3000:]
+    m = re.search(r"All tests passed \((\d+) assertions? in (\d+) test cases?\)", out)
+    assert m and int(m.group(2)) == 20 and int(m.group(1)) == 21 * trials, out[-2000:]
+
+
 def test_the_stand_in_is_not_part_of_the_product():
     """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
     for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):
