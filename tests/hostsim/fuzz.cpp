@@ -139,7 +139,7 @@ void svOps(Rng& rng, StateVector& psi, AmpArray& truth, Nat n, Nat numOps, Stats
         if (kind == 10) {
             // a burst of one-target gates (what the gate queue and its swap-in planning are for): either a sweep over consecutive
             // qubits starting anywhere, or random targets; each gate with 0-3 controls
-            const Nat count = rng.between(3, 40), start = rng.below(n);
+            const Nat count = rng.below(25) == 0 ? rng.between(250, 600) : rng.between(3, 40), start = rng.below(n);      // (now and then past the queue's 256-gate limit)
             const bool sweep = rng.below(2) == 0;
             log += sweep ? " sweep(" + std::to_string(start) + "x" + std::to_string(count) + ")" : " burst(" + std::to_string(count) + ")";
             for (Nat b = 0; b < count; b++) {
