@@ -298,6 +298,48 @@ def ncu_traffic():
         return None
 
 
+def parse_cpulist(text):
+    """'0-31,64-95' -> {0, ..., 31, 64, ..., 95} (the format of /sys/devices/system/node/nodeN/cpulist)"""
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-GPU runs: put this rank's host threads -- and with them the pinned buffer of the end-to-end leg, which the kernel
+    places on the node of the thread that allocates it -- on the NUMA node its GPU hangs off (what `numactl` does for a launcher
+    that knows the topology; torchrun does not). Without it a rank may sit on the other socket and every host<->device copy
+    crosses the socket interconnect, which several ranks then share. Best effort, never raises; the outcome goes into the line."""
+    try:
+        sel = str(local_rank)
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        if visible:
+            ids = [x.strip() for x in visible.split(",") if x.strip()]
+            if local_rank < len(ids):
+                sel = ids[local_rank]                       # nvidia-smi -i takes physical indices or UUIDs
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", sel], capture_output=True, text=True, timeout=60).stdout
+        bus = out.strip().splitlines()[0].strip().lower()     # "00000000:1b:00.0": sysfs uses a 4-digit domain
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"bound": False, "why": "the platform reports no NUMA node for %s" % bus}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = parse_cpulist(f.read())
+        target = cpus & os.sched_getaffinity(0)
+        if not target:
+            return {"bound": False, "why": "no allowed CPU on node %d" % node}
+        os.sched_setaffinity(0, target)
+        return {"bound": True, "node": node, "cpus": len(target), "gpu": bus}
+    except Exception as e:                                   # noqa: BLE001 -- placement is an optimisation, not a requirement
+        return {"bound": False, "why": repr(e)[:200]}
+
+
 def gates_equiv(num_gates, num_qubits, seconds):
     return num_gates * (2.0 ** (num_qubits - 34)) / seconds
 
@@ -388,6 +430,8 @@ class Job:
         self.world, self.rank, self.local_rank = world, rank, local_rank
         self.k = world.bit_length() - 1
         self.torch = self.dist = None
+        # host placement (multi-GPU only: at one rank the same process later times the CPU reference on all cores)
+        self.numa = bind_to_gpu_numa_node(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
         if world > 1:
             import torch                                  # load torch's NCCL before ours; torch.distributed = plumbing only
             import torch.distributed as dist
@@ -909,7 +953,8 @@ def run_product(args, world, rank, local_rank):
                        "parallelism": "%d-way state sharding (top %d qubits = rank)" % (world, k), "transport": lib.dfsa_comm_transport().decode(),
                        "exchange": {0: "staged", 1: "fused, host-synchronised", 2: "fused, stream-ordered"}[lib.dfsa_comm_fused_active()] if world > 1 else "none",
                        "gate_fusion": "one-target gates deferred and applied in shared passes over HBM (DFSA_FUSE_GATES=0 turns it off)" if fusion else "off",
-                       "l2": "inputs >> L2 (every gate streams the whole %d GiB shard)" % (shard_bytes >> 30)},
+                       "l2": "inputs >> L2 (every gate streams the whole %d GiB shard)" % (shard_bytes >> 30),
+                       "host_numa_binding": getattr(job, "numa", None)},
             "gates_per_s_actual": len(ops) / (step_ms * 1e-3),
             "amp_updates_per_s": len(ops) * float(1 << nq) / (step_ms * 1e-3),
             "gate_fusion": fusion, "step_roofline": step_roofline, "roofline": roofline, "per_gate_mode": per_gate_mode,

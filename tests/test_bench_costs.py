@@ -71,3 +71,15 @@ def test_fused_step_accounting_is_a_pure_function_of_the_flush_plan():
     assert out["error"] and out["passes"] == [] and out["relocation_pairs"] == []
     out = bench.fused_accounting(None, [("sv_oneTargGate", 0, None), ("sv_manyCtrlOneTargGate", [1, 2], 0, None)], Lib, 32, lambda rc: None)
     assert out["pairs"] == A / 2 + A / 8 and out["error"] is None
+
+
+def test_numa_binding_helper_is_best_effort():
+    assert bench.parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and bench.parse_cpulist("") == set()
+    import os
+    before = os.sched_getaffinity(0)
+    res = bench.bind_to_gpu_numa_node(0)                 # no nvidia-smi / no GPU here: reports why, changes nothing, raises nothing
+    assert isinstance(res, dict) and "bound" in res
+    if not res["bound"]:
+        assert os.sched_getaffinity(0) == before and res["why"]
+    else:
+        os.sched_setaffinity(0, before)
