@@ -65,4 +65,15 @@ case $MODE in
     DFSA_REMOTE_INFLIGHT=${BEST_INFLIGHT:-8192} timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29578 tools/link_sweep.py \
         2> $OUT/${TAG}_link_sweep_n${NP}.err | grep '^{' > $OUT/${TAG}_link_sweep_n${NP}.jsonl; cat $OUT/${TAG}_link_sweep_n${NP}.jsonl
     ;;
+  next)
+    # FIRST thing to run in the next GPU session: what was written after the round-2 GPU budget was spent --
+    # the grouped swap-in of rank-bit qubits (multi-pair relocation in the default-mode sweep), the staggered multi-pair gather,
+    # the NUMA binding of the end-to-end leg. NP = 4 or 8.
+    NP=${NP:-8}
+    timeout 500 python -m pytest tests -m gpu -q --durations=8 -k "fused or relocation or lazy or multi_rank_circuit" > $OUT/${TAG}_pytest_next_n${NP}.log 2>&1; tail -n 8 $OUT/${TAG}_pytest_next_n${NP}.log
+    timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29579 bench.py --gpus $NP --steps 5 --warmup 3 \
+        > $OUT/${TAG}_bench_n${NP}.json 2> $OUT/${TAG}_bench_n${NP}.err; echo "bench rc=$?"; grep -v "^\[" $OUT/${TAG}_bench_n${NP}.err | tail -n 5; cat $OUT/${TAG}_bench_n${NP}.json
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29580 tools/link_sweep.py \
+        2> $OUT/${TAG}_link_sweep_n${NP}.err | grep '^{' > $OUT/${TAG}_link_sweep_n${NP}.jsonl; cat $OUT/${TAG}_link_sweep_n${NP}.jsonl
+    ;;
 esac

@@ -26,6 +26,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     job = bench.Job(world, rank, int(os.environ.get("LOCAL_RANK", "0")))
     assert world > 1, "needs at least 2 GPUs"
+    job.dfsa.set_gate_fusion(False)       # what is measured here are the exchange kernels of single gates: nothing may stay queued
     k = job.k
     nq = int(sys.argv[1]) if len(sys.argv) > 1 else 30 + k
     rng = np.random.default_rng(1)
@@ -76,6 +77,13 @@ def main():
     t_many = timed(many)
     t_local = timed(lambda: st.sv_manyTargGate([20, 0, 9, 13, 21], g32))
     add("manyTargGate 1 prefix target: 2 relocations (2 x 8A) [local gate %.2f ms subtracted]" % t_local, t_many - t_local, 16.0 * A)
+    # several rank bits at once: ONE gather pass over the 2^m shards of the group, (1 - 2^-m) * 16A bytes per direction each way
+    # (also what the gate queue's launch plan uses to bring m rank-bit qubits into the shard together)
+    for m in range(2, k + 1):
+        def many_m():
+            st.sv_manyTargGate([nq - 1 - i for i in range(m)] + [0, 9, 13, 21][: 5 - m], g32)
+            st.restore_layout()
+        add("manyTargGate %d prefix targets: 2 relocations of %d pairs (2 x %.0fA) [local gate subtracted]" % (m, m, (1 - 0.5 ** m) * 16), timed(many_m) - t_local, 2 * (1 - 0.5 ** m) * 16.0 * A)
     st.close()
 
     N = (nq + k) // 2 if (nq + k) % 2 == 0 else (nq + k - 1) // 2
