@@ -33,13 +33,14 @@ for name in cases.SV_OPS:
 if P > 1:
     top = nq - 1
     g = cases.random_matrix(rng, 2) / 1.5
-    # one-target gates on a rank-bit qubit: queued and swapped into the shard by the flush (default), then -- with the queue off -- through
-    # the fused combine and the fused sub-cube combine + unpack
-    st.sv_oneTargGate(top, g); st.sv_manyCtrlOneTargGate([1, 4], top, g); st.sv_oneTargGate(top - 1 if k >= 2 else 0, g); st.flush()
+    # one-target gates on a rank-bit qubit: with the queue off through the fused combine and the fused sub-cube combine + unpack (the
+    # layout is still the identity here), then (default) queued and swapped into the shard by the flush
+    st.restore_layout()
     dfsa.set_gate_fusion(False)
     st.sv_oneTargGate(top, g)
     st.sv_manyCtrlOneTargGate([1, 4], top, g)
     dfsa.set_gate_fusion(True)
+    st.sv_oneTargGate(top, g); st.sv_manyCtrlOneTargGate([1, 4], top, g); st.sv_oneTargGate(top - 1 if k >= 2 else 0, g); st.flush()
     st.sv_pauliGadget([top, 0, 3], [2, 3, 1], 0.4)                       # fused Pauli combine
     st.sv_pauliTensor([top, 2], [1, 2])
     st.sv_swapGate(top, 2); st.sv_swapGate(top, L - 1)                   # fused suffix<->prefix swap
