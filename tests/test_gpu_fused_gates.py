@@ -93,6 +93,9 @@ def test_comm_synch_launches_pending_gates(dfsa):
     st.sv_oneTargGate(3, np.eye(2))
     st.sv_manyCtrlOneTargGate([1], 5, np.eye(2))
     assert st.pending_gates() == 2
+    # what the flush will do (host/layout.hpp planFlush through the C API): one run of both gates, on their own index bits
+    steps, layout_after = st.plan_pending_flush()
+    assert steps == [("gates", [(3, 0), (5, 1 << 1)])] and layout_after == list(range(14))
     dfsa.comm_synch()
     assert st.pending_gates() == 0
     st.close()
