@@ -146,6 +146,13 @@ inline void StateVector::noteSwapped(Nat posA, Nat posB) { dfsa_detail::relabel(
 //     -- circuits are mostly layers that visit the qubits in the same order again and again, so the most recent target is the
 //     one whose next turn is furthest away. bench.py's sweep pays one log2(P)-pair relocation per layer.
 namespace dfsa_detail {
+// DFSA_GROUP_SWAPIN=0: one (suffix, rank) pair per relocation step, as before the queue was planned as a whole (for A/B timing)
+inline Nat maxSwapInPairs() {
+    static int pairs = -1;
+    if (pairs < 0) { const char* e = std::getenv("DFSA_GROUP_SWAPIN"); pairs = (e && std::atoi(e) == 0) ? 1 : 4; }
+    return Nat(pairs);
+}
+
 struct FlushStep {
     bool relocation = false;
     NatArray landing, prefix;              // relocation: (suffix bit, rank bit) index-bit pairs of one dfsa_xk_relocate call
@@ -178,7 +185,7 @@ inline std::vector<FlushStep> planFlush(NatArray where, Nat L, const std::vector
         });
         FlushStep reloc;
         reloc.relocation = true;
-        for (std::size_t w = 0; w < wanted.size() && w < victims.size() && w < 4; w++) {
+        for (std::size_t w = 0; w < wanted.size() && w < victims.size() && w < maxSwapInPairs(); w++) {
             if (w > 0 && !(nextUse[victims[w]] > nextUse[wanted[w]])) break;      // it would evict a qubit that is needed sooner
             reloc.landing.push_back(where[victims[w]]);
             reloc.prefix.push_back(where[wanted[w]]);

@@ -153,6 +153,23 @@ def test_reference_catch2_cases_pass_on_the_host_layer_over_the_stand_in(fuzz_bi
     assert m and int(m.group(2)) == 20 and int(m.group(1)) == 21 * trials, out[-2000:]
 
 
+@pytest.mark.parametrize("nodes", [4, 16])
+def test_random_circuits_with_rank_bit_qubits_brought_in_one_pair_at_a_time(fuzz_binary, nodes):
+    """DFSA_GROUP_SWAPIN=0: the gate queue's launch plan with one (suffix, rank) pair per relocation step (the A/B switch)."""
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES"):
+        env.pop(k, None)
+    env.update(DFSA_NP=str(nodes), DFSA_GROUP_SWAPIN="0")
+    proc = subprocess.Popen([fuzz_binary, "250", "9"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("hostsim fuzz hung at %d ranks:\n%s" % (nodes, err[-3000:]))
+    assert proc.returncode == 0 and "failures=0" in out, (out + err)[-3000:]
+
+
 def test_the_stand_in_is_not_part_of_the_product():
     """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
     for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):

@@ -73,6 +73,9 @@ case $MODE in
     timeout 500 python -m pytest tests -m gpu -q --durations=8 -k "fused or relocation or lazy or multi_rank_circuit" > $OUT/${TAG}_pytest_next_n${NP}.log 2>&1; tail -n 8 $OUT/${TAG}_pytest_next_n${NP}.log
     timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29579 bench.py --gpus $NP --steps 5 --warmup 3 \
         > $OUT/${TAG}_bench_n${NP}.json 2> $OUT/${TAG}_bench_n${NP}.err; echo "bench rc=$?"; grep -v "^\[" $OUT/${TAG}_bench_n${NP}.err | tail -n 5; cat $OUT/${TAG}_bench_n${NP}.json
+    # A/B: rank-bit qubits brought in one pair per relocation step (the version measured in round 2)
+    DFSA_GROUP_SWAPIN=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29581 bench.py --gpus $NP --steps 5 --warmup 3 \
+        --skip-configs --skip-parity > $OUT/${TAG}_bench_n${NP}_single_swapin.json 2> $OUT/${TAG}_bench_n${NP}_single_swapin.err; echo "bench (single swap-in) rc=$?"; cat $OUT/${TAG}_bench_n${NP}_single_swapin.json
     timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NP --master-addr 127.0.0.1 --master-port 29580 tools/link_sweep.py \
         2> $OUT/${TAG}_link_sweep_n${NP}.err | grep '^{' > $OUT/${TAG}_link_sweep_n${NP}.jsonl; cat $OUT/${TAG}_link_sweep_n${NP}.jsonl
     ;;
