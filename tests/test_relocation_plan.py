@@ -54,3 +54,34 @@ def test_gather_equals_the_sequence_of_swaps(log_nodes):
                 for sigma in range(1 << k):
                     theirs, their_rho = plan(owners[sigma], L, prefix)
                     assert their_rho == sigma and theirs[rho] == rank
+
+
+@pytest.mark.parametrize("log_nodes", [2, 3, 4])
+def test_staggered_walk_is_a_bijection_and_a_perfect_matching_at_every_step(log_nodes):
+    """The gather kernel (csrc/dfsa_kernels_sv.cu dfsaLaunchRelocate) takes item jj as output index j = jj ^ rhoBits, so that every
+    rank starts with its own shard: all ranks sweep jj in the same order at about the same speed, and at the same jj the ranks of
+    a group must read from pairwise DIFFERENT owners (each owner's NVLink egress serves one reader at a time) -- and the items
+    must still cover every output index exactly once."""
+    rng = np.random.default_rng(40 + log_nodes)
+    L, P = 5, 1 << log_nodes
+    n = L + log_nodes
+    for k in range(2, log_nodes + 1):
+        for _ in range(4):
+            prefix = [int(x) for x in rng.permutation(np.arange(L, n))[:k]]
+            landing = [int(x) for x in rng.permutation(L)[:k]]
+            group_mask = sum(1 << (p - L) for p in prefix)
+            readers = {}                                   # (group id, jj) -> owners read at that item by the ranks of the group
+            for rank in range(P):
+                owners, rho = plan(rank, L, prefix)
+                rho_bits = sum(((rho >> i) & 1) << landing[i] for i in range(k))
+                outputs = set()
+                for jj in range(1 << L):
+                    j = jj ^ rho_bits
+                    outputs.add(j)
+                    sigma = sum(((j >> landing[i]) & 1) << i for i in range(k))
+                    readers.setdefault((rank & ~group_mask, jj), []).append(owners[sigma])
+                    if jj == 0:
+                        assert owners[sigma] == rank     # the walk starts at home
+                assert outputs == set(range(1 << L))
+            for (group, jj), who in readers.items():
+                assert len(who) == 1 << k and len(set(who)) == 1 << k, (prefix, landing, group, jj, who)
