@@ -6,12 +6,15 @@
 // wrong without any kernel being wrong, and they can be exercised without a GPU: this file implements the SEMANTICS each C-ABI
 // entry documents in include/dfsa_b200.h with plain loops over shards that live in a shared-memory arena, one forked process
 // per rank (DFSA_NP, like the real library's fork mode), so that tests/hostsim/fuzz.cpp can run random circuits through the
-// real host headers at 1...16 ranks and compare against a dense ground truth that knows nothing about ranks.
+// real host headers at 1...16 ranks and compare against a dense ground truth that knows nothing about ranks. The same file
+// carries the reference's own Catch2 cases (catch_on_standin), the extern "C" face of the host layer (capi_on_standin.py) and a
+// toy-size dry run of bench.py's control flow (bench_dry_run.py) -- see tests/test_host_layer_fuzz.py.
 //
 // What it is NOT: it is not part of the product, is never built into or loaded by the package (libdfsa_b200.so /
 // libdfsa_host.so), and nothing under distributed-full-state-algorithms_b200/ or bench.py refers to it. The product has no CPU
-// path: without a CUDA device every entry of libdfsa_b200.so fails (tests/test_cabi_symbols.py). Only the fuzz binary of this
-// directory links it. Entries the host layer never calls (staged building blocks) return DFSA_ERR_UNSUPPORTED.
+// path: without a CUDA device every entry of libdfsa_b200.so fails (tests/test_cabi_symbols.py). Only the binaries of this
+// directory (tests/hostsim/_build) link it. Entries the host layer never calls (staged building blocks) and the reference's
+// literal twoQubitDepolarising formulas on the prefix branches (pinned on the GPU by tests/golden) return DFSA_ERR_UNSUPPORTED.
 //
 // Pairwise operations synchronise PAIRWISE (a rank that fails a prefix control never enters them, reference
 // distributed_statevector.hpp:92-93), collective ones with a barrier over all ranks; every wait times out with a message, so a
