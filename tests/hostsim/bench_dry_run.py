@@ -88,8 +88,41 @@ def main():
 
     bench.Job = DryJob
     per_rank = int(sys.argv[1]) if len(sys.argv) > 1 else 13
-    args = types.SimpleNamespace(gpus=world, steps=2, warmup=1, impl="product", qubits=per_rank + world.bit_length() - 1,
-                                 no_cpu_baseline=True, skip_parity=False, skip_configs=True, per_gate=False)
+    with_configs = len(sys.argv) > 2 and sys.argv[2] == "configs"
+    k = world.bit_length() - 1
+    args = types.SimpleNamespace(gpus=world, steps=2, warmup=1, impl="product", qubits=per_rank + k,
+                                 no_cpu_baseline=True, skip_parity=False, skip_configs=not with_configs, per_gate=False)
+    if with_configs:
+        # BASELINE configs 3-5 at toy sizes: the same op mix (bench.config_workload decides the real sizes), so that bench.run_config --
+        # cost model, restore plans, labels, per-op tables -- runs at this rank count
+        import numpy as np
+
+        def toy_workload(name, world_, seed=7, dm_qubits=None):
+            rng = np.random.default_rng(seed)
+            if name == "circuit":
+                nq = 11 + k
+                ops = []
+                for _ in range(6):
+                    ops.append(("sv_manyTargGate", [int(x) for x in rng.permutation(nq)[:5]], bench.haar(rng, 32)))
+                    nt = int(rng.integers(3, 7))
+                    paulis = [int(x) for x in rng.integers(1, 4, size=nt)]
+                    ops.append(("sv_pauliGadget", [int(x) for x in rng.permutation(nq)[:nt]], paulis, float(rng.uniform(-3, 3))))
+                    ops.append(("sv_phaseGadget", [int(x) for x in rng.permutation(nq)[:int(rng.integers(1, 8))]], float(rng.uniform(-3, 3))))
+                return "sv", nq, ops, "toy config 3"
+            N = 6 + (k + 1) // 2
+            if name == "dm":
+                ops = []
+                for q in range(N):
+                    ops.append(("dm_manyTargGate", [q, (q + 1) % N], bench.haar(rng, 4)))
+                    ops.append(("dm_oneQubitDepolarising", q, float(rng.uniform(0, 0.5))))
+                    ops.append(("dm_twoQubitDephasing", q, (q + 1) % N, float(rng.uniform(0, 0.5))))
+                    ops.append(("dm_damping", q, float(rng.uniform(0, 0.5))))
+                return "dm", N, ops, "toy config 4"
+            coeffs = rng.uniform(-10, 10, 16)
+            paulis = rng.integers(0, 4, size=(16, N))
+            return "dm", N, [("dm_expecPauliString", coeffs, paulis)] * 2 + [("dm_partialTrace", [0, 2]), ("dm_partialTrace", [N - 2, N - 1])], "toy config 5"
+
+        bench.config_workload = toy_workload
     # the parity block needs the oracle and every channel of the API: only the full-size self-check part of it is kept
     bench.parity_selfcheck = lambda job: None
     bench.run_product(args, world, rank, rank)

@@ -101,7 +101,7 @@ def test_bench_product_arm_dry_run_on_the_stand_in(fuzz_binary, nodes):
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES"):
         env.pop(k, None)
     env["DFSA_NP"] = str(nodes)
-    proc = subprocess.Popen([sys.executable, os.path.join(HERE, "bench_dry_run.py"), "12"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    proc = subprocess.Popen([sys.executable, os.path.join(HERE, "bench_dry_run.py"), "12", "configs"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
     try:
         out, err = proc.communicate(timeout=240)
     except subprocess.TimeoutExpired:
@@ -124,6 +124,16 @@ def test_bench_product_arm_dry_run_on_the_stand_in(fuzz_binary, nodes):
         assert (len(step) >= 1) == (nodes > 1) and all(1 <= m <= max(k, 1) for m in step)
     assert 0 < roof["frac"] and 0 < line["step_roofline"]["frac"] and line["e2e"]["h2d_bytes_per_step"] == 16 * (1 << (12 + k))
     assert (line["exchange_gates"] is not None) == (nodes > 1)
+    # BASELINE configs 3-5 at toy sizes (same op mix): bench.run_config's cost model, restore plans and per-op tables at this rank count
+    configs = line["configs"]
+    assert "config3_circuit" in configs and any(name.startswith("config4_") for name in configs) and any(name.startswith("config5_") for name in configs)
+    for name, c in configs.items():
+        assert c["roofline_frac"] > 0 and c["per_op"], name
+        labels = " ".join(c["per_op"])
+        if nodes > 1 and name.startswith("config3"):
+            assert "[exchange]" in labels
+        if nodes > 1 and name.startswith("config5"):
+            assert "(relocating)" in labels and "(local)" in labels
 
 
 @pytest.mark.parametrize("nodes", [1, 2, 4, 8, 16])
