@@ -705,7 +705,7 @@ def run_config(job, name, peaks, reps, dm_qubits=None):
                 label = "layout restore (deferred undo of relocations)"
             if op[0] == "dm_partialTrace":
                 label += " (relocating)" if max(op[1]) + nq >= (2 * nq - k) else " (local)"
-            elif any(c[1] > 0 for c in cost) and op[0] != "layout_restore":
+            elif any(c[1] > 0 or (len(c) > 3 and c[3] > 0) for c in cost) and op[0] != "layout_restore":      # NVLink bytes, both ways or one way
                 label += " [exchange]"
             d = per_type.setdefault(label, {"n": 0, "ms": 0.0, "bound_ms": 0.0})
             d["n"] += 1
