@@ -6,9 +6,9 @@ step, fused-pass accounting, per-gate mode, end-to-end leg, the JSON line) canno
 NUMBERS of this run mean nothing (host time stamps instead of CUDA events, plain loops instead of kernels) and it is never
 reported anywhere; what the test checks is that the line is produced and has the shape the contract asks for.
 
-How: THIS script (not the product) points api.py's cached library handles at tests/hostsim/_build/libdfsa_host_on_standin.so;
-the host-only planners (dfsa_plan_*) still come from the real libdfsa_b200.so, which loads without a GPU. The product itself has
-no switch that would let it run on anything but the CUDA library.
+How: standin_env.install() (this directory, not the product) points api.py's cached library handles at
+tests/hostsim/_build/libdfsa_host_on_standin.so; the host-only planners (dfsa_plan_*) still come from the real libdfsa_b200.so, which
+loads without a GPU. The product itself has no switch that would let it run on anything but the CUDA library.
 
     [DFSA_NP=4] python tests/hostsim/bench_dry_run.py [qubits-per-rank=13]     -> the JSON line on stdout (rank 0)
 """
@@ -22,43 +22,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-PKG = "distributed-full-state-algorithms_b200"
-
-
-class DeviceLibOnStandIn:
-    """attribute access like a ctypes.CDLL: host-only planners from the real library, everything else from the stand-in"""
-
-    def __init__(self, standin, real):
-        self._standin, self._real = standin, real
-
-    def __getattr__(self, name):
-        return getattr(self._real if name.startswith("dfsa_plan_") else self._standin, name)
+sys.path.insert(0, HERE)
 
 
 def main():
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
-        os.environ.pop(k, None)
-    api = importlib.import_module(PKG + ".api")
-    standin = C.CDLL(os.path.join(HERE, "_build", "libdfsa_host_on_standin.so"), mode=C.RTLD_GLOBAL)
-    real = C.CDLL(os.path.join(ROOT, PKG, "libdfsa_b200.so"))
-    # the restypes api.device_lib() / api.host_lib() set on the real libraries
-    standin.dfsa_last_error.restype = C.c_char_p
-    standin.dfsa_version.restype = C.c_char_p
-    standin.dfsa_comm_transport.restype = C.c_char_p
-    standin.dfsa_stream_compute.restype = C.c_void_p
-    standin.dfsa_state_ptr.restype = C.c_void_p
-    standin.dfsa_state_ptr.argtypes = [C.c_void_p, C.c_int]
-    standin.dfsa_state_num_amps_per_node.restype = C.c_uint64
-    standin.dfsa_state_num_amps_per_node.argtypes = [C.c_void_p]
-    standin.dfsa_launch_count.restype = C.c_uint64
-    for name in ("dfsa_host_StateVector_new", "dfsa_host_DensityMatrix_new", "dfsa_host_dm_partialTrace", "dfsa_host_state_handle"):
-        getattr(standin, name).restype = C.c_void_p
-    standin.dfsa_host_state_numAmpsPerNode.restype = C.c_uint64
-    standin.dfsa_host_state_getNorm2.restype = C.c_double
-    standin.dfsa_host_comm_getRank.restype = C.c_uint
-    standin.dfsa_host_comm_getNumNodes.restype = C.c_uint
-    api._dev = DeviceLibOnStandIn(standin, real)
-    api._host = standin
+    import standin_env
+    api, standin = standin_env.install()
+    PKG = standin_env.PKG
     import bench
     api.comm_init()                                        # the stand-in forks the ranks here: from now on every rank runs this script
     world, rank = api.comm_size(), api.comm_rank()

@@ -146,6 +146,7 @@ inline Amp hashAmp(uint64_t seed, uint64_t globalIndex) {
     return Amp(double(z >> 40) / double(1 << 24) - 0.5, double((z >> 16) & 0xFFFFFF) / double(1 << 24) - 0.5);
 }
 inline int parity(uint64_t x) { return __builtin_parityll(x); }
+unsigned long long g_remoteAmps = 0;      // amplitudes this rank has read from (or, dfsa_x_exchange, received from) other ranks' shards
 std::map<std::string, unsigned long long>& callCounts() { static std::map<std::string, unsigned long long> c; return c; }
 inline void touchOp(const char* entry) { if (g.ctl) g.ctl->opCount[g.rank].fetch_add(1); callCounts()[entry]++; }
 #define touchOp() touchOp(__func__)
@@ -156,6 +157,9 @@ extern "C" {
 const char* dfsa_last_error(void) { return g_err; }
 // stand-in only (declared by fuzz.cpp): how often this rank entered a C-ABI function -- lets a test assert that the paths it
 // means to exercise (relocations, swap-ins, exchanges) were actually taken
+// stand-in only: amplitudes this rank has pulled from other ranks so far -- what must cross NVLink in one direction for this rank,
+// whatever the implementation; tests/hostsim/cost_model_check.py holds bench.py's roofline cost model against it
+unsigned long long hostsim_remote_amps(void) { return g_remoteAmps; }
 unsigned long long hostsim_call_count(const char* entry) { auto it = callCounts().find(entry); return it == callCounts().end() ? 0ULL : it->second; }
 const char* dfsa_version(void) { return "hostsim (CPU stand-in for tests; not the product)"; }
 
@@ -394,6 +398,7 @@ int dfsa_x_exchange(dfsa_state* s, int sendWhich, uint64_t sendStart, int recvWh
     std::vector<Amp> out(s->arr(g.rank, sendWhich) + sendStart, s->arr(g.rank, sendWhich) + sendStart + num);
     pairSync(pairRank);                                              // the partner has read what it sends
     memcpy(static_cast<void*>(s->arr(pairRank, recvWhich) + recvStart), out.data(), num * sizeof(Amp));
+    g_remoteAmps += num;                                             // (the partner sends as much as it receives)
     pairSync(pairRank);                                              // what I receive has landed
     return DFSA_OK;
 }
@@ -408,6 +413,7 @@ int dfsa_xk_exchangeCombine(dfsa_state* s, int pairRank, const double f0[2], con
     pairSync(pairRank);
     const Amp *mine = s->amps(), *theirs = s->arr(pairRank, DFSA_AMPS);
     for (uint64_t j = 0; j < s->numAmps; j++) out[j] = amp2(f0) * mine[j] + amp2(f1) * theirs[j];
+    g_remoteAmps += s->numAmps;
     pairSync(pairRank);
     memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
     return DFSA_OK;
@@ -423,7 +429,7 @@ int dfsa_xk_ctrlPrefixTarg(dfsa_state* s, const uint32_t* suffixCtrls, unsigned 
     pairSync(pairRank);
     const Amp *mine = s->amps(), *theirs = s->arr(pairRank, DFSA_AMPS);
     for (uint64_t j = 0; j < s->numAmps; j++)
-        if ((j & mask) == mask) out[j] = amp2(f0) * mine[j] + amp2(f1) * theirs[j];
+        if ((j & mask) == mask) { out[j] = amp2(f0) * mine[j] + amp2(f1) * theirs[j]; g_remoteAmps++; }
     pairSync(pairRank);
     memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
     return DFSA_OK;
@@ -437,6 +443,7 @@ int dfsa_xk_swapSuffixPrefix(dfsa_state* s, unsigned qb1, unsigned movingBit, in
     pairSync(pairRank);
     const Amp *mine = s->amps(), *theirs = s->arr(pairRank, DFSA_AMPS);
     for (uint64_t j = 0; j < s->numAmps; j++) out[j] = (((j >> qb1) & 1ULL) != movingBit) ? mine[j] : theirs[j ^ (1ULL << qb1)];
+    g_remoteAmps += s->numAmps / 2;
     pairSync(pairRank);
     memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
     return DFSA_OK;
@@ -464,6 +471,7 @@ int dfsa_xk_relocate(dfsa_state* s, const uint32_t* suffixQubits, const uint32_t
             if (a != b) src ^= (1ULL << suffixQubits[i]) | (1ULL << prefixQubits[i]);
         }
         out[j] = s->arr(int(src >> L), DFSA_AMPS)[src & (s->numAmps - 1)];
+        g_remoteAmps += int(src >> L) != g.rank;
     }
     barrierAll();
     memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
@@ -483,6 +491,7 @@ int dfsa_xk_exchangePauliCombine(dfsa_state* s, int pairRank, uint64_t maskXY, u
         const uint64_t j1 = j0 ^ maskXY, global1 = (uint64_t(pairRank) << s->logNumAmps) | j1;
         const Amp b = powI[numY & 3u] * (parity(global1 & maskYZ) ? -1.0 : 1.0);
         out[j0] = amp2(f) * mine[j0] + amp2(gg) * b * theirs[j1];
+        g_remoteAmps++;
     }
     pairSync(pairRank);
     memcpy(static_cast<void*>(s->amps()), out.data(), s->numAmps * sizeof(Amp));
@@ -658,7 +667,10 @@ int dfsa_k_partialTrace(dfsa_state* in, dfsa_state* out, const uint32_t* targets
 // ---- the remaining channels and the expectation value, written against the GLOBAL Choi index (flat = 2^N col + row; bit q = ket bit
 // of qubit q, bit q + N = its bra bit) wherever the amplitude lives: an entry that needs other ranks' amplitudes reads them from the
 // arena between two barriers over all ranks (every rank makes these calls: the host layer never skips a rank for a channel).
-static Amp globalAmp(const dfsa_state* s, uint64_t i) { return s->arr(int(i >> s->logNumAmps), DFSA_AMPS)[i & (s->numAmps - 1)]; }
+static Amp globalAmp(const dfsa_state* s, uint64_t i) {
+    g_remoteAmps += int(i >> s->logNumAmps) != g.rank;
+    return s->arr(int(i >> s->logNumAmps), DFSA_AMPS)[i & (s->numAmps - 1)];
+}
 
 template <class F>      // f(global index) -> new amplitude, from the OLD global state
 static int channelFromGlobal(dfsa_state* s, bool collective, F f) {

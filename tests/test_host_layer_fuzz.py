@@ -180,6 +180,29 @@ def test_random_circuits_with_rank_bit_qubits_brought_in_one_pair_at_a_time(fuzz
     assert proc.returncode == 0 and "failures=0" in out, (out + err)[-3000:]
 
 
+@pytest.mark.parametrize("nodes", [2, 4, 8, 16])
+def test_bench_nvlink_cost_model_equals_what_the_stand_in_pulls_over_the_link(fuzz_binary, nodes):
+    """Every roofline fraction of the bench line divides an algorithmic cost by a time; the NVLink part of that cost (bench.op_cost,
+    restore_cost, relocation_cost, the fused-step accounting) is held against the stand-in's own count of the amplitudes each rank
+    pulls from other ranks, op by op, for the op mix of BASELINE configs 3-5, layout restores and the sweep in both modes --
+    tests/hostsim/cost_model_check.py."""
+    import sys
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "DFSA_LAZY_LAYOUT", "DFSA_FUSE_GATES", "DFSA_GROUP_SWAPIN"):
+        env.pop(k, None)
+    env["DFSA_NP"] = str(nodes)
+    proc = subprocess.Popen([sys.executable, os.path.join(HERE, "cost_model_check.py")], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=240)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        pytest.fail("cost_model_check.py hung at %d ranks:\n%s" % (nodes, err[-3000:]))
+    assert proc.returncode == 0, (out + err)[-3000:]
+    m = re.search(r"cost model check: ok at (\d+) rank\(s\), (\d+) ops compared, (\d+) of them with NVLink traffic", out)
+    assert m and int(m.group(1)) == nodes and int(m.group(2)) >= 100 and int(m.group(3)) >= 30, out[-2000:]
+
+
 def test_the_stand_in_is_not_part_of_the_product():
     """Nothing under the package, include/ or bench.py names the stand-in, and the product's host library links libdfsa_b200."""
     for base, _, files in os.walk(os.path.join(product.ROOT, "distributed-full-state-algorithms_b200")):
