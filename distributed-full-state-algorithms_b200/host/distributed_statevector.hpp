@@ -2,8 +2,9 @@
 // Entry points, signatures and semantics follow the reference's src/distributed_statevector.hpp
 // (:18 oneTargGate, :81 manyCtrlOneTargGate, :109 swapGate, :190 manyTargGate, :279 pauliTensor,
 // :287 pauliGadget, :295 phaseGadget). What stays on the host is only the decision "local kernel or
-// pairwise exchange" (qubit index vs. logNumAmpsPerNode) and the relocation planning; every loop over
-// amplitudes is a CUDA kernel and every exchange an NCCL/NVLink transfer behind the C-ABI.
+// pairwise exchange" (qubit index vs. logNumAmpsPerNode), the relocation planning, the lazy qubit layout and
+// the launch plan of the deferred one-target gates (layout.hpp); every loop over amplitudes is a CUDA kernel
+// and every exchange an NCCL/NVLink transfer behind the C-ABI.
 #pragma once
 
 #include <algorithm>

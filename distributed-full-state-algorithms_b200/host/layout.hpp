@@ -10,6 +10,8 @@
 // before anything that looks at amplitudes by index: downloads, comparisons, the density-matrix channels, expecPauliString,
 // partialTrace -- so results, including the mutated input of partialTrace, are what the reference produces.
 // DFSA_LAZY_LAYOUT=0 turns the laziness off (relocations are undone at once, as in the reference).
+// The second half of this file is the launch plan of the deferred one-target gates (states.hpp gateQueue): with a layout that
+// may change, a gate on a rank-bit qubit brings its qubit into the shard instead of exchanging whole shards (planFlush).
 //
 // Included at the bottom of states.hpp; uses only the C-ABI.
 #pragma once
